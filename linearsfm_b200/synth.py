@@ -1,0 +1,232 @@
+"""Synthetic local-map generator (SURVEY.md section 8(d) "Concrete inputs").
+
+The reference ships no datasets (DataForC/* hold Drive links only), so every test and bench input
+is a seeded synthetic scene written in the reference's own local-map format.  Geometry follows the
+reference's conventions (LinearSFMImp.cpp:132-143, 449-451): a pose is (t, alpha, beta, gamma),
+R = Rx(gamma) Ry(beta) Rz(alpha) in the passive sense and a point maps as X_local = R (X - t).
+
+Stereo scene ("NC-shape"): N+1 stereo frames on a smooth path; map k (1-based) is built from frames
+(k, k+1): Ref = k, state = pose k+1 (6) + every landmark seen in both frames (3 each), all in the
+frame of pose k; information = sum J' Sigma^-1 J of the 6 stereo measurements per landmark, i.e.
+exactly the (U, W, V) a two-view bundle adjustment would hand to LinearSFM; the estimate is the
+truth plus one Gauss-Newton-consistent draw of the measurement noise.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .localmap import LocalMap
+
+SEED0 = 20150328
+
+
+def rot_ypr(a, b, g):
+    """R(alpha, beta, gamma), row-major 3x3 (LinearSFMImp.cpp:132-143). Vectorised: [...,3,3]."""
+    a, b, g = np.asarray(a, float), np.asarray(b, float), np.asarray(g, float)
+    ca, sa, cb, sb, cg, sg = np.cos(a), np.sin(a), np.cos(b), np.sin(b), np.cos(g), np.sin(g)
+    R = np.empty(a.shape + (3, 3))
+    R[..., 0, 0] = cb * ca
+    R[..., 0, 1] = cb * sa
+    R[..., 0, 2] = -sb
+    R[..., 1, 0] = sg * sb * ca - cg * sa
+    R[..., 1, 1] = sg * sb * sa + cg * ca
+    R[..., 1, 2] = sg * cb
+    R[..., 2, 0] = cg * sb * ca + sg * sa
+    R[..., 2, 1] = cg * sb * sa - sg * ca
+    R[..., 2, 2] = cg * cb
+    return R
+
+
+def drot_ypr(a, b, g):
+    """(dR/dalpha, dR/dbeta, dR/dgamma) of rot_ypr."""
+    a, b, g = np.asarray(a, float), np.asarray(b, float), np.asarray(g, float)
+    ca, sa, cb, sb, cg, sg = np.cos(a), np.sin(a), np.cos(b), np.sin(b), np.cos(g), np.sin(g)
+    z = np.zeros_like(ca)
+    dA = np.stack([
+        np.stack([-cb * sa, cb * ca, z], -1),
+        np.stack([-sg * sb * sa - cg * ca, sg * sb * ca - cg * sa, z], -1),
+        np.stack([-cg * sb * sa + sg * ca, cg * sb * ca + sg * sa, z], -1)], -2)
+    dB = np.stack([
+        np.stack([-sb * ca, -sb * sa, -cb], -1),
+        np.stack([sg * cb * ca, sg * cb * sa, -sg * sb], -1),
+        np.stack([cg * cb * ca, cg * cb * sa, -cg * sb], -1)], -2)
+    dG = np.stack([
+        np.stack([z, z, z], -1),
+        np.stack([cg * sb * ca + sg * sa, cg * sb * sa - sg * ca, cg * cb], -1),
+        np.stack([-sg * sb * ca + cg * sa, -sg * sb * sa - cg * ca, -sg * cb], -1)], -2)
+    return dA, dB, dG
+
+
+def ypr_from_rot(R):
+    """Inverse of rot_ypr away from gimbal lock (LinearSFMImp.cpp:162-177)."""
+    beta = np.arctan2(-R[..., 0, 2], np.sqrt(R[..., 0, 0] ** 2 + R[..., 0, 1] ** 2))
+    cb = np.cos(beta)
+    alpha = np.arctan2(R[..., 0, 1] / cb, R[..., 0, 0] / cb)
+    gamma = np.arctan2(R[..., 1, 2] / cb, R[..., 2, 2] / cb)
+    return alpha, beta, gamma
+
+
+class StereoCam:
+    """Pinhole stereo rig in the pose's local frame: x forward, y left, z up; the right camera sits
+    at y = -baseline."""
+
+    def __init__(self, f=400.0, baseline=0.12, cx=256.0, cy=192.0, sigma=0.5):
+        self.f, self.b, self.cx, self.cy, self.sigma = f, baseline, cx, cy, sigma
+
+    def project(self, Xc):
+        x, y, z = Xc[..., 0], Xc[..., 1], Xc[..., 2]
+        return np.stack([self.cx - self.f * y / x, self.cy - self.f * z / x,
+                         self.cx - self.f * (y + self.b) / x], -1)
+
+    def jac(self, Xc):
+        x, y, z = Xc[..., 0], Xc[..., 1], Xc[..., 2]
+        f, b = self.f, self.b
+        J = np.zeros(Xc.shape[:-1] + (3, 3))
+        J[..., 0, 0] = f * y / x ** 2
+        J[..., 0, 1] = -f / x
+        J[..., 1, 0] = f * z / x ** 2
+        J[..., 1, 2] = -f / x
+        J[..., 2, 0] = f * (y + b) / x ** 2
+        J[..., 2, 1] = -f / x
+        return J
+
+
+def make_trajectory(nframes: int, rng: np.random.Generator):
+    """World poses of the frames: position p[j] and angles (alpha, beta, gamma)[j]."""
+    step = rng.uniform(0.3, 0.5, nframes)
+    # smooth yaw rate: low-pass filtered noise, clipped to 5 deg / frame
+    w = rng.normal(0.0, 1.0, nframes)
+    k = np.exp(-np.arange(40) / 12.0)
+    yaw_rate = np.convolve(w, k / k.sum(), mode="full")[:nframes]
+    yaw_rate = np.clip(yaw_rate * np.deg2rad(6.0), -np.deg2rad(5.0), np.deg2rad(5.0))
+    yaw = np.cumsum(yaw_rate)
+    pitch = np.deg2rad(2.0) * np.sin(np.arange(nframes) * 0.11 + rng.uniform(0, 6.28))
+    roll = np.deg2rad(1.5) * np.sin(np.arange(nframes) * 0.07 + rng.uniform(0, 6.28))
+    ang = np.stack([yaw, pitch, roll], -1)
+    R = rot_ypr(yaw, pitch, roll)
+    fwd = R[:, 0, :]                           # local x axis expressed in world = first row of R
+    p = np.zeros((nframes, 3))
+    p[1:] = np.cumsum(fwd[:-1] * step[:-1, None], axis=0)
+    p[:, 2] += 0.05 * np.sin(np.arange(nframes) * 0.05)
+    return p, ang, R
+
+
+def make_stereo_scene(num_maps: int, feats_per_frame: int = 128, seed: int = SEED0,
+                      min_life: int = 2, max_life: int = 6, cam: StereoCam | None = None,
+                      return_truth: bool = False):
+    """Generate `num_maps` consistent stereo local maps. Returns a list of LocalMap (views into
+    flat arrays) and, optionally, the ground truth dict."""
+    cam = cam or StereoCam()
+    rng = np.random.default_rng(np.random.PCG64(seed))
+    N = int(num_maps)
+    nf = N + 1
+    p, ang, Rw = make_trajectory(nf, rng)           # frame j (0-based) has pose id j+1
+
+    # landmarks: spawned in frame j's frustum, tracked for `life` consecutive frames
+    L_total = nf * feats_per_frame
+    start = np.repeat(np.arange(nf), feats_per_frame)
+    life = rng.integers(min_life, max_life + 1, L_total)
+    end = np.minimum(start + life - 1, nf - 1)          # last frame (inclusive)
+    depth = rng.uniform(4.0, 30.0, L_total)
+    th = rng.uniform(-np.deg2rad(28.0), np.deg2rad(28.0), L_total)
+    tv = rng.uniform(-np.deg2rad(20.0), np.deg2rad(20.0), L_total)
+    Xl = np.stack([depth, depth * np.tan(th), depth * np.tan(tv)], -1)
+    Xw = np.einsum("nji,nj->ni", Rw[start], Xl) + p[start]   # R^T Xl + p
+    gid = np.arange(1, L_total + 1, dtype=np.int64)
+
+    # (map k, landmark) rows: landmark belongs to maps k (0-based frame index of Ref) in [start, end-1]
+    nmaps_of = np.maximum(end - start, 0)
+    rows_l = np.repeat(np.arange(L_total), nmaps_of)
+    offs = np.arange(nmaps_of.sum()) - np.repeat(np.cumsum(nmaps_of) - nmaps_of, nmaps_of)
+    rows_k = start[rows_l] + offs
+    keep = rows_k < N
+    rows_l, rows_k = rows_l[keep], rows_k[keep]
+    order = np.lexsort((gid[rows_l], rows_k))
+    rows_l, rows_k = rows_l[order], rows_k[order]
+    T = rows_k.shape[0]
+    n_of_map = np.bincount(rows_k, minlength=N)
+    foff = np.concatenate([[0], np.cumsum(n_of_map)])
+    if np.any(n_of_map == 0):
+        raise ValueError("a local map has no features; increase feats_per_frame")
+
+    # truth: relative pose of frame k+1 in frame k, landmark in frame k
+    Rk, Rk1 = Rw[:N], Rw[1:N + 1]
+    t_rel = np.einsum("kij,kj->ki", Rk, p[1:N + 1] - p[:N])
+    R_rel = np.einsum("kij,klj->kil", Rk1, Rk)
+    a_rel = np.stack(ypr_from_rot(R_rel), -1)
+    X0 = np.einsum("tij,tj->ti", Rk[rows_k], Xw[rows_l] - p[rows_k])      # in frame k
+
+    sig = cam.sigma
+    eps0 = rng.normal(0.0, sig, (T, 3))
+    eps1 = rng.normal(0.0, sig, (T, 3))
+
+    def linearise(t_p, a_p, X):
+        """Jacobians of the two stereo observations of every row at (pose, X)."""
+        R1 = rot_ypr(a_p[:, 0], a_p[:, 1], a_p[:, 2])
+        dA, dB, dG = drot_ypr(a_p[:, 0], a_p[:, 1], a_p[:, 2])
+        R1r, dAr, dBr, dGr = R1[rows_k], dA[rows_k], dB[rows_k], dG[rows_k]
+        d = X - t_p[rows_k]
+        Xc1 = np.einsum("tij,tj->ti", R1r, d)
+        J0 = cam.jac(X)                                   # obs in frame k: d z / d X
+        Jp1 = cam.jac(Xc1)
+        JX1 = np.einsum("tij,tjk->tik", Jp1, R1r)          # d z / d X
+        Jang = np.stack([np.einsum("tij,tj->ti", dAr, d), np.einsum("tij,tj->ti", dBr, d),
+                         np.einsum("tij,tj->ti", dGr, d)], -1)     # [T,3(xyz),3(angles)]
+        JP1 = np.concatenate([-JX1, np.einsum("tij,tjk->tik", Jp1, Jang)], -1)   # [T,3,6]
+        return J0, JX1, JP1, Xc1
+
+    def assemble(J0, JX1, JP1):
+        w = 1.0 / sig ** 2
+        V = w * (np.einsum("tki,tkj->tij", J0, J0) + np.einsum("tki,tkj->tij", JX1, JX1))
+        W = w * np.einsum("tki,tkj->tij", JP1, JX1)                  # [T,6,3]
+        Ub = w * np.einsum("tki,tkj->tij", JP1, JP1)                 # [T,6,6]
+        U = np.add.reduceat(Ub, foff[:-1], axis=0)
+        return U, W, V
+
+    # Gauss-Newton-consistent draw at the truth
+    J0, JX1, JP1, _ = linearise(t_rel, a_rel, X0)
+    U, W, V = assemble(J0, JX1, JP1)
+    w = 1.0 / sig ** 2
+    gF = w * (np.einsum("tki,tk->ti", J0, eps0) + np.einsum("tki,tk->ti", JX1, eps1))
+    gP = np.add.reduceat(w * np.einsum("tki,tk->ti", JP1, eps1), foff[:-1], axis=0)
+    Vi = np.linalg.inv(V)
+    WVi = np.einsum("tij,tjk->tik", W, Vi)
+    S = U - np.add.reduceat(np.einsum("tij,tkj->tik", WVi, W), foff[:-1], axis=0)
+    e = gP - np.add.reduceat(np.einsum("tij,tj->ti", WVi, gF), foff[:-1], axis=0)
+    dP = np.linalg.solve(S, e[..., None])[..., 0]
+    dF = np.einsum("tij,tj->ti", Vi, gF - np.einsum("tji,tj->ti", W, dP[rows_k]))
+
+    t_est = t_rel + dP[:, :3]
+    a_est = a_rel + dP[:, 3:]
+    X_est = X0 + dF
+
+    # information at the estimate = what the BA front-end would export
+    J0, JX1, JP1, _ = linearise(t_est, a_est, X_est)
+    U, W, V = assemble(J0, JX1, JP1)
+
+    maps = []
+    ids32 = gid.astype(np.int32)
+    for k in range(N):
+        s, e_ = foff[k], foff[k + 1]
+        n = e_ - s
+        stno = np.empty(6 + 3 * n, np.int32)
+        stno[:6] = -(k + 2)
+        stno[6:] = np.repeat(ids32[rows_l[s:e_]], 3)
+        stVal = np.concatenate([t_est[k], a_est[k], X_est[s:e_].reshape(-1)])
+        ar = np.arange(n, dtype=np.int32)
+        maps.append(LocalMap(Ref=k + 1, stno=stno, stVal=stVal, m=1, n=int(n),
+                             U=U[k:k + 1], Ui=np.zeros(1, np.int32), Uj=np.zeros(1, np.int32),
+                             W=W[s:e_], photo=np.zeros(n, np.int32), feature=ar,
+                             V=V[s:e_], FBlock=ar.copy()))
+    if not return_truth:
+        return maps
+    # truth of the final map: everything in the frame of pose 1
+    R0 = Rw[0]
+    truth = {
+        "pose_ids": np.arange(1, nf + 1),
+        "pose_t": np.einsum("ij,kj->ki", R0, p - p[0]),
+        "pose_R": np.einsum("kij,lj->kil", Rw, R0),
+        "feat_ids": gid,
+        "feat_X": np.einsum("ij,kj->ki", R0, Xw - p[0]),
+    }
+    return maps, truth

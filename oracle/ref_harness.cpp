@@ -1,0 +1,313 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY (CPU). Not part of the product path.
+//
+// Builds the UNMODIFIED reference translation unit
+//   /root/reference/linux/src/LinearSFMImp/LinearSFMImp.cpp   (included in place, never copied)
+// into a shared library with a C ABI so tests / bench.py's cpu_baseline leg can drive the
+// reference's own operators on in-memory maps and read back full-precision results
+// (the reference's text writers print %lf = 6 decimals, Imp.cpp:2113, 7946, 7959).
+//
+// What is exposed, and the reference code each entry runs:
+//   ref_transform_stereo      -> CLinearSFMImp::lmj_Transform_PF3DStereo        Imp.cpp:349-1924
+//   ref_join_stereo           -> CLinearSFMImp::lmj_LinearLS_PF3DStereo         Imp.cpp:2551-2978
+//   ref_solve_stereo          -> CLinearSFMImp::lmj_solveLinearSFMStereo        Imp.cpp:2119-2378
+//   ref_run_tree_stereo       -> CLinearSFMImp::lmj_PF3D_Divide_ConquerStereo   Imp.cpp:1926-2099
+//   ref_load_localmap_stereo  -> CLinearSFMImp::lmj_readInformationStereo       Imp.cpp:3044-3132
+//   (mono twins: lmj_Transform_PF3DMono 3173, lmj_LinearLS_PF3DMono 7282, Divide_ConquerMono 6511,
+//    lmj_readInformationMono 6660)
+//
+// Two preprocessor hooks are applied to the reference TU (they change no arithmetic):
+//   * `private` -> `public`, so the harness can place maps in m_GMapS / m_LMsetS;
+//   * `printf`  -> ref_printf_hook, which (a) drops the per-join progress lines and (b) when the
+//     scheduler prints "Total Used Time" (Imp.cpp:2072 / 6639) snapshots the final map, because
+//     the scheduler frees it a few lines later (Imp.cpp:2081-2096).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <math.h>
+#include <float.h>
+#include <time.h>
+#include <stdarg.h>
+#include <vector>
+#include <map>
+#include <set>
+#include <algorithm>
+#include <cmath>
+#include <Eigen/Core>
+#include <Eigen/Geometry>
+#include <Eigen/LU>
+#include <Eigen/StdVector>
+#include <Eigen/Cholesky>
+#include "suitesparse/cholmod.h"
+
+extern "C" int ref_printf_hook(const char *fmt, ...);
+
+#define private public
+#define printf ref_printf_hook
+#include "LinearSFMImp.cpp"
+#undef printf
+#undef private
+
+extern "C" {
+
+// Mirrors LocalMapInfoStereo / LocalMapInfo (Imp.h:75-178) with plain C fields.
+typedef struct ref_map {
+    int Ref, FRef, r, m, n, nU, nW;
+    int ScaP, Fix, Sign, FScaP, FFix;      // mono only (Imp.h:172-176)
+    int *stno; double *stVal;
+    double *U; int *Ui, *Uj;
+    double *W; int *photo, *feature;
+    double *V; int *FBlock;
+} ref_map;
+} // extern "C"
+
+static CLinearSFMImp *g_imp = NULL;
+static int g_is_mono = 0;
+static ref_map g_final;              // snapshot taken by the printf hook
+static int g_have_final = 0;
+static double g_total_time = 0.0;    // the reference's own clock()-based figure
+static int g_echo = 0;
+
+static void *dup_bytes(const void *p, size_t n)
+{
+    void *q = malloc(n ? n : 1);
+    if (n && p) memcpy(q, p, n);
+    return q;
+}
+
+static void to_stereo(const ref_map *a, LocalMapInfoStereo &b)
+{
+    b.Ref = a->Ref; b.FRef = a->FRef; b.r = a->r; b.m = a->m; b.n = a->n; b.nU = a->nU; b.nW = a->nW;
+    b.stno = (int *)dup_bytes(a->stno, sizeof(int) * a->r);
+    b.stVal = (double *)dup_bytes(a->stVal, sizeof(double) * a->r);
+    b.U = (double *)dup_bytes(a->U, sizeof(double) * 36 * a->nU);
+    b.Ui = (int *)dup_bytes(a->Ui, sizeof(int) * a->nU);
+    b.Uj = (int *)dup_bytes(a->Uj, sizeof(int) * a->nU);
+    b.W = (double *)dup_bytes(a->W, sizeof(double) * 18 * a->nW);
+    b.photo = (int *)dup_bytes(a->photo, sizeof(int) * a->nW);
+    b.feature = (int *)dup_bytes(a->feature, sizeof(int) * a->nW);
+    b.V = (double *)dup_bytes(a->V, sizeof(double) * 9 * a->n);
+    b.FBlock = (int *)dup_bytes(a->FBlock, sizeof(int) * a->n);
+}
+
+template <class T> static void from_any(const T &b, ref_map *a, bool deep)
+{
+    memset(a, 0, sizeof(*a));
+    a->Ref = b.Ref; a->FRef = b.FRef; a->m = b.m; a->n = b.n; a->nU = b.nU; a->nW = b.nW;
+    a->r = 6 * b.m + 3 * b.n;
+    if (deep) {
+        a->stno = (int *)dup_bytes(b.stno, sizeof(int) * a->r);
+        a->stVal = (double *)dup_bytes(b.stVal, sizeof(double) * a->r);
+        a->U = (double *)dup_bytes(b.U, sizeof(double) * 36 * b.nU);
+        a->Ui = (int *)dup_bytes(b.Ui, sizeof(int) * b.nU);
+        a->Uj = (int *)dup_bytes(b.Uj, sizeof(int) * b.nU);
+        a->W = (double *)dup_bytes(b.W, sizeof(double) * 18 * b.nW);
+        a->photo = (int *)dup_bytes(b.photo, sizeof(int) * b.nW);
+        a->feature = (int *)dup_bytes(b.feature, sizeof(int) * b.nW);
+        a->V = (double *)dup_bytes(b.V, sizeof(double) * 9 * b.n);
+        a->FBlock = (int *)dup_bytes(b.FBlock, sizeof(int) * b.n);
+    } else {
+        a->stno = b.stno; a->stVal = b.stVal; a->U = b.U; a->Ui = b.Ui; a->Uj = b.Uj;
+        a->W = b.W; a->photo = b.photo; a->feature = b.feature; a->V = b.V; a->FBlock = b.FBlock;
+    }
+}
+
+static void to_mono(const ref_map *a, LocalMapInfo &b)
+{
+    LocalMapInfoStereo s; to_stereo(a, s);
+    b.Ref = s.Ref; b.FRef = s.FRef; b.r = s.r; b.m = s.m; b.n = s.n; b.nU = s.nU; b.nW = s.nW;
+    b.stno = s.stno; b.stVal = s.stVal; b.U = s.U; b.Ui = s.Ui; b.Uj = s.Uj; b.W = s.W;
+    b.photo = s.photo; b.feature = s.feature; b.V = s.V; b.FBlock = s.FBlock;
+    b.ScaP = a->ScaP; b.Fix = a->Fix; b.Sign = a->Sign; b.FScaP = a->FScaP; b.FFix = a->FFix;
+}
+
+static void from_mono(const LocalMapInfo &b, ref_map *a, bool deep)
+{
+    from_any(b, a, deep);
+    a->ScaP = b.ScaP; a->Fix = b.Fix; a->Sign = b.Sign; a->FScaP = b.FScaP; a->FFix = b.FFix;
+}
+
+extern "C" {
+
+void ref_free_map(ref_map *a)
+{
+    free(a->stno); free(a->stVal); free(a->U); free(a->Ui); free(a->Uj);
+    free(a->W); free(a->photo); free(a->feature); free(a->V); free(a->FBlock);
+    memset(a, 0, sizeof(*a));
+}
+
+int ref_printf_hook(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    if (strncmp(fmt, "Total Used Time", 15) == 0) {
+        va_list ap2; va_copy(ap2, ap);
+        g_total_time = va_arg(ap2, double);
+        va_end(ap2);
+        if (g_imp) {
+            if (g_have_final) ref_free_map(&g_final);
+            if (g_is_mono) from_mono(g_imp->m_GMap, &g_final, true);
+            else from_any(g_imp->m_GMapS, &g_final, true);
+            g_have_final = 1;
+        }
+    }
+    int rc = 0;
+    if (g_echo) rc = vprintf(fmt, ap);
+    va_end(ap);
+    return rc;
+}
+
+void ref_set_echo(int on) { g_echo = on; }
+
+static CLinearSFMImp *imp()
+{
+    if (!g_imp) g_imp = new CLinearSFMImp();
+    return g_imp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stereo operators
+// ---------------------------------------------------------------------------------------------
+int ref_transform_stereo(const ref_map *in, int Ref, ref_map *out)
+{
+    CLinearSFMImp *I = imp();
+    to_stereo(in, I->m_GMapS);
+    LocalMapInfoStereo res;
+    bool alias = (I->m_GMapS.Ref == Ref);            // Imp.cpp:352-355: shallow alias, no work
+    I->lmj_Transform_PF3DStereo(res, Ref);
+    from_any(res, out, true);
+    ref_map tmp;
+    from_any(I->m_GMapS, &tmp, false); ref_free_map(&tmp);
+    if (!alias) { from_any(res, &tmp, false); ref_free_map(&tmp); }
+    return 0;
+}
+
+int ref_join_stereo(const ref_map *end, const ref_map *cur, ref_map *out)
+{
+    CLinearSFMImp *I = imp();
+    LocalMapInfoStereo E, C;
+    to_stereo(end, E); to_stereo(cur, C);
+    I->lmj_LinearLS_PF3DStereo(E, C);               // frees E and C (Imp.cpp:2937-2958)
+    from_any(I->m_GMapS, out, true);
+    ref_map tmp; from_any(I->m_GMapS, &tmp, false); ref_free_map(&tmp);
+    return 0;
+}
+
+int ref_solve_stereo(double *stVal, double *eb, double *ea, double *U, double *W, double *V,
+                     int *Ui, int *Uj, int *photo, int *feature, int m, int n, int nU, int nW)
+{
+    imp()->lmj_solveLinearSFMStereo(stVal, eb, ea, U, W, V, Ui, Uj, photo, feature, m, n, nU, nW);
+    return 0;
+}
+
+// Whole merge tree through the reference's own scheduler. maps are deep-copied.
+// seconds_ref  = the reference's own clock()-based "Total Used Time" (Imp.cpp:2068-2072)
+// seconds_wall = wall clock around lmj_PF3D_Divide_ConquerStereo
+int ref_run_tree_stereo(const ref_map *maps, int num, ref_map *out, double *seconds_ref,
+                        double *seconds_wall)
+{
+    CLinearSFMImp *I = imp();
+    g_is_mono = 0;
+    I->m_szSt = NULL; I->m_szPose = NULL; I->m_szFeature = NULL;
+    I->m_LMsetS = new LocalMapInfoStereo[num];
+    for (int i = 0; i < num; i++) to_stereo(&maps[i], I->m_LMsetS[i]);
+    g_have_final = 0;
+    struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (num > 1) {
+        I->lmj_PF3D_Divide_ConquerStereo(num);
+    } else {
+        return -1;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    delete[] I->m_LMsetS; I->m_LMsetS = NULL;
+    if (seconds_ref) *seconds_ref = g_total_time;
+    if (seconds_wall) *seconds_wall = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    if (!g_have_final) return -2;
+    *out = g_final; g_have_final = 0; memset(&g_final, 0, sizeof(g_final));
+    return 0;
+}
+
+int ref_load_localmap_stereo(const char *path, ref_map *out)
+{
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    fclose(f);
+    LocalMapInfoStereo M;
+    std::string p(path);
+    imp()->lmj_readInformationStereo(M, (char *)p.c_str());
+    from_any(M, out, false);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mono operators
+// ---------------------------------------------------------------------------------------------
+int ref_transform_mono(const ref_map *in, int Ref, int ScaP, int Fix, ref_map *out)
+{
+    CLinearSFMImp *I = imp();
+    to_mono(in, I->m_GMap);
+    LocalMapInfo res;
+    I->lmj_Transform_PF3DMono(res, Ref, ScaP, Fix);
+    from_mono(res, out, true);
+    ref_map tmp;
+    from_mono(I->m_GMap, &tmp, false); ref_free_map(&tmp);
+    from_mono(res, &tmp, false); ref_free_map(&tmp);
+    return 0;
+}
+
+int ref_join_mono(const ref_map *end, const ref_map *cur, ref_map *out)
+{
+    CLinearSFMImp *I = imp();
+    LocalMapInfo E, C;
+    to_mono(end, E); to_mono(cur, C);
+    I->lmj_LinearLS_PF3DMono(E, C);
+    from_mono(I->m_GMap, out, true);
+    ref_map tmp; from_mono(I->m_GMap, &tmp, false); ref_free_map(&tmp);
+    return 0;
+}
+
+int ref_run_tree_mono(const ref_map *maps, int num, ref_map *out, double *seconds_ref,
+                      double *seconds_wall)
+{
+    CLinearSFMImp *I = imp();
+    g_is_mono = 1;
+    I->m_szSt = NULL; I->m_szPose = NULL; I->m_szFeature = NULL;
+    I->m_LMset = new LocalMapInfo[num];
+    for (int i = 0; i < num; i++) to_mono(&maps[i], I->m_LMset[i]);
+    g_have_final = 0;
+    struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (num > 1) I->lmj_PF3D_Divide_ConquerMono(num); else return -1;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    delete[] I->m_LMset; I->m_LMset = NULL;
+    g_is_mono = 0;
+    if (seconds_ref) *seconds_ref = g_total_time;
+    if (seconds_wall) *seconds_wall = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    if (!g_have_final) return -2;
+    *out = g_final; g_have_final = 0; memset(&g_final, 0, sizeof(g_final));
+    return 0;
+}
+
+int ref_load_localmap_mono(const char *path, ref_map *out)
+{
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    fclose(f);
+    LocalMapInfo M;
+    std::string p(path);
+    imp()->lmj_readInformationMono(M, (char *)p.c_str());
+    from_mono(M, out, false);
+    return 0;
+}
+
+// result writers, for the CLI drop-in comparison (Imp.cpp:2102-2117, 7876-7967)
+int ref_save_outputs(const ref_map *a, const char *st, const char *pose, const char *feat)
+{
+    CLinearSFMImp *I = imp();
+    if (st) { std::string s(st); I->lmj_SaveStateVector((char *)s.c_str(), a->stVal, a->stno, a->r); }
+    if (pose && feat) {
+        std::string p(pose), f(feat);
+        I->lmj_SavePoses_3DPF((char *)p.c_str(), (char *)f.c_str(), a->stno, a->stVal, a->r);
+    }
+    return 0;
+}
+
+} // extern "C"
