@@ -1,0 +1,123 @@
+/*
+ * linearsfm_b200.h -- C ABI of the B200-native LinearSFM hot path (liblinearsfm_b200.so).
+ *
+ * The reference (LiangZhaoPKUImperial/LinearSFM) has no FFI; its in-process boundary is the public
+ * member functions of class CLinearSFMImp (linux/src/LinearSFMImp/LinearSFMImp.h:181-253) working
+ * on the POD containers LocalMapInfoStereo / LocalMapInfo (LinearSFMImp.h:75-178).  Every entry
+ * point below names the reference interface it replaces.  All pointers are HOST pointers, sizes
+ * are plain ints, no C++/torch types cross the boundary.  Device residency is hidden behind the
+ * opaque lsfm_tree handle.  Every function returns an int status (LSFM_OK = 0); the text of the
+ * last error is available from lsfm_last_error().  There is NO CPU fallback: without a CUDA
+ * device every compute entry returns LSFM_ERR_NO_DEVICE.
+ *
+ * Threading: one context per process, not re-entrant (same as the reference, which keeps scratch
+ * in members m_sparseS/m_factorS/..., LinearSFMImp.h:244-247).
+ */
+#ifndef LINEARSFM_B200_H
+#define LINEARSFM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSFM_OK 0
+#define LSFM_ERR_CUDA 1
+#define LSFM_ERR_ARG 2
+#define LSFM_ERR_REF_NOT_FOUND 3
+#define LSFM_ERR_NOT_SPD 4
+#define LSFM_ERR_IO 5
+#define LSFM_ERR_FORMAT 6
+#define LSFM_ERR_NO_DEVICE 7
+
+/* Field-for-field mirror of LocalMapInfoStereo (LinearSFMImp.h:75-121) and LocalMapInfo
+ * (LinearSFMImp.h:124-178; the mono-only fields are ignored by the stereo entry points).
+ * Arrays are malloc()'d by the producer and released with lsfm_free_map() (the reference's
+ * ownership convention: producer mallocs, consumer frees).
+ *   stno[r], stVal[r]  r = 6m+3n; pose rows carry -poseID (x6), feature rows +featID (x3)
+ *   U[36 nU] row-major 6x6, Ui/Uj[nU] with Ui<=Uj;  W[18 nW] row-major 6x3, photo/feature[nW]
+ *   (feature non-decreasing);  V[9 n];  FBlock[n] = first W block of the feature or -1.        */
+typedef struct lsfm_map {
+    int Ref, FRef, r, m, n, nU, nW;
+    int ScaP, Fix, Sign, FScaP, FFix;
+    int *stno;
+    double *stVal;
+    double *U;
+    int *Ui, *Uj;
+    double *W;
+    int *photo, *feature;
+    double *V;
+    int *FBlock;
+} lsfm_map;
+
+typedef struct lsfm_tree lsfm_tree; /* opaque: leaf maps resident in HBM + the last result */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int lsfm_init(int device);                 /* replaces CLinearSFMImp::CLinearSFMImp (Imp.cpp:80-87) */
+void lsfm_shutdown(void);                  /* replaces ~CLinearSFMImp (Imp.cpp:90-93)               */
+const char *lsfm_last_error(void);
+int lsfm_device_count(void);
+void lsfm_free_map(lsfm_map *m);
+/* per-stage statistics of the calls since the last reset, as a JSON object string */
+void lsfm_stats_reset(int enable_stage_timing);
+const char *lsfm_stats_json(void);
+
+/* ---- operators (host buffers in / host buffers out) ---------------------------------------- */
+/* void lmj_Transform_PF3DStereo(LocalMapInfoStereo& out, int Ref) with m_GMapS = *in
+ * (LinearSFMImp.h:206, LinearSFMImp.cpp:349-1924).  Ref == in->Ref returns a copy.            */
+int lsfm_transform_stereo(const lsfm_map *in, int Ref, lsfm_map *out);
+/* K independent transforms in one segmented launch set (what the scheduler uses per level).   */
+int lsfm_transform_stereo_batch(const lsfm_map *in, const int *Ref, int K, lsfm_map *out);
+
+/* void lmj_LinearLS_PF3DStereo(LocalMapInfoStereo& End, LocalMapInfoStereo& Cur), result in
+ * m_GMapS (LinearSFMImp.h:207, LinearSFMImp.cpp:2551-2978).  Inputs are NOT freed here.       */
+int lsfm_join_stereo(const lsfm_map *end, const lsfm_map *cur, lsfm_map *out);
+int lsfm_join_stereo_batch(const lsfm_map *end, const lsfm_map *cur, int K, lsfm_map *out);
+
+/* void lmj_solveLinearSFMStereo(double* stVal, double* eb, double* ea, double* U, double* W,
+ *      double* V, int* Ui, int* Uj, int* photo, int* feature, int m, int n, int nU, int nW)
+ * (LinearSFMImp.h:209, LinearSFMImp.cpp:2119-2378): same argument order and meaning; stVal[6m+3n]
+ * is caller-allocated output; V is left untouched (the reference overwrites and restores it).  */
+int lsfm_solve_stereo(double *stVal, const double *eb, const double *ea, const double *U,
+                      const double *W, const double *V, const int *Ui, const int *Uj,
+                      const int *photo, const int *feature, int m, int n, int nU, int nW);
+
+/* Debug capture of the last lsfm_solve_stereo / single join (integer parity tests):
+ * block CRS of S (the reference's Sidxij, LinearSFMImp.cpp:2190-2205), block elimination ordering
+ * (replaces cholmod_amd, LinearSFMImp.cpp:2413).  Pointers stay valid until the next solve.    */
+int lsfm_debug_last_solve(int *m, const int **rowptr, const int **colidx, const double **S,
+                          const double **E, const int **perm);
+/* the ordering routine alone: upper block pattern (CSC: Ap[m+1], Ai) -> perm[m]               */
+int lsfm_block_ordering(int m, const int *Ap, const int *Ai, int *perm);
+
+/* ---- whole merge tree ----------------------------------------------------------------------- */
+/* void lmj_PF3D_Divide_ConquerStereo(int nLocalMapCount) over m_LMsetS (LinearSFMImp.cpp:1926-2099)
+ * with host maps in, final map out (H2D of the leaves and D2H of the result inside the call).   */
+int lsfm_run_stereo(const lsfm_map *maps, int num, lsfm_map *out);
+
+/* Resident variant: upload once, solve many times (bench), download state or full map.
+ * first_index = global index of maps[0] in the full sequence (multi-GPU sharding: the re-base
+ * rule of LinearSFMImp.cpp:1997 depends on the global output index).                           */
+int lsfm_tree_create_stereo(const lsfm_map *maps, int num, lsfm_tree **tree);
+int lsfm_tree_solve(lsfm_tree *tree, int verbose, int first_index, int max_levels);
+int lsfm_tree_result_count(const lsfm_tree *tree);
+int lsfm_tree_result_shape(const lsfm_tree *tree, int idx, lsfm_map *shape_only);
+int lsfm_tree_download(const lsfm_tree *tree, int idx, lsfm_map *out);
+int lsfm_tree_download_state(const lsfm_tree *tree, int idx, int *stno, double *stVal);
+/* replace leaf/result set by host maps (multi-GPU hand-over between ranks)                      */
+int lsfm_tree_set_maps(lsfm_tree *tree, const lsfm_map *maps, int num);
+void lsfm_tree_free(lsfm_tree *tree);
+
+/* ---- files + CLI (drop-in process boundary) ------------------------------------------------- */
+/* lmj_readInformationStereo (LinearSFMImp.cpp:3044-3132)                                        */
+int lsfm_load_localmap_stereo(const char *path, lsfm_map *out);
+/* lmj_SaveStateVector (2102-2117) and lmj_SavePoses_3DPF (7876-7967); NULL = skip              */
+int lsfm_save_outputs(const lsfm_map *m, const char *state_path, const char *pose_path,
+                      const char *feature_path);
+/* CLinearSFMImp::run(argc, argv) (LinearSFMImp.cpp:7972-8106): same flags
+ *   -path <dir> -num <N> -type {Monocular|Stereo} [-p <pose>] [-f <feature>] [-st <state>] [-help] */
+int lsfm_cli_main(int argc, char **argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

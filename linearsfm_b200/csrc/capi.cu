@@ -1,0 +1,305 @@
+// C ABI of liblinearsfm_b200.so (declared in include/linearsfm_b200.h).
+#include "../../include/linearsfm_b200.h"
+#include "mapio.h"
+#include "scheduler.h"
+#include "chol_symbolic.h"
+#include <cstring>
+#include <sstream>
+#include <algorithm>
+#include <mutex>
+
+namespace {
+
+Context *g_ctx = nullptr;
+std::string g_err;
+std::string g_stats_json;
+SolveDebug g_dbg;
+bool g_dbg_valid = false;
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+int ensure_ctx()
+{
+    if (g_ctx) return LSFM_OK;
+    return lsfm_init(0);
+}
+
+template <class F> int guarded(F &&f)
+{
+    try {
+        int rc = ensure_ctx();
+        if (rc != LSFM_OK) return rc;
+        f();
+        return LSFM_OK;
+    } catch (const LsfmError &e) {
+        return fail(e.code, e.what());
+    } catch (const std::exception &e) {
+        return fail(LSFM_ERR_CUDA, e.what());
+    }
+}
+
+} // namespace
+
+struct lsfm_tree {
+    std::vector<MapHandle> leaves;
+    std::vector<MapHandle> result;
+};
+
+extern "C" {
+
+int lsfm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int lsfm_init(int device)
+{
+    try {
+        int n = lsfm_device_count();
+        if (n <= 0)
+            return fail(LSFM_ERR_NO_DEVICE, "no CUDA device visible: the LinearSFM hot path has no CPU fallback");
+        if (device < 0 || device >= n) return fail(LSFM_ERR_ARG, "bad device index");
+        if (g_ctx && g_ctx->device == device) return LSFM_OK;
+        if (g_ctx) lsfm_shutdown();
+        CUDA_CHECK(cudaSetDevice(device));
+        Context *c = new Context();
+        c->device = device;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreate(&c->ev0));
+        CUDA_CHECK(cudaEventCreate(&c->ev1));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        c->num_sms = prop.multiProcessorCount;
+        // keep freed blocks in the stream-ordered pool: allocation becomes a pointer bump
+        cudaMemPool_t pool;
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long thr = ~0ull;
+        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        g_ctx = c;
+        return LSFM_OK;
+    } catch (const LsfmError &e) {
+        return fail(e.code, e.what());
+    }
+}
+
+void lsfm_shutdown(void)
+{
+    if (!g_ctx) return;
+    cudaStreamSynchronize(g_ctx->stream);
+    cudaEventDestroy(g_ctx->ev0);
+    cudaEventDestroy(g_ctx->ev1);
+    cudaStreamDestroy(g_ctx->stream);
+    delete g_ctx;
+    g_ctx = nullptr;
+}
+
+const char *lsfm_last_error(void) { return g_err.c_str(); }
+
+void lsfm_free_map(lsfm_map *m) { free_host_map(m); }
+
+void lsfm_stats_reset(int enable_stage_timing)
+{
+    if (ensure_ctx() != LSFM_OK) return;
+    g_ctx->stats.clear();
+    g_ctx->launches = 0;
+    g_ctx->objectives.clear();
+    g_ctx->timing = (enable_stage_timing & 1) != 0;
+    g_ctx->want_objective = (enable_stage_timing & 2) != 0;
+}
+
+const char *lsfm_stats_json(void)
+{
+    std::ostringstream os;
+    os.precision(17);
+    os << "{\"launches\": " << (g_ctx ? g_ctx->launches : 0) << ", \"stages\": {";
+    bool first = true;
+    if (g_ctx)
+        for (auto &kv : g_ctx->stats) {
+            if (!first) os << ", ";
+            first = false;
+            os << "\"" << kv.first << "\": {\"ms\": " << kv.second.ms << ", \"launches\": " << kv.second.launches
+               << ", \"bytes\": " << kv.second.bytes << ", \"flops\": " << kv.second.flops << "}";
+        }
+    os << "}, \"objectives\": [";
+    if (g_ctx)
+        for (size_t i = 0; i < g_ctx->objectives.size(); i++) os << (i ? ", " : "") << g_ctx->objectives[i];
+    os << "]}";
+    g_stats_json = os.str();
+    return g_stats_json.c_str();
+}
+
+int lsfm_transform_stereo_batch(const lsfm_map *in, const int *Ref, int K, lsfm_map *out)
+{
+    return guarded([&] {
+        std::vector<MapHandle> h = upload_maps(*g_ctx, in, K, true);
+        std::vector<int> refs(Ref, Ref + K);
+        std::vector<MapHandle> r = transform_or_pass(*g_ctx, h, refs);
+        for (int k = 0; k < K; k++) download_map(*g_ctx, r[k], &out[k]);
+    });
+}
+
+int lsfm_transform_stereo(const lsfm_map *in, int Ref, lsfm_map *out)
+{
+    return lsfm_transform_stereo_batch(in, &Ref, 1, out);
+}
+
+int lsfm_join_stereo_batch(const lsfm_map *end, const lsfm_map *cur, int K, lsfm_map *out)
+{
+    return guarded([&] {
+        std::vector<MapHandle> E = upload_maps(*g_ctx, end, K, true);
+        std::vector<MapHandle> C = upload_maps(*g_ctx, cur, K, true);
+        std::vector<MapHandle> J = join_stereo_batch(*g_ctx, E, C);
+        for (int k = 0; k < K; k++) download_map(*g_ctx, J[k], &out[k]);
+    });
+}
+
+int lsfm_join_stereo(const lsfm_map *end, const lsfm_map *cur, lsfm_map *out)
+{
+    return lsfm_join_stereo_batch(end, cur, 1, out);
+}
+
+int lsfm_solve_stereo(double *stVal, const double *eb, const double *ea, const double *U,
+                      const double *W, const double *V, const int *Ui, const int *Uj,
+                      const int *photo, const int *feature, int m, int n, int nU, int nW)
+{
+    return guarded([&] {
+        if (m <= 0 || n < 0) throw LsfmError(LSFM_ERR_ARG, "solve: bad sizes");
+        // wrap the raw arrays into a map (state values are outputs)
+        lsfm_map M;
+        memset(&M, 0, sizeof(M));
+        M.m = m; M.n = n; M.nU = nU; M.nW = nW; M.r = 6 * m + 3 * n;
+        std::vector<int> stno(M.r);
+        for (int i = 0; i < 6 * m; i++) stno[i] = -(i / 6 + 1);
+        for (int i = 0; i < 3 * n; i++) stno[6 * m + i] = i / 3 + 1;
+        std::vector<double> zeros(M.r, 0.0);
+        M.stno = stno.data(); M.stVal = zeros.data();
+        M.U = (double *)U; M.Ui = (int *)Ui; M.Uj = (int *)Uj;
+        M.W = (double *)W; M.photo = (int *)photo; M.feature = (int *)feature;
+        M.V = (double *)V; M.FBlock = nullptr;
+        std::vector<MapHandle> h = upload_maps(*g_ctx, &M, 1, true);
+        OpMaps J;
+        J.build(h, g_ctx->stream);
+        DevBuf<double> eP(6 * (size_t)m, g_ctx->stream), eF(3 * (size_t)n, g_ctx->stream);
+        eP.upload(ea, 6 * (size_t)m);
+        if (n) eF.upload(eb, 3 * (size_t)n);
+        g_dbg = SolveDebug();
+        solve_stereo_batch(*g_ctx, J, eP.p, eF.p, &g_dbg);
+        g_dbg_valid = true;
+        std::vector<int> tmpno(M.r);
+        download_state(*g_ctx, h[0], tmpno.data(), stVal);
+    });
+}
+
+int lsfm_debug_last_solve(int *m, const int **rowptr, const int **colidx, const double **S,
+                          const double **E, const int **perm)
+{
+    if (!g_dbg_valid) return fail(LSFM_ERR_ARG, "no solve captured");
+    if (m) *m = (int)g_dbg.rowptr.size() - 1;
+    if (rowptr) *rowptr = g_dbg.rowptr.data();
+    if (colidx) *colidx = g_dbg.colidx.data();
+    if (S) *S = g_dbg.S.data();
+    if (E) *E = g_dbg.E.data();
+    if (perm) *perm = g_dbg.perm.data();
+    return LSFM_OK;
+}
+
+int lsfm_block_ordering(int m, const int *Ap, const int *Ai, int *perm)
+{
+    // host-only integer routine (no device needed): upper CSC block pattern -> LSFM-ND ordering
+    try {
+        std::vector<int> ptr(m + 1, 0);
+        for (int j = 0; j < m; j++)
+            for (int p = Ap[j]; p < Ap[j + 1]; p++)
+                if (Ai[p] != j) { ptr[Ai[p] + 1]++; ptr[j + 1]++; }
+        for (int i = 0; i < m; i++) ptr[i + 1] += ptr[i];
+        std::vector<int> adj(ptr[m]), fill(ptr.begin(), ptr.end() - 1);
+        for (int j = 0; j < m; j++)
+            for (int p = Ap[j]; p < Ap[j + 1]; p++)
+                if (Ai[p] != j) { adj[fill[Ai[p]]++] = j; adj[fill[j]++] = Ai[p]; }
+        for (int v = 0; v < m; v++) std::sort(adj.begin() + ptr[v], adj.begin() + ptr[v + 1]);
+        std::vector<int> p, nodes;
+        lsfm_nd_order(m, ptr.data(), adj.data(), p, nodes);
+        for (int i = 0; i < m; i++) perm[i] = p[i];
+        return LSFM_OK;
+    } catch (const std::exception &e) {
+        return fail(LSFM_ERR_ARG, e.what());
+    }
+}
+
+int lsfm_run_stereo(const lsfm_map *maps, int num, lsfm_map *out)
+{
+    return guarded([&] {
+        if (num < 1) throw LsfmError(LSFM_ERR_ARG, "need at least one local map");
+        std::vector<MapHandle> leaves = upload_maps(*g_ctx, maps, num, true);
+        std::vector<MapHandle> top = solve_tree_stereo(*g_ctx, std::move(leaves), false, 0, -1);
+        MapHandle root = final_rebase_stereo(*g_ctx, top[0]);
+        download_map(*g_ctx, root, out);
+    });
+}
+
+int lsfm_tree_create_stereo(const lsfm_map *maps, int num, lsfm_tree **tree)
+{
+    return guarded([&] {
+        lsfm_tree *t = new lsfm_tree();
+        t->leaves = upload_maps(*g_ctx, maps, num, true);
+        *tree = t;
+    });
+}
+
+int lsfm_tree_set_maps(lsfm_tree *tree, const lsfm_map *maps, int num)
+{
+    return guarded([&] {
+        tree->result.clear();
+        tree->leaves = upload_maps(*g_ctx, maps, num, true);
+    });
+}
+
+int lsfm_tree_solve(lsfm_tree *tree, int verbose, int first_index, int max_levels)
+{
+    return guarded([&] {
+        tree->result.clear();
+        std::vector<MapHandle> top = solve_tree_stereo(*g_ctx, tree->leaves, verbose != 0, first_index, max_levels);
+        if (max_levels < 0 && top.size() == 1) top[0] = final_rebase_stereo(*g_ctx, top[0]);
+        tree->result = std::move(top);
+        CUDA_CHECK(cudaStreamSynchronize(g_ctx->stream));
+    });
+}
+
+int lsfm_tree_result_count(const lsfm_tree *tree) { return (int)tree->result.size(); }
+
+int lsfm_tree_result_shape(const lsfm_tree *tree, int idx, lsfm_map *o)
+{
+    if (idx < 0 || idx >= (int)tree->result.size()) return fail(LSFM_ERR_ARG, "bad result index");
+    const DMap &d = tree->result[idx].d;
+    memset(o, 0, sizeof(*o));
+    o->Ref = d.Ref; o->FRef = d.FRef; o->m = d.m; o->n = d.n; o->nU = d.nU; o->nW = d.nW;
+    o->r = 6 * d.m + 3 * d.n;
+    return LSFM_OK;
+}
+
+int lsfm_tree_download(const lsfm_tree *tree, int idx, lsfm_map *out)
+{
+    return guarded([&] {
+        if (idx < 0 || idx >= (int)tree->result.size()) throw LsfmError(LSFM_ERR_ARG, "bad result index");
+        download_map(*g_ctx, tree->result[idx], out);
+    });
+}
+
+int lsfm_tree_download_state(const lsfm_tree *tree, int idx, int *stno, double *stVal)
+{
+    return guarded([&] {
+        if (idx < 0 || idx >= (int)tree->result.size()) throw LsfmError(LSFM_ERR_ARG, "bad result index");
+        download_state(*g_ctx, tree->result[idx], stno, stVal);
+    });
+}
+
+void lsfm_tree_free(lsfm_tree *tree)
+{
+    if (!tree) return;
+    if (g_ctx) cudaStreamSynchronize(g_ctx->stream);
+    delete tree;
+}
+
+} // extern "C"

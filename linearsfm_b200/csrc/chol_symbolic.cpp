@@ -1,0 +1,280 @@
+// Symbolic phase of the block multifrontal Cholesky (host, integer work).
+//
+// Replaces, for the reduced camera system S of every join:
+//   cholmod_amd on the m x m block pattern          LinearSFMImp.cpp:2413
+//   x6 scalar permutation + cholmod_analyze_p       LinearSFMImp.cpp:2425-2440
+// CHOLMOD itself is not part of the reference tree; the ordering implemented here is
+// the documented LSFM-ND rule, chosen because it yields a shallow, wide assembly tree (fronts of one
+// level are factorised by one segmented launch) instead of the chain a minimum-degree ordering
+// produces on the band+arrow structure of sequential map joining.
+#include "chol_symbolic.h"
+#include <algorithm>
+#include <cmath>
+#include <thread>
+#include <stdexcept>
+#include <string>
+
+static int isqrt_floor(int n)
+{
+    int r = (int)std::floor(std::sqrt((double)n));
+    while ((long long)r * r > n) r--;
+    while ((long long)(r + 1) * (r + 1) <= n) r++;
+    return r;
+}
+
+void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm,
+                   std::vector<int> &nodes)
+{
+    perm.clear(); nodes.clear();
+    perm.reserve(m);
+    nodes.push_back(0);
+    if (m <= 32) {
+        for (int i = 0; i < m; i++) perm.push_back(i);
+        if (m > 0) nodes.push_back(m);
+        return;
+    }
+    int tau = std::max(16, std::min(m / 2, 10 * isqrt_floor(m)));
+    std::vector<char> dense(m, 0);
+    std::vector<int> rest;
+    rest.reserve(m);
+    for (int v = 0; v < m; v++) {
+        if (ptr[v + 1] - ptr[v] > tau) dense[v] = 1; else rest.push_back(v);
+    }
+    // explicit work stack of vertex lists; `emit` entries are separators waiting for their subtrees
+    struct Item { std::vector<int> L; bool emit; };
+    std::vector<Item> stack;
+    stack.push_back({std::move(rest), false});
+    std::vector<char> inB(m, 0);
+    while (!stack.empty()) {
+        Item it = std::move(stack.back());
+        stack.pop_back();
+        const std::vector<int> &L = it.L;
+        if (L.empty()) continue;
+        if (it.emit || L.size() <= 8) {
+            perm.insert(perm.end(), L.begin(), L.end());
+            nodes.push_back((int)perm.size());
+            continue;
+        }
+        size_t h = L.size() / 2;
+        for (size_t i = h; i < L.size(); i++) inB[L[i]] = 1;
+        std::vector<int> keep, sep;
+        for (size_t i = 0; i < h; i++) {
+            int a = L[i];
+            bool hit = false;
+            for (int p = ptr[a]; p < ptr[a + 1]; p++) {
+                int w = adj[p];
+                if (!dense[w] && inB[w]) { hit = true; break; }
+            }
+            (hit ? sep : keep).push_back(a);
+        }
+        std::vector<int> B(L.begin() + h, L.end());
+        for (int b : B) inB[b] = 0;
+        // elimination order: keep-subtree, B-subtree, separator  => push in reverse
+        stack.push_back({std::move(sep), true});
+        stack.push_back({std::move(B), false});
+        stack.push_back({std::move(keep), false});
+    }
+    size_t before = perm.size();
+    for (int v = 0; v < m; v++) if (dense[v]) perm.push_back(v);
+    if (perm.size() > before) nodes.push_back((int)perm.size());
+}
+
+namespace {
+
+struct JoinSym {
+    int m = 0;
+    std::vector<int> perm, iperm, nodes, snOf;
+    std::vector<std::vector<int>> structs, children;
+    std::vector<int> parent, level;
+};
+
+typedef unsigned long long u64;
+const u64 M22 = (1ull << 22) - 1;
+
+void analyse_join(int m, const u64 *keys, int nk, JoinSym &J)
+{
+    J.m = m;
+    // symmetric adjacency without self loops
+    std::vector<int> ptr(m + 1, 0);
+    for (int i = 0; i < nk; i++) {
+        int a = (int)((keys[i] >> 22) & M22), b = (int)(keys[i] & M22);
+        if (a != b) { ptr[a + 1]++; ptr[b + 1]++; }
+    }
+    for (int i = 0; i < m; i++) ptr[i + 1] += ptr[i];
+    std::vector<int> adj(ptr[m]), fill(ptr.begin(), ptr.end() - 1);
+    for (int i = 0; i < nk; i++) {
+        int a = (int)((keys[i] >> 22) & M22), b = (int)(keys[i] & M22);
+        if (a != b) { adj[fill[a]++] = b; adj[fill[b]++] = a; }
+    }
+    for (int v = 0; v < m; v++) std::sort(adj.begin() + ptr[v], adj.begin() + ptr[v + 1]);
+    lsfm_nd_order(m, ptr.data(), adj.data(), J.perm, J.nodes);
+    if ((int)J.perm.size() != m) throw std::runtime_error("ordering lost vertices");
+    J.iperm.assign(m, 0);
+    for (int k = 0; k < m; k++) J.iperm[J.perm[k]] = k;
+    int ns = (int)J.nodes.size() - 1;
+    J.snOf.assign(m, 0);
+    for (int s = 0; s < ns; s++)
+        for (int c = J.nodes[s]; c < J.nodes[s + 1]; c++) J.snOf[c] = s;
+    J.structs.assign(ns, {});
+    J.children.assign(ns, {});
+    J.parent.assign(ns, -1);
+    J.level.assign(ns, 0);
+    std::vector<int> mark(m, -1);
+    for (int s = 0; s < ns; s++) {
+        int end = J.nodes[s + 1];
+        std::vector<int> &st = J.structs[s];
+        for (int c = J.nodes[s]; c < end; c++) {
+            int v = J.perm[c];
+            for (int p = ptr[v]; p < ptr[v + 1]; p++) {
+                int r = J.iperm[adj[p]];
+                if (r >= end && mark[r] != s) { mark[r] = s; st.push_back(r); }
+            }
+        }
+        for (int ch : J.children[s])
+            for (int r : J.structs[ch])
+                if (r >= end && mark[r] != s) { mark[r] = s; st.push_back(r); }
+        std::sort(st.begin(), st.end());
+        if (!st.empty()) {
+            int par = J.snOf[st[0]];
+            J.parent[s] = par;
+            J.children[par].push_back(s);
+        }
+        int lev = 0;
+        for (int ch : J.children[s]) lev = std::max(lev, J.level[ch] + 1);
+        J.level[s] = lev;
+    }
+}
+
+} // namespace
+
+void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &posePre,
+                    const std::vector<u64> &keys, const std::vector<int> &sOff,
+                    BatchSymbolic &out, int nthreads)
+{
+    std::vector<JoinSym> js(K);
+    nthreads = std::max(1, std::min(nthreads, K));
+    long long work = (long long)keys.size();
+    if (work < 20000) nthreads = 1;
+    std::vector<std::string> errs(nthreads);
+    auto worker = [&](int tid) {
+        try {
+            for (int k = tid; k < K; k += nthreads)
+                analyse_join(m[k], keys.data() + sOff[k], sOff[k + 1] - sOff[k], js[k]);
+        } catch (const std::exception &e) { errs[tid] = e.what(); }
+    };
+    if (nthreads == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++) th.emplace_back(worker, t);
+        for (auto &t : th) t.join();
+    }
+    for (auto &e : errs) if (!e.empty()) throw std::runtime_error(e);
+
+    out = BatchSymbolic();
+    int totPose = posePre[K];
+    out.poseSn.assign(totPose, -1);
+    out.poseLcol.assign(totPose, 0);
+    out.perm.assign(totPose, 0);
+    out.slot.resize(keys.size());
+    std::vector<int> snBase(K + 1, 0);
+    for (int k = 0; k < K; k++) snBase[k + 1] = snBase[k] + (int)js[k].structs.size();
+    int nsTot = snBase[K];
+    out.sn.resize(nsTot);
+    int maxLevel = 0;
+    long long structTot = 0, childTot = 0;
+    for (int k = 0; k < K; k++)
+        for (size_t s = 0; s < js[k].structs.size(); s++) {
+            structTot += (long long)js[k].structs[s].size();
+            childTot += (long long)js[k].children[s].size();
+            maxLevel = std::max(maxLevel, js[k].level[s]);
+        }
+    out.structIdx.resize(structTot);
+    out.relIdx.assign(structTot, -1);
+    out.childIdx.resize(childTot);
+    long long so = 0, co = 0, fo = 0;
+    for (int k = 0; k < K; k++) {
+        JoinSym &J = js[k];
+        int ns = (int)J.structs.size();
+        for (int s = 0; s < ns; s++) {
+            SnodeDesc &d = out.sn[snBase[k] + s];
+            d.join = k;
+            d.first = J.nodes[s];
+            d.ncols = J.nodes[s + 1] - J.nodes[s];
+            d.structOff = (int)so;
+            d.nstruct = (int)J.structs[s].size();
+            std::copy(J.structs[s].begin(), J.structs[s].end(), out.structIdx.begin() + so);
+            so += d.nstruct;
+            d.parent = J.parent[s] < 0 ? -1 : snBase[k] + J.parent[s];
+            d.childOff = (int)co;
+            d.nchild = (int)J.children[s].size();
+            for (int ch : J.children[s]) out.childIdx[co++] = snBase[k] + ch;
+            d.poseOff = posePre[k];
+            d.level = J.level[s];
+            long long fdim = d.ncols + d.nstruct;
+            long long fs = 6 * fdim;
+            d.frontOff = fo;
+            fo += (fs + 1) * fs;
+            fo = (fo + 1) & ~1ll;
+            out.maxFdim = std::max(out.maxFdim, (int)fdim);
+            double nc = 6.0 * d.ncols, nr = 6.0 * d.nstruct;
+            for (int q = 0; q < 6 * d.ncols; q++) { double c = (nc - q) + nr; out.flops += c * c; }
+        }
+        // relative indices of every supernode's struct inside its parent's front
+        for (int s = 0; s < ns; s++) {
+            int par = J.parent[s];
+            if (par < 0) continue;
+            const SnodeDesc &d = out.sn[snBase[k] + s];
+            const std::vector<int> &ps = J.structs[par];
+            int pf = J.nodes[par], pe = J.nodes[par + 1], pn = pe - pf;
+            size_t q = 0;
+            for (int i = 0; i < d.nstruct; i++) {
+                int r = out.structIdx[d.structOff + i];
+                int pos;
+                if (r < pe) pos = r - pf;
+                else {
+                    while (q < ps.size() && ps[q] < r) q++;
+                    if (q >= ps.size() || ps[q] != r) throw std::runtime_error("symbolic: struct not nested");
+                    pos = pn + (int)q;
+                }
+                out.relIdx[d.structOff + i] = pos;
+            }
+        }
+        for (int c = 0; c < J.m; c++) {
+            int s = J.snOf[c];
+            out.poseSn[posePre[k] + J.perm[c]] = snBase[k] + s;
+            out.poseLcol[posePre[k] + J.perm[c]] = c - J.nodes[s];
+            out.perm[posePre[k] + c] = J.perm[c];
+        }
+        // S slot -> front block
+        for (int i = sOff[k]; i < sOff[k + 1]; i++) {
+            int a = (int)((keys[i] >> 22) & M22), b = (int)(keys[i] & M22);
+            int pa = J.iperm[a], pb = J.iperm[b];
+            int c = std::min(pa, pb), r = std::max(pa, pb);
+            int s = J.snOf[c];
+            SlotMap &sm = out.slot[i];
+            sm.sn = snBase[k] + s;
+            sm.lcol = c - J.nodes[s];
+            sm.pad = 0;
+            if (r < J.nodes[s + 1]) sm.lrow = r - J.nodes[s];
+            else {
+                const std::vector<int> &st = J.structs[s];
+                auto it = std::lower_bound(st.begin(), st.end(), r);
+                if (it == st.end() || *it != r) throw std::runtime_error("symbolic: S block outside front");
+                sm.lrow = (J.nodes[s + 1] - J.nodes[s]) + (int)(it - st.begin());
+            }
+            // front block (row r, col c) = S_full(perm[r], perm[c]); slot holds S_full(a, b)
+            sm.transpose = (pa == r) ? 0 : 1;
+            // diagonal blocks: the reference reads only the UPPER triangle (LinearSFMImp.cpp:2221-2230,
+            // 2474-2481); the front keeps the lower triangle, so take it from the transposed block
+            if (a == b) sm.transpose = 1;
+        }
+    }
+    out.frontDoubles = fo;
+    // level sets
+    out.levelPtr.assign(maxLevel + 2, 0);
+    for (auto &d : out.sn) out.levelPtr[d.level + 1]++;
+    for (int l = 0; l <= maxLevel; l++) out.levelPtr[l + 1] += out.levelPtr[l];
+    out.levelSn.resize(nsTot);
+    std::vector<int> fillp(out.levelPtr.begin(), out.levelPtr.end() - 1);
+    for (int s = 0; s < nsTot; s++) out.levelSn[fillp[out.sn[s].level]++] = s;
+}

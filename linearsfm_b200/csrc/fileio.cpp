@@ -1,0 +1,226 @@
+// Drop-in process boundary: the reference's file formats and command line.
+//   lmj_readInformationStereo       LinearSFMImp.cpp:3044-3132   (format: SURVEY Appendix A.1)
+//   lmj_SaveStateVector             LinearSFMImp.cpp:2102-2117
+//   lmj_SavePoses_3DPF              LinearSFMImp.cpp:7876-7967
+//   run / lmj_parseArgs / printHelp LinearSFMImp.cpp:7972-8106
+// The reader slurps the file and tokenises with strtol/strtod (the reference calls fscanf once per
+// number); files of one run are parsed by several host threads.
+#include "../../include/linearsfm_b200.h"
+#include "common.h"
+#include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include <map>
+#include <thread>
+#include <chrono>
+#include <algorithm>
+
+namespace {
+
+std::string g_io_err;
+
+struct Tok {
+    char *p, *end;
+    bool fail = false;
+    long next_int()
+    {
+        char *q;
+        long v = strtol(p, &q, 10);
+        if (q == p) fail = true;
+        p = q;
+        return v;
+    }
+    double next_dbl()
+    {
+        char *q;
+        double v = strtod(p, &q);
+        if (q == p) fail = true;
+        p = q;
+        return v;
+    }
+};
+
+int load_stereo_impl(const char *path, lsfm_map *M, std::string &err)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) { err = std::string("cannot open ") + path; return LSFM_ERR_IO; }
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> buf(sz + 1);
+    size_t got = fread(buf.data(), 1, sz, f);
+    fclose(f);
+    buf[got] = 0;
+    Tok t{buf.data(), buf.data() + got};
+    memset(M, 0, sizeof(*M));
+    M->Ref = (int)t.next_int();
+    M->FRef = M->Ref;                                   // LinearSFMImp.cpp:3053
+    M->r = (int)t.next_int();
+    if (t.fail || M->r < 0) { err = std::string(path) + ": bad header"; return LSFM_ERR_FORMAT; }
+    auto A = [](size_t n, size_t s) { return malloc((n * s) ? (n * s) : 1); };
+    M->stno = (int *)A(M->r, sizeof(int));
+    M->stVal = (double *)A(M->r, sizeof(double));
+    for (int i = 0; i < M->r; i++) { M->stno[i] = (int)t.next_int(); M->stVal[i] = t.next_dbl(); }
+    M->m = (int)t.next_int();
+    M->n = (int)t.next_int();
+    M->nU = (int)t.next_int();
+    if (t.fail || M->m < 0 || M->n < 0 || M->nU < 0 || M->r != 6 * M->m + 3 * M->n) {
+        err = std::string(path) + ": inconsistent sizes"; lsfm_free_map(M); return LSFM_ERR_FORMAT;
+    }
+    M->U = (double *)A(36 * (size_t)M->nU, sizeof(double));
+    M->Ui = (int *)A(M->nU, sizeof(int));
+    M->Uj = (int *)A(M->nU, sizeof(int));
+    for (size_t i = 0; i < 36 * (size_t)M->nU; i++) M->U[i] = t.next_dbl();
+    for (int i = 0; i < M->nU; i++) M->Ui[i] = (int)t.next_int();
+    for (int i = 0; i < M->nU; i++) M->Uj[i] = (int)t.next_int();
+    M->nW = (int)t.next_int();
+    if (t.fail || M->nW < 0) { err = std::string(path) + ": bad nW"; lsfm_free_map(M); return LSFM_ERR_FORMAT; }
+    M->W = (double *)A(18 * (size_t)M->nW, sizeof(double));
+    M->photo = (int *)A(M->nW, sizeof(int));
+    M->feature = (int *)A(M->nW, sizeof(int));
+    for (size_t i = 0; i < 18 * (size_t)M->nW; i++) M->W[i] = t.next_dbl();
+    for (int i = 0; i < M->nW; i++) M->photo[i] = (int)t.next_int();
+    for (int i = 0; i < M->nW; i++) M->feature[i] = (int)t.next_int();
+    M->V = (double *)A(9 * (size_t)M->n, sizeof(double));
+    for (size_t i = 0; i < 9 * (size_t)M->n; i++) M->V[i] = t.next_dbl();
+    M->FBlock = (int *)A(M->n, sizeof(int));
+    for (int i = 0; i < M->n; i++) M->FBlock[i] = (int)t.next_int();
+    if (t.fail) { err = std::string(path) + ": truncated file"; lsfm_free_map(M); return LSFM_ERR_FORMAT; }
+    return LSFM_OK;
+}
+
+void print_help()
+{
+    printf("Linear SFM Solution General Options\n\n");
+    printf("-path			Set Data Path.\n");
+    printf("-st            Set Path to Save Final State Vector\n");
+    printf("-p			Set Path to Save Poses\n");
+    printf("-f			Set Path to Save Features\n");
+    printf("-num			Number of Initial Recontruction\n");
+    printf("-type			Set Data Type.\n");
+    printf("Data Type Listed As Following:\n");
+    printf("			I  : Monocular\n");
+    printf("			II : Stereo\n");
+    printf("\n");
+}
+
+} // namespace
+
+extern "C" {
+
+int lsfm_load_localmap_stereo(const char *path, lsfm_map *out)
+{
+    return load_stereo_impl(path, out, g_io_err);
+}
+
+int lsfm_save_outputs(const lsfm_map *M, const char *st, const char *pose, const char *feat)
+{
+    if (st) {
+        FILE *fp = fopen(st, "w");
+        if (!fp) { printf("Please Input Path to Save Final State Vector!"); return LSFM_ERR_IO; }
+        for (int i = 0; i < M->r; i++) fprintf(fp, "%d %lf\n", M->stno[i], M->stVal[i]);
+        fclose(fp);
+    }
+    if (!pose && !feat) return LSFM_OK;
+    // sorted by id; a repeated id keeps its last occurrence (std::map overwrite, 7907/7925)
+    std::map<int, int> poseIdx, featIdx;
+    for (int i = 0; i < M->r;) {
+        if (M->stno[i] <= 0) { poseIdx[-M->stno[i]] = i; i += 6; }
+        else { featIdx[M->stno[i]] = i; i += 3; }
+    }
+    if (pose) {
+        FILE *fp = fopen(pose, "w");
+        if (!fp) return LSFM_ERR_IO;
+        for (auto &kv : poseIdx) {
+            const double *x = M->stVal + kv.second;
+            fprintf(fp, "%d  %lf  %lf  %lf %lf  %lf  %lf\n", kv.first, x[0], x[1], x[2], x[3], x[4], x[5]);
+        }
+        fclose(fp);
+    }
+    if (feat) {
+        FILE *fp = fopen(feat, "w");
+        if (!fp) return LSFM_ERR_IO;
+        for (auto &kv : featIdx) {
+            const double *x = M->stVal + kv.second;
+            fprintf(fp, "%d  %lf  %lf %lf\n", kv.first, x[0], x[1], x[2]);
+        }
+        fclose(fp);
+    }
+    return LSFM_OK;
+}
+
+int lsfm_cli_main(int argc, char **argv)
+{
+    std::string path, st, pose, feat, type;
+    int num = 0;
+    bool hasPath = false, hasNum = false, hasType = false;
+    for (int i = 1; i < argc; i++) {
+        std::string name = argv[i];
+        if (name[0] != '-') return 0;                    // LinearSFMImp.cpp:8000-8002: silent return
+        size_t d = name.find_first_not_of('-');
+        if (d != std::string::npos) name = name.substr(d);
+        if (name == "help") { print_help(); return 0; }
+        auto arg = [&](std::string &dst) { if (i + 1 < argc) dst = argv[++i]; };
+        if (name == "path") { arg(path); hasPath = true; }
+        else if (name == "st") arg(st);
+        else if (name == "p") arg(pose);
+        else if (name == "f") arg(feat);
+        else if (name == "num") { std::string v; arg(v); num = atoi(v.c_str()); hasNum = true; }
+        else if (name == "type") {
+            std::string v; arg(v);
+            if (v == "Monocular" || v == "Stereo") { type = v; hasType = true; }
+        }
+    }
+    if (!hasPath) { printf("LinerSFM Error: Please Input Right File Path:\n"); return 0; }
+    if (!hasNum) { printf("LinerSFM Error: Please Set Local Map Number:\n"); return 0; }
+    if (!hasType) { printf("LinerSFM Error: Please Set Data Type:\n"); return 0; }
+    if (type == "Monocular") {
+        fprintf(stderr, "LinearSFM (B200): -type Monocular is not built in this round (stereo hot path only)\n");
+        return 0;
+    }
+    if (num < 1) return 0;
+    if (lsfm_init(0) != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0; }
+
+    std::vector<lsfm_map> maps(num);
+    std::vector<int> rc(num, LSFM_OK);
+    std::vector<std::string> errs(num);
+    int nth = std::min<int>(std::max(1u, std::thread::hardware_concurrency()), 32);
+    nth = std::min(nth, num);
+    auto work = [&](int tid) {
+        for (int i = tid; i < num; i += nth) {
+            std::string p = path + "/localmap_" + std::to_string(i + 1) + ".txt";
+            rc[i] = load_stereo_impl(p.c_str(), &maps[i], errs[i]);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; t++) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
+    for (int i = 0; i < num; i++)
+        if (rc[i] != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", errs[i].c_str()); return 0; }
+
+    lsfm_tree *tree = nullptr;
+    if (lsfm_tree_create_stereo(maps.data(), num, &tree) != LSFM_OK) {
+        fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+    }
+    for (auto &m : maps) lsfm_free_map(&m);
+    auto t0 = std::chrono::steady_clock::now();
+    if (lsfm_tree_solve(tree, 1, 0, -1) != LSFM_OK) {
+        fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+    }
+    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("Total Used Time:  %lf  sec\n\n", sec);          // LinearSFMImp.cpp:2072
+    lsfm_map out;
+    if (lsfm_tree_download(tree, 0, &out) != LSFM_OK) {
+        fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+    }
+    lsfm_tree_free(tree);
+    if (!st.empty()) lsfm_save_outputs(&out, st.c_str(), nullptr, nullptr);
+    if (!pose.empty() && !feat.empty())                     // both required, LinearSFMImp.cpp:2078
+        lsfm_save_outputs(&out, nullptr, pose.c_str(), feat.c_str());
+    lsfm_free_map(&out);
+    return 0;
+}
+
+} // extern "C"

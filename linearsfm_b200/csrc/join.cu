@@ -1,0 +1,413 @@
+// Batched linear join of map pairs: rows a6-a7 of SURVEY 8(a) (+ the optional per-join objective).
+//
+// Reference: CLinearSFMImp::lmj_LinearLS_PF3DStereo, LinearSFMImp.cpp:2551-2978
+//   common-feature search (std::find, O(n1 n2))     2565-2599   -> device hash join, O(n1+n2)
+//   joint layout, U/W/V merge, RHS eP/eF            2606-2930
+//   -> lmj_solveLinearSFMStereo                     2966        (solve.cu)
+//
+// Output ordering is the reference's: poses = End then Cur (+m1); features =
+// End's (common ones get V summed) then Cur-only in Cur order; U list = End's then Cur's; per joint
+// feature the End blocks then the Cur blocks.
+#include "ops.h"
+#include "small_mat.cuh"
+#include <cub/cub.cuh>
+
+namespace {
+
+typedef unsigned long long u64;
+#define HASH_EMPTY 0xffffffffffffffffull
+
+__device__ __forceinline__ u64 mix64(u64 x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+__global__ void k_hash_insert(const DMap *__restrict__ C, const int *__restrict__ featPreC, int K,
+                              int totC, u64 *__restrict__ keys, int *__restrict__ vals, u64 mask)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totC) return;
+    int k = seg_find(featPreC, K, g);
+    int c = g - featPreC[k];
+    u64 key = ((u64)(unsigned)k << 32) | (unsigned)C[k].featNo[c];
+    u64 h = mix64(key) & mask;
+    while (true) {
+        u64 prev = atomicCAS(&keys[h], HASH_EMPTY, key);
+        if (prev == HASH_EMPTY || prev == key) { atomicMin(&vals[h], c); return; }   // first index wins
+        h = (h + 1) & mask;
+    }
+}
+
+// for each End feature: first Cur feature with the same id (LinearSFMImp.cpp:2581-2599)
+__global__ void k_hash_probe(const DMap *__restrict__ E, const int *__restrict__ featPreE,
+                             const int *__restrict__ featPreC, int K, int totE,
+                             const u64 *__restrict__ keys, const int *__restrict__ vals, u64 mask,
+                             int *__restrict__ ownerOfCur)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totE) return;
+    int k = seg_find(featPreE, K, g);
+    int i = g - featPreE[k];
+    u64 key = ((u64)(unsigned)k << 32) | (unsigned)E[k].featNo[i];
+    u64 h = mix64(key) & mask;
+    while (true) {
+        u64 cur = keys[h];
+        if (cur == HASH_EMPTY) return;
+        if (cur == key) { atomicMax(&ownerOfCur[featPreC[k] + vals[h]], i); return; }  // last i wins (2596)
+        h = (h + 1) & mask;
+    }
+}
+
+__global__ void k_only_flag(const int *__restrict__ ownerOfCur, int totC, int *__restrict__ flag)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > totC) return;
+    flag[g] = (g < totC && ownerOfCur[g] < 0) ? 1 : 0;
+}
+
+__global__ void k_only_count(const int *__restrict__ featPreC, int K, const int *__restrict__ scan,
+                             int *__restrict__ nOnly)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    nOnly[k] = scan[featPreC[k + 1]] - scan[featPreC[k]];
+}
+
+// joint index of every Cur feature (Curfeature2, 2596/2639) and the inverse map joint -> Cur
+__global__ void k_joint_index(const DMap *__restrict__ E, const int *__restrict__ featPreC,
+                              const int *__restrict__ featPreJ, int K, int totC,
+                              const int *__restrict__ ownerOfCur, const int *__restrict__ scan,
+                              int *__restrict__ jointOfCur, int *__restrict__ curOfJoint)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totC) return;
+    int k = seg_find(featPreC, K, g);
+    int own = ownerOfCur[g];
+    int jf = own >= 0 ? own : E[k].n + (scan[g] - scan[featPreC[k]]);
+    jointOfCur[g] = jf;
+    curOfJoint[featPreJ[k] + jf] = g - featPreC[k];
+}
+
+__global__ void k_joint_count(const DMap *__restrict__ E, const DMap *__restrict__ C,
+                              const int *__restrict__ featPreJ, int K, int totJ,
+                              const int *__restrict__ curOfJoint, int *__restrict__ cnt)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > totJ) return;
+    if (g == totJ) { cnt[g] = 0; return; }
+    int k = seg_find(featPreJ, K, g);
+    int jf = g - featPreJ[k];
+    int c = curOfJoint[g];
+    int n = 0;
+    if (jf < E[k].n) n += E[k].wPtr[jf + 1] - E[k].wPtr[jf];
+    if (c >= 0) n += C[k].wPtr[c + 1] - C[k].wPtr[c];
+    cnt[g] = n;
+}
+
+__global__ void k_join_pose(const DMap *__restrict__ E, const DMap *__restrict__ C,
+                            DMap *__restrict__ J, const int *__restrict__ posePreJ, int K, int totP)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totP) return;
+    int k = seg_find(posePreJ, K, g);
+    int p = g - posePreJ[k];
+    int m1 = E[k].m;
+    J[k].poseNo[p] = p < m1 ? E[k].poseNo[p] : C[k].poseNo[p - m1];
+}
+
+// U list = End's then Cur's (+m1); eP += U xhat (and the transposed product for off-diagonal blocks)
+__global__ void k_join_u(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__restrict__ J,
+                         const int *__restrict__ uPreJ, const int *__restrict__ posePreJ, int K, int totU,
+                         double *__restrict__ eP)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totU) return;
+    int k = seg_find(uPreJ, K, g);
+    int b = g - uPreJ[k];
+    const DMap &S = (b < E[k].nU) ? E[k] : C[k];
+    int off = (b < E[k].nU) ? 0 : E[k].m;
+    int sb = (b < E[k].nU) ? b : b - E[k].nU;
+    double U[36];
+    sm::load<36>(S.U + 36 * (size_t)sb, U);
+    sm::store<36>(J[k].U + 36 * (size_t)b, U);
+    int i = S.Ui[sb], j = S.Uj[sb];
+    J[k].Ui[b] = i + off;
+    J[k].Uj[b] = j + off;
+    double xi[6], xj[6], y[6];
+    sm::load<6>(S.poseVal + 6 * (size_t)j, xj);
+    sm::mm<6, 6, 1>(U, xj, y);
+    double *e = eP + 6 * (size_t)(posePreJ[k] + i + off);
+#pragma unroll
+    for (int q = 0; q < 6; q++) atomicAdd(e + q, y[q]);
+    if (i != j) {
+        sm::load<6>(S.poseVal + 6 * (size_t)i, xi);
+        sm::mtm<6, 6, 1>(U, xi, y);
+        e = eP + 6 * (size_t)(posePreJ[k] + j + off);
+#pragma unroll
+        for (int q = 0; q < 6; q++) atomicAdd(e + q, y[q]);
+    }
+}
+
+// one thread per joint feature: V merge, W copy, eF, eP contributions (2747-2930)
+__global__ void __launch_bounds__(128)
+k_join_feat(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__restrict__ J,
+            const int *__restrict__ featPreJ, const int *__restrict__ posePreJ, int K, int totJ,
+            const int *__restrict__ curOfJoint, const int *__restrict__ wScan,
+            double *__restrict__ eP, double *__restrict__ eF)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = g < totJ;
+    int k = live ? seg_find(featPreJ, K, g) : 0;
+    int jf = live ? g - featPreJ[k] : 0;
+    const DMap &Em = E[k];
+    const DMap &Cm = C[k];
+    const DMap &Jm = J[k];
+    int m1 = Em.m;
+    int c = live ? curOfJoint[g] : -1;
+    bool hasE = live && jf < Em.n;
+    double ef[3] = {0.0, 0.0, 0.0};
+    double V[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) V[i] = 0.0;
+    double xe[3] = {0, 0, 0}, xc[3] = {0, 0, 0};
+    int e0 = 0, ke = 0, c0 = 0, kc = 0, o0 = 0;
+    if (hasE) {
+        sm::load<9>(Em.V + 9 * (size_t)jf, V);
+        sm::load<3>(Em.featVal + 3 * (size_t)jf, xe);
+        sm::mm<3, 3, 1>(V, xe, ef);
+        e0 = Em.wPtr[jf]; ke = Em.wPtr[jf + 1] - e0;
+        Jm.featNo[jf] = Em.featNo[jf];
+    }
+    if (c >= 0) {
+        double Vc[9], t[3];
+        sm::load<9>(Cm.V + 9 * (size_t)c, Vc);
+        sm::load<3>(Cm.featVal + 3 * (size_t)c, xc);
+        sm::mm<3, 3, 1>(Vc, xc, t);
+#pragma unroll
+        for (int i = 0; i < 9; i++) V[i] += Vc[i];
+        ef[0] += t[0]; ef[1] += t[1]; ef[2] += t[2];
+        c0 = Cm.wPtr[c]; kc = Cm.wPtr[c + 1] - c0;
+        if (!hasE) Jm.featNo[jf] = Cm.featNo[c];
+    }
+    if (live) {
+        sm::store<9>(Jm.V + 9 * (size_t)jf, V);
+        o0 = wScan[g] - wScan[featPreJ[k]];
+        Jm.wPtr[jf] = o0;
+    }
+    int kt = ke + kc;
+    int kmax = __reduce_max_sync(0xffffffffu, kt);
+    for (int jj = 0; jj < kmax; jj++) {
+        bool act = jj < kt;
+        double y[6];
+        int p = 0;
+        if (act) {
+            bool fromE = jj < ke;
+            const DMap &S = fromE ? Em : Cm;
+            int sb = fromE ? e0 + jj : c0 + (jj - ke);
+            double W[18];
+            sm::load<18>(S.W + 18 * (size_t)sb, W);
+            sm::store<18>(Jm.W + 18 * (size_t)(o0 + jj), W);
+            int sp = S.photo[sb];
+            p = sp + (fromE ? 0 : m1);
+            Jm.photo[o0 + jj] = p;
+            Jm.feature[o0 + jj] = jf;
+            const double *xf = fromE ? xe : xc;
+            sm::mm<6, 3, 1>(W, xf, y);                           // eP_p += W xhat_f
+            double xp[6], t[3];
+            sm::load<6>(S.poseVal + 6 * (size_t)sp, xp);
+            sm::mtm<3, 6, 1>(W, xp, t);                           // eF_f += W^T xhat_p
+            ef[0] += t[0]; ef[1] += t[1]; ef[2] += t[2];
+        }
+        sm::warp_agg_atomic_add<6>(eP + 6 * (size_t)(posePreJ[k] + p), y, act);
+    }
+    if (live) sm::store<3>(eF + 3 * (size_t)g, ef);
+}
+
+__global__ void k_wptr_end(DMap *__restrict__ J, int K)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    J[k].wPtr[J[k].n] = J[k].nW;
+}
+
+// F_k = sum over End and Cur of (x|_k - xhat_k)^T I_k (x|_k - xhat_k)   (residual form)
+// thread per source block; one atomic per block into obj[k].
+__global__ void k_objective(const DMap *__restrict__ E, const DMap *__restrict__ C,
+                            const DMap *__restrict__ J, int K, const int *__restrict__ uPreJ,
+                            const int *__restrict__ wPreJ, const int *__restrict__ featPreE,
+                            const int *__restrict__ featPreC, int totU, int totW, int totFE, int totFC,
+                            const int *__restrict__ jointOfCur, double *__restrict__ obj)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int which = 0;                      // 0:U 1:W 2:V(End) 3:V(Cur)
+    int idx = g;
+    if (idx >= totU) { idx -= totU; which = 1;
+        if (idx >= totW) { idx -= totW; which = 2;
+            if (idx >= totFE) { idx -= totFE; which = 3; if (idx >= totFC) return; } } }
+    double val = 0.0;
+    int k;
+    if (which == 0) {
+        k = seg_find(uPreJ, K, idx);
+        int b = idx - uPreJ[k];
+        bool fromE = b < E[k].nU;
+        const DMap &S = fromE ? E[k] : C[k];
+        int sb = fromE ? b : b - E[k].nU, off = fromE ? 0 : E[k].m;
+        int i = S.Ui[sb], j = S.Uj[sb];
+        double di[6], dj[6], U[36], y[6];
+        for (int q = 0; q < 6; q++) {
+            di[q] = J[k].poseVal[6 * (size_t)(i + off) + q] - S.poseVal[6 * (size_t)i + q];
+            dj[q] = J[k].poseVal[6 * (size_t)(j + off) + q] - S.poseVal[6 * (size_t)j + q];
+        }
+        sm::load<36>(S.U + 36 * (size_t)sb, U);
+        sm::mm<6, 6, 1>(U, dj, y);
+        for (int q = 0; q < 6; q++) val += di[q] * y[q];
+        if (i != j) val *= 2.0;
+    } else if (which == 1) {
+        // W blocks are enumerated in SOURCE order: End's blocks then Cur's blocks of join k
+        k = seg_find(wPreJ, K, idx);
+        int b = idx - wPreJ[k];
+        bool fromE = b < E[k].nW;
+        const DMap &S = fromE ? E[k] : C[k];
+        int sb = fromE ? b : b - E[k].nW, off = fromE ? 0 : E[k].m;
+        int p = S.photo[sb], f = S.feature[sb];
+        int jf = fromE ? f : jointOfCur[featPreC[k] + f];
+        double dp[6], df[3], W[18], y[6];
+        for (int q = 0; q < 6; q++)
+            dp[q] = J[k].poseVal[6 * (size_t)(p + off) + q] - S.poseVal[6 * (size_t)p + q];
+        for (int q = 0; q < 3; q++)
+            df[q] = J[k].featVal[3 * (size_t)jf + q] - S.featVal[3 * (size_t)f + q];
+        sm::load<18>(S.W + 18 * (size_t)sb, W);
+        sm::mm<6, 3, 1>(W, df, y);
+        for (int q = 0; q < 6; q++) val += dp[q] * y[q];
+        val *= 2.0;
+    } else {
+        bool fromE = which == 2;
+        const int *pre = fromE ? featPreE : featPreC;
+        k = seg_find(pre, K, idx);
+        int f = idx - pre[k];
+        const DMap &S = fromE ? E[k] : C[k];
+        int jf = fromE ? f : jointOfCur[featPreC[k] + f];
+        double df[3], V[9], y[3];
+        for (int q = 0; q < 3; q++)
+            df[q] = J[k].featVal[3 * (size_t)jf + q] - S.featVal[3 * (size_t)f + q];
+        sm::load<9>(S.V + 9 * (size_t)f, V);
+        sm::mm<3, 3, 1>(V, df, y);
+        val = df[0] * y[0] + df[1] * y[1] + df[2] * y[2];
+    }
+    atomicAdd(&obj[k], val);
+}
+
+void exclusive_scan(Context &ctx, const int *in, int *out, int n)
+{
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, n, ctx.stream);
+    DevBuf<char> tmp(tmp_bytes, ctx.stream);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, n, ctx.stream);
+}
+
+} // namespace
+
+std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHandle> &End,
+                                         const std::vector<MapHandle> &Cur)
+{
+    const int K = (int)End.size();
+    if (K == 0) return {};
+    if ((int)Cur.size() != K) throw LsfmError(LSFM_ERR_ARG, "join: End/Cur count mismatch");
+    cudaStream_t s = ctx.stream;
+    const int TB = 256;
+    int nl = 0;
+    ctx.begin("join.match");
+    OpMaps E, C;
+    E.build(End, s);
+    C.build(Cur, s);
+
+    // ---- a6: common features (hash join) ----
+    u64 cap = 1024;
+    while (cap < 2ull * (u64)C.totFeat) cap <<= 1;
+    DevBuf<u64> hkeys(cap, s);
+    DevBuf<int> hvals(cap, s);
+    CUDA_CHECK(cudaMemsetAsync(hkeys.p, 0xff, cap * sizeof(u64), s));
+    CUDA_CHECK(cudaMemsetAsync(hvals.p, 0x7f, cap * sizeof(int), s));
+    DevBuf<int> owner(C.totFeat + 1, s), onlyFlag(C.totFeat + 1, s), onlyScan(C.totFeat + 1, s);
+    CUDA_CHECK(cudaMemsetAsync(owner.p, 0xff, (C.totFeat + 1) * sizeof(int), s));
+    if (C.totFeat > 0) {
+        k_hash_insert<<<ceil_div(C.totFeat, TB), TB, 0, s>>>(C.d.p, C.dFeatPre.p, K, C.totFeat, hkeys.p, hvals.p, cap - 1); nl++;
+    }
+    if (E.totFeat > 0 && C.totFeat > 0) {
+        k_hash_probe<<<ceil_div(E.totFeat, TB), TB, 0, s>>>(E.d.p, E.dFeatPre.p, C.dFeatPre.p, K, E.totFeat,
+                                                           hkeys.p, hvals.p, cap - 1, owner.p); nl++;
+    }
+    k_only_flag<<<ceil_div(C.totFeat + 1, TB), TB, 0, s>>>(owner.p, C.totFeat, onlyFlag.p); nl++;
+    exclusive_scan(ctx, onlyFlag.p, onlyScan.p, C.totFeat + 1); nl += 2;
+    DevBuf<int> dOnly(K, s);
+    k_only_count<<<ceil_div(K, TB), TB, 0, s>>>(C.dFeatPre.p, K, onlyScan.p, dOnly.p); nl++;
+    std::vector<int> nOnly(K);
+    dOnly.download(nOnly.data(), K);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    KERNEL_CHECK();
+    ctx.end(8.0 * (E.totFeat + C.totFeat), 0.0, nl);
+    nl = 0;
+
+    // ---- joint shapes (2606-2611) ----
+    ctx.begin("join.merge");
+    std::vector<DMap> shapes(K);
+    double bytes = 0.0;
+    for (int k = 0; k < K; k++) {
+        DMap &j = shapes[k];
+        memset(&j, 0, sizeof(j));
+        j.m = E.h[k].m + C.h[k].m;
+        j.n = E.h[k].n + nOnly[k];
+        j.nU = E.h[k].nU + C.h[k].nU;
+        j.nW = E.h[k].nW + C.h[k].nW;
+        j.Ref = C.h[k].Ref;             // 2974
+        j.FRef = E.h[k].FRef;           // 2624
+        bytes += map_bytes(E.h[k]) + map_bytes(C.h[k]);
+    }
+    std::vector<MapHandle> out = alloc_maps(ctx, shapes);
+    OpMaps J;
+    J.build(out, s);
+    for (int k = 0; k < K; k++) bytes += map_bytes(J.h[k]);
+
+    DevBuf<int> jointOfCur(C.totFeat + 1, s), curOfJoint(J.totFeat + 1, s);
+    CUDA_CHECK(cudaMemsetAsync(curOfJoint.p, 0xff, (J.totFeat + 1) * sizeof(int), s));
+    if (C.totFeat > 0) {
+        k_joint_index<<<ceil_div(C.totFeat, TB), TB, 0, s>>>(E.d.p, C.dFeatPre.p, J.dFeatPre.p, K, C.totFeat,
+                                                            owner.p, onlyScan.p, jointOfCur.p, curOfJoint.p); nl++;
+    }
+    DevBuf<int> wCnt(J.totFeat + 1, s), wScan(J.totFeat + 1, s);
+    k_joint_count<<<ceil_div(J.totFeat + 1, TB), TB, 0, s>>>(E.d.p, C.d.p, J.dFeatPre.p, K, J.totFeat,
+                                                            curOfJoint.p, wCnt.p); nl++;
+    exclusive_scan(ctx, wCnt.p, wScan.p, J.totFeat + 1); nl += 2;
+
+    DevBuf<double> eP(6 * (size_t)J.totPose, s), eF(3 * (size_t)J.totFeat, s);
+    eP.zero();
+    k_join_pose<<<ceil_div(J.totPose, TB), TB, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dPosePre.p, K, J.totPose); nl++;
+    if (J.totU > 0) {
+        k_join_u<<<ceil_div(J.totU, 128), 128, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dUPre.p, J.dPosePre.p, K, J.totU, eP.p); nl++;
+    }
+    if (J.totFeat > 0) {
+        k_join_feat<<<ceil_div(J.totFeat, 128), 128, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dFeatPre.p, J.dPosePre.p, K,
+                                                            J.totFeat, curOfJoint.p, wScan.p, eP.p, eF.p); nl++;
+    }
+    k_wptr_end<<<ceil_div(K, TB), TB, 0, s>>>(J.d.p, K); nl++;
+    KERNEL_CHECK();
+    ctx.end(bytes, 0.0, nl);
+
+    // ---- a8-a13 ----
+    solve_stereo_batch(ctx, J, eP.p, eF.p, nullptr);
+
+    if (ctx.want_objective) {
+        ctx.begin("objective");
+        DevBuf<double> obj(K, s);
+        obj.zero();
+        int tot = J.totU + J.totW + E.totFeat + C.totFeat;
+        k_objective<<<ceil_div(tot, TB), TB, 0, s>>>(E.d.p, C.d.p, J.d.p, K, J.dUPre.p, J.dWPre.p, E.dFeatPre.p,
+                                                    C.dFeatPre.p, J.totU, J.totW, E.totFeat, C.totFeat,
+                                                    jointOfCur.p, obj.p);
+        std::vector<double> h = obj.to_host();
+        ctx.objectives.insert(ctx.objectives.end(), h.begin(), h.end());
+        ctx.end(0.0, 0.0, 1);
+    }
+    return out;
+}

@@ -1,0 +1,52 @@
+// Host-side interfaces of the batched ("segmented") device operators of the hot path.
+// Each operator processes EVERY map / join of one merge-tree level in a handful of launches.
+#pragma once
+#include "device.h"
+#include <vector>
+
+// Device view of the maps an operator works on: descriptor array + prefix sums of their sizes.
+struct OpMaps {
+    int K = 0;
+    std::vector<DMap> h;
+    std::vector<int> posePre, featPre, uPre, wPre;     // K+1 prefix sums
+    DevBuf<DMap> d;
+    DevBuf<int> dPosePre, dFeatPre, dUPre, dWPre;
+    int totPose = 0, totFeat = 0, totU = 0, totW = 0;
+    void build(const std::vector<MapHandle> &maps, cudaStream_t s);
+    void build(const std::vector<DMap> &maps, cudaStream_t s);
+};
+
+// R(map) of SURVEY 8(d): bytes of one map's arrays (stVal+stno, U+Ui+Uj, W+photo+feature, V+FBlock)
+static inline double map_bytes(const DMap &d)
+{
+    return 12.0 * (6.0 * d.m + 3.0 * d.n) + 296.0 * d.nU + 152.0 * d.nW + 76.0 * d.n;
+}
+
+// Allocate one arena holding `shapes.size()` maps with the given sizes; fills pointers of `out`.
+std::vector<MapHandle> alloc_maps(Context &ctx, std::vector<DMap> &shapes);
+
+// a2-a5: re-express each map in the frame of pose `newRef[k]` (LinearSFMImp.cpp:349-1924).
+std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<MapHandle> &in,
+                                              const std::vector<int> &newRef);
+
+// a6-a13: linear join of End[k] (already in Cur[k]'s frame) with Cur[k]
+// (LinearSFMImp.cpp:2551-2978 + 2119-2378). Returns the joint maps.
+std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHandle> &End,
+                                         const std::vector<MapHandle> &Cur);
+
+// a8-a13 alone: solve the joint system of every map given the right-hand sides
+// (LinearSFMImp.cpp:2119-2378). eP: concatenated 6m per map, eF: concatenated 3n per map.
+// Writes poseVal/featVal of the maps in place.
+struct SolveDebug;   // optional capture of pattern / ordering for the parity tests
+void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const double *eF,
+                        SolveDebug *dbg);
+
+struct SolveDebug {
+    // for the first map of the batch only
+    std::vector<int> rowptr, colidx;          // block CRS of S (reference's Sidxij, 2190-2205)
+    std::vector<double> S;                    // 36 per block, row-major, diagonal blocks full
+    std::vector<double> E;                    // reduced rhs
+    std::vector<int> perm;                    // block elimination ordering
+    std::vector<int> snode_first, snode_parent;
+    double chol_flops = 0.0;
+};

@@ -1,0 +1,88 @@
+// Merge-tree scheduler: row a14 of SURVEY 8(a).
+//
+// Reference: CLinearSFMImp::lmj_PF3D_Divide_ConquerStereo, LinearSFMImp.cpp:1926-2099 -- a
+// sequential loop over levels and pairs.  Here every level is ONE batch: all End maps of the level
+// are re-expressed in their partner's frame by one segmented Transform, all pairs are joined and
+// solved by one segmented Join/Solve, and the re-base of the odd outputs (1997-2025) is one more
+// segmented Transform.  Pairing, leftover handling (1940-1948) and the re-base rule are the
+// reference's, evaluated on GLOBAL output indices so that a rank owning a power-of-two aligned
+// slice of the leaves reproduces exactly what the sequential scheduler would do with that slice.
+#include "scheduler.h"
+#include <cstdio>
+
+std::vector<MapHandle> transform_or_pass(Context &ctx, const std::vector<MapHandle> &in,
+                                         const std::vector<int> &newRef)
+{
+    // maps already in the requested frame are passed through (LinearSFMImp.cpp:352-355)
+    std::vector<MapHandle> todo;
+    std::vector<int> refs, where;
+    for (size_t i = 0; i < in.size(); i++)
+        if (in[i].d.Ref != newRef[i]) { todo.push_back(in[i]); refs.push_back(newRef[i]); where.push_back((int)i); }
+    std::vector<MapHandle> done = transform_stereo_batch(ctx, todo, refs);
+    std::vector<MapHandle> out = in;
+    for (size_t j = 0; j < where.size(); j++) out[where[j]] = done[j];
+    return out;
+}
+
+std::vector<MapHandle> solve_tree_stereo(Context &ctx, std::vector<MapHandle> level, bool verbose,
+                                         int first_index, int max_levels)
+{
+    int L = 0;
+    long long base = first_index;             // global index of level[0] at the current level
+    while (level.size() > 1 && (max_levels < 0 || L < max_levels)) {
+        int count = (int)level.size();
+        int npairs = count / 2;
+        bool leftover = (count % 2) != 0;
+        if (base % 2 != 0) throw LsfmError(LSFM_ERR_ARG, "tree slice must start at an even index");
+        std::vector<MapHandle> E(npairs), C(npairs);
+        std::vector<int> refs(npairs);
+        for (int i = 0; i < npairs; i++) {
+            E[i] = level[2 * i];
+            C[i] = level[2 * i + 1];
+            refs[i] = C[i].d.Ref;
+            if (verbose) {
+                printf("Join Level %d Local Map %lld\n", L, base + 2 * i + 1);
+                printf("Join Level %d Local Map %lld\n", L, base + 2 * i + 2);
+                printf("Generate Level %d Local Map %lld\n\n", L + 1, base / 2 + i + 1);
+            }
+        }
+        if (verbose && leftover) {
+            printf("Join Level %d Local Map %lld\n", L, base + count);
+            printf("Generate Level %d Local Map %lld\n\n", L + 1, base / 2 + npairs + 1);
+        }
+        std::vector<MapHandle> Et = transform_or_pass(ctx, E, refs);
+        E.clear();
+        std::vector<MapHandle> next = join_stereo_batch(ctx, Et, C);
+        Et.clear(); C.clear();
+        if (leftover) next.push_back(level[count - 1]);
+        level.clear();
+        base /= 2;
+        // re-base every output with even (index+1) whose Ref is ahead of its first frame (1997-2025)
+        std::vector<MapHandle> rb;
+        std::vector<int> rbRef, rbIdx;
+        for (size_t i = 0; i < next.size(); i++) {
+            long long gi = base + (long long)i;
+            if ((gi + 1) % 2 == 0 && next[i].d.Ref > next[i].d.FRef) {
+                rb.push_back(next[i]); rbRef.push_back(next[i].d.FRef); rbIdx.push_back((int)i);
+            }
+        }
+        if (!rb.empty()) {
+            std::vector<MapHandle> done = transform_stereo_batch(ctx, rb, rbRef);
+            for (size_t j = 0; j < rbIdx.size(); j++) next[rbIdx[j]] = done[j];
+        }
+        level = std::move(next);
+        L++;
+    }
+    return level;
+}
+
+MapHandle final_rebase_stereo(Context &ctx, const MapHandle &root)
+{
+    // final re-base to the first frame (LinearSFMImp.cpp:2039-2063)
+    if (root.d.Ref > root.d.FRef) {
+        std::vector<MapHandle> in{root};
+        std::vector<int> ref{root.d.FRef};
+        return transform_stereo_batch(ctx, in, ref)[0];
+    }
+    return root;
+}

@@ -1,0 +1,515 @@
+// Batched solve of the joint linear systems: rows a8-a13 of SURVEY 8(a).
+//
+// Reference: CLinearSFMImp::lmj_solveLinearSFMStereo, LinearSFMImp.cpp:2119-2378
+//   block mask / Sidxij (O(m^2) char mask)       2131-2205  -> sorted unique pair keys (O(nnz))
+//   pba_inverseV                                  3022-3042
+//   S = U - W V^-1 W^T,  E = ea - W V^-1 eb       2214-2332
+//   CSC build + CHOLMOD (AMD, factorize, solve)   2334-2361, 2380-2549 -> block multifrontal
+//                                                 Cholesky on the GPU (chol_symbolic.cpp + here)
+//   pba_solveFeatures                             2980-3020
+#include "ops.h"
+#include "chol_symbolic.h"
+#include "small_mat.cuh"
+#include <cub/cub.cuh>
+#include <thread>
+
+namespace {
+
+typedef unsigned long long u64;
+__host__ __device__ inline u64 pair_key(int k, int a, int b)
+{
+    int lo = a < b ? a : b, hi = a < b ? b : a;
+    return ((u64)(unsigned)k << 44) | ((u64)(unsigned)lo << 22) | (u64)(unsigned)hi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8: block pattern of S.  A feature whose observer list equals the previous feature's adds no
+// new pairs (consecutive features almost always share their observers), so only "changed" features
+// emit their k(k+1)/2 pairs; sort + unique gives the reference's row-major CRS order.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool same_observers(const DMap &M, int f)
+{
+    if (f == 0) return false;
+    int a0 = M.wPtr[f - 1], a1 = M.wPtr[f], b1 = M.wPtr[f + 1];
+    if (a1 - a0 != b1 - a1) return false;
+    for (int i = 0; i < a1 - a0; i++)
+        if (M.photo[a0 + i] != M.photo[a1 + i]) return false;
+    return true;
+}
+
+__global__ void k_pat_count(const DMap *__restrict__ J, const int *__restrict__ featPre, int K,
+                            int totF, int totU, int *__restrict__ cnt)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > totF + totU) return;
+    if (g == totF + totU) { cnt[g] = 0; return; }
+    if (g >= totF) { cnt[g] = 1; return; }
+    int k = seg_find(featPre, K, g);
+    int f = g - featPre[k];
+    const DMap &M = J[k];
+    int kf = M.wPtr[f + 1] - M.wPtr[f];
+    cnt[g] = same_observers(M, f) ? 0 : kf * (kf + 1) / 2;
+}
+
+__global__ void k_pat_emit(const DMap *__restrict__ J, const int *__restrict__ featPre,
+                           const int *__restrict__ uPre, int K, int totF, int totU,
+                           const int *__restrict__ scan, u64 *__restrict__ keys)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totF + totU) return;
+    int o = scan[g];
+    if (g >= totF) {
+        int u = g - totF;
+        int k = seg_find(uPre, K, u);
+        int b = u - uPre[k];
+        keys[o] = pair_key(k, J[k].Ui[b], J[k].Uj[b]);
+        return;
+    }
+    if (scan[g + 1] == o) return;
+    int k = seg_find(featPre, K, g);
+    int f = g - featPre[k];
+    const DMap &M = J[k];
+    int w0 = M.wPtr[f], w1 = M.wPtr[f + 1];
+    for (int a = w0; a < w1; a++)
+        for (int b = a; b < w1; b++) keys[o++] = pair_key(k, M.photo[a], M.photo[b]);
+}
+
+// rowPtr[global pose] = first slot of that block row (keys are sorted by join,row,col)
+__global__ void k_rowptr(const u64 *__restrict__ keys, int n, const int *__restrict__ posePre, int K,
+                         int totP, int *__restrict__ rowPtr)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > totP) return;
+    if (g == totP) { rowPtr[g] = n; return; }
+    int k = seg_find(posePre, K, g);
+    int p = g - posePre[k];
+    u64 key = ((u64)(unsigned)k << 44) | ((u64)(unsigned)p << 22);
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    rowPtr[g] = lo;
+}
+
+__device__ __forceinline__ int find_slot(const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
+                                         int gposeRow, u64 key)
+{
+    int lo = rowPtr[gposeRow], hi = rowPtr[gposeRow + 1];
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;          // the pattern contains every queried pair by construction
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9: V^-1 by the cofactor formula Eigen's Matrix3d::inverse uses, symmetrised from the upper
+// triangle exactly as pba_inverseV does (LinearSFMImp.cpp:3035-3040)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_vinv(const DMap *__restrict__ J, const int *__restrict__ featPre, int K, int totF,
+                       double *__restrict__ Vinv)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totF) return;
+    int k = seg_find(featPre, K, g);
+    int f = g - featPre[k];
+    double a[9];
+    sm::load<9>(J[k].V + 9 * (size_t)f, a);
+    double c00 = a[4] * a[8] - a[5] * a[7];
+    double c10 = a[5] * a[6] - a[3] * a[8];     // cofactor of (1,0)... first-column cofactors
+    double c20 = a[3] * a[7] - a[4] * a[6];
+    double det = a[0] * c00 + a[1] * c10 + a[2] * c20;
+    double id = 1.0 / det;
+    double i00 = c00 * id;
+    double i01 = (a[2] * a[7] - a[1] * a[8]) * id;
+    double i02 = (a[1] * a[5] - a[2] * a[4]) * id;
+    double i11 = (a[0] * a[8] - a[2] * a[6]) * id;
+    double i12 = (a[2] * a[3] - a[0] * a[5]) * id;
+    double i22 = (a[0] * a[4] - a[1] * a[3]) * id;
+    double *o = Vinv + 9 * (size_t)g;
+    o[0] = i00; o[1] = i01; o[2] = i02;
+    o[3] = i01; o[4] = i11; o[5] = i12;
+    o[6] = i02; o[7] = i12; o[8] = i22;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a10: S = U - W V^-1 W^T, E = eP - W V^-1 eF
+// ---------------------------------------------------------------------------------------------
+__global__ void k_s_from_u(const DMap *__restrict__ J, const int *__restrict__ uPre,
+                           const int *__restrict__ posePre, int K, int totU,
+                           const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
+                           double *__restrict__ S)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totU) return;
+    int k = seg_find(uPre, K, g);
+    int b = g - uPre[k];
+    int i = J[k].Ui[b], j = J[k].Uj[b];
+    int slot = find_slot(keys, rowPtr, posePre[k] + i, pair_key(k, i, j));
+    const double *u = J[k].U + 36 * (size_t)b;
+    double *s = S + 36 * (size_t)slot;
+    // blocks of one list are distinct in stereo; atomics keep the mono duplicate case (+=) valid
+#pragma unroll
+    for (int q = 0; q < 36; q++) atomicAdd(s + q, u[q]);
+}
+
+// v1: one thread per (W block a); loops over the blocks b of the same feature with photo_b >= photo_a
+__global__ void __launch_bounds__(128)
+k_schur(const DMap *__restrict__ J, const int *__restrict__ wPre, const int *__restrict__ featPre,
+        const int *__restrict__ posePre, int K, int totW, const double *__restrict__ Vinv,
+        const double *__restrict__ eF, const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
+        double *__restrict__ S, double *__restrict__ E)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = g < totW;
+    int k = live ? seg_find(wPre, K, g) : 0;
+    int a = live ? g - wPre[k] : 0;
+    const DMap &M = J[k];
+    int f = live ? M.feature[a] : 0;
+    int pa = live ? M.photo[a] : 0;
+    double WV[18], y[6];
+    if (live) {
+        double W[18], Vi[9];
+        sm::load<18>(M.W + 18 * (size_t)a, W);
+        sm::load<9>(Vinv + 9 * (size_t)(featPre[k] + f), Vi);
+        sm::mmt<6, 3, 3>(W, Vi, WV);                       // WV[i][j] = sum_k W[i][k] Vinv[j][k] (2269-2270)
+        double ef[3];
+        sm::load<3>(eF + 3 * (size_t)(featPre[k] + f), ef);
+        sm::mm<6, 3, 1>(WV, ef, y);
+#pragma unroll
+        for (int q = 0; q < 6; q++) y[q] = -y[q];
+    }
+    sm::warp_agg_atomic_add<6>(E + 6 * (size_t)(posePre[k] + pa), y, live);
+    if (!live) return;
+    int w0 = M.wPtr[f], w1 = M.wPtr[f + 1];
+    for (int b = w0; b < w1; b++) {
+        int pb = M.photo[b];
+        if (pb < pa) continue;
+        double Wb[18], P[36];
+        sm::load<18>(M.W + 18 * (size_t)b, Wb);
+        sm::mmt<6, 3, 6>(WV, Wb, P);
+        int slot = find_slot(keys, rowPtr, posePre[k] + pa, pair_key(k, pa, pb));
+        double *s = S + 36 * (size_t)slot;
+#pragma unroll
+        for (int q = 0; q < 36; q++) atomicAdd(s + q, -P[q]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a11-a12: numeric block multifrontal Cholesky with the right-hand side carried as an extra row
+// ---------------------------------------------------------------------------------------------
+__global__ void k_front_assemble(const SlotMap *__restrict__ slot, int nslot,
+                                 const SnodeDesc *__restrict__ sn, const double *__restrict__ S,
+                                 double *__restrict__ fronts)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = g / 36, e = g - 36 * i;
+    if (i >= nslot) return;
+    SlotMap m = slot[i];
+    const SnodeDesc &d = sn[m.sn];
+    int ld = 6 * (d.ncols + d.nstruct) + 1;
+    int x = e / 6, y = e - 6 * x;                       // front block entry (x,y)
+    double v = m.transpose ? S[36 * (size_t)i + 6 * y + x] : S[36 * (size_t)i + 6 * x + y];
+    fronts[d.frontOff + (size_t)(6 * m.lcol + y) * ld + 6 * m.lrow + x] = v;
+}
+
+__global__ void k_front_rhs(const int *__restrict__ poseSn, const int *__restrict__ poseLcol, int totP,
+                            const SnodeDesc *__restrict__ sn, const double *__restrict__ E,
+                            double *__restrict__ fronts)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = g / 6, q = g - 6 * p;
+    if (p >= totP) return;
+    const SnodeDesc &d = sn[poseSn[p]];
+    int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1;
+    fronts[d.frontOff + (size_t)(6 * poseLcol[p] + q) * ld + fs] = E[6 * (size_t)p + q];
+}
+
+// one CTA per front of the level: extend-add the children, factor the leading ncols block columns,
+// leave the Schur complement (+ updated rhs row) in place for the parent.
+__global__ void __launch_bounds__(256)
+k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
+               const int *__restrict__ childIdx, const int *__restrict__ relIdx,
+               double *__restrict__ fronts, int *__restrict__ errflag)
+{
+    const SnodeDesc d = sn[levelSn[blockIdx.x]];
+    double *F = fronts + d.frontOff;
+    const int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1, nc = 6 * d.ncols;
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    for (int ci = 0; ci < d.nchild; ci++) {
+        const SnodeDesc c = sn[childIdx[d.childOff + ci]];
+        const double *Fc = fronts + c.frontOff;
+        const int ncc = 6 * c.ncols, us = 6 * c.nstruct, ldc = 6 * (c.ncols + c.nstruct) + 1;
+        const int *rel = relIdx + c.structOff;
+        const int rows = us + 1;
+        for (int t = tid; t < rows * us; t += nt) {
+            int cc = t / rows, r = t - cc * rows;
+            if (r < cc) continue;
+            int pr = (r == us) ? fs : 6 * rel[r / 6] + (r % 6);
+            int pc = 6 * rel[cc / 6] + (cc % 6);
+            F[(size_t)pc * ld + pr] += Fc[(size_t)(ncc + cc) * ldc + ncc + r];
+        }
+        __syncthreads();
+    }
+
+    for (int c0 = 0; c0 < nc; c0 += 6) {
+        if (tid == 0) {
+            // 6x6 Cholesky of the diagonal block, in place (lower)
+            for (int j = 0; j < 6; j++) {
+                double djj = F[(size_t)(c0 + j) * ld + c0 + j];
+                for (int p = 0; p < j; p++) { double l = F[(size_t)(c0 + p) * ld + c0 + j]; djj -= l * l; }
+                if (!(djj > 0.0)) { atomicOr(errflag, 1); djj = 1.0; }
+                djj = sqrt(djj);
+                F[(size_t)(c0 + j) * ld + c0 + j] = djj;
+                for (int i = j + 1; i < 6; i++) {
+                    double v = F[(size_t)(c0 + j) * ld + c0 + i];
+                    for (int p = 0; p < j; p++)
+                        v -= F[(size_t)(c0 + p) * ld + c0 + i] * F[(size_t)(c0 + p) * ld + c0 + j];
+                    F[(size_t)(c0 + j) * ld + c0 + i] = v / djj;
+                }
+            }
+        }
+        __syncthreads();
+        // panel: rows below the diagonal block (including the rhs row fs)
+        for (int r = c0 + 6 + tid; r <= fs; r += nt) {
+            double x[6];
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                double v = F[(size_t)(c0 + q) * ld + r];
+#pragma unroll
+                for (int p = 0; p < q; p++) v -= x[p] * F[(size_t)(c0 + p) * ld + c0 + q];
+                x[q] = v / F[(size_t)(c0 + q) * ld + c0 + q];
+            }
+#pragma unroll
+            for (int q = 0; q < 6; q++) F[(size_t)(c0 + q) * ld + r] = x[q];
+        }
+        __syncthreads();
+        // trailing update (lower triangle + rhs row)
+        const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+        for (int c = c0 + 6 + warp; c < fs; c += nw) {
+            double lc[6];
+#pragma unroll
+            for (int q = 0; q < 6; q++) lc[q] = F[(size_t)(c0 + q) * ld + c];
+            for (int r = c + lane; r <= fs; r += 32) {
+                double v = F[(size_t)c * ld + r];
+#pragma unroll
+                for (int q = 0; q < 6; q++) v -= F[(size_t)(c0 + q) * ld + r] * lc[q];
+                F[(size_t)c * ld + r] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// top-down: x_J = L11^-T (y_J - L21^T x_struct); xperm holds the solution in elimination order
+__global__ void __launch_bounds__(128)
+k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
+                  const int *__restrict__ structIdx, const double *__restrict__ fronts,
+                  double *__restrict__ xperm)
+{
+    const SnodeDesc d = sn[levelSn[blockIdx.x]];
+    const double *F = fronts + d.frontOff;
+    const int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1, nc = 6 * d.ncols, us = 6 * d.nstruct;
+    extern __shared__ double sh[];
+    double *xs = sh;            // us entries: solution at the struct rows
+    double *t = sh + us;        // nc entries
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    double *xj = xperm + 6 * (size_t)d.poseOff;
+    for (int i = tid; i < us; i += nt) xs[i] = xj[6 * structIdx[d.structOff + i / 6] + (i % 6)];
+    __syncthreads();
+    for (int c = warp; c < nc; c += nw) {
+        double acc = 0.0;
+        for (int r = lane; r < us; r += 32) acc += F[(size_t)c * ld + nc + r] * xs[r];
+        acc = sm::warp_sum(acc);
+        if (lane == 0) t[c] = F[(size_t)c * ld + fs] - acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int c = nc - 1; c >= 0; c--) {
+            double acc = 0.0;
+            for (int r = c + 1 + lane; r < nc; r += 32) acc += F[(size_t)c * ld + r] * t[r];
+            acc = sm::warp_sum(acc);
+            if (lane == 0) t[c] = (t[c] - acc) / F[(size_t)c * ld + c];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < nc; c += nt) xj[6 * (size_t)d.first + c] = t[c];
+}
+
+__global__ void k_unpermute(DMap *__restrict__ J, const int *__restrict__ posePre, int K, int totP,
+                            const int *__restrict__ perm, const double *__restrict__ xperm)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int gp = g / 6, q = g - 6 * gp;
+    if (gp >= totP) return;
+    int k = seg_find(posePre, K, gp);
+    J[k].poseVal[6 * (size_t)perm[gp] + q] = xperm[6 * (size_t)gp + q];
+}
+
+// a13: x_f = V^-1 (eF_f - sum_p W_pf^T x_p)      (LinearSFMImp.cpp:2980-3020)
+__global__ void k_backsub(DMap *__restrict__ J, const int *__restrict__ featPre, int K, int totF,
+                          const double *__restrict__ Vinv, const double *__restrict__ eF)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totF) return;
+    int k = seg_find(featPre, K, g);
+    int f = g - featPre[k];
+    const DMap &M = J[k];
+    double acc[3] = {0, 0, 0};
+    for (int j = M.wPtr[f]; j < M.wPtr[f + 1]; j++) {
+        double W[18], xp[6], t[3];
+        sm::load<18>(M.W + 18 * (size_t)j, W);
+        sm::load<6>(M.poseVal + 6 * (size_t)M.photo[j], xp);
+        sm::mtm<3, 6, 1>(W, xp, t);
+        acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2];
+    }
+    double r[3] = {eF[3 * (size_t)g] - acc[0], eF[3 * (size_t)g + 1] - acc[1], eF[3 * (size_t)g + 2] - acc[2]};
+    double Vi[9], x[3];
+    sm::load<9>(Vinv + 9 * (size_t)g, Vi);
+    sm::mm<3, 3, 1>(Vi, r, x);
+    double *o = M.featVal + 3 * (size_t)f;
+    o[0] = x[0]; o[1] = x[1]; o[2] = x[2];
+}
+
+void exclusive_scan(Context &ctx, const int *in, int *out, int n)
+{
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, n, ctx.stream);
+    DevBuf<char> tmp(tmp_bytes, ctx.stream);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, n, ctx.stream);
+}
+
+} // namespace
+
+void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const double *eF,
+                        SolveDebug *dbg)
+{
+    const int K = J.K;
+    cudaStream_t s = ctx.stream;
+    const int TB = 256;
+    int nl = 0;
+
+    // ---- a8: pattern ----
+    ctx.begin("solve.pattern");
+    int nItems = J.totFeat + J.totU;
+    DevBuf<int> pcnt(nItems + 1, s), pscan(nItems + 1, s);
+    k_pat_count<<<ceil_div(nItems + 1, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, K, J.totFeat, J.totU, pcnt.p); nl++;
+    exclusive_scan(ctx, pcnt.p, pscan.p, nItems + 1); nl += 2;
+    int nRaw = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&nRaw, pscan.p + nItems, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    DevBuf<u64> rawKeys(nRaw, s), sortedKeys(nRaw, s), keys(nRaw, s);
+    k_pat_emit<<<ceil_div(nItems, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, J.dUPre.p, K, J.totFeat, J.totU, pscan.p, rawKeys.p); nl++;
+    {
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tb, rawKeys.p, sortedKeys.p, nRaw, 0, 64, s);
+        DevBuf<char> tmp(tb, s);
+        cub::DeviceRadixSort::SortKeys(tmp.p, tb, rawKeys.p, sortedKeys.p, nRaw, 0, 64, s); nl += 8;
+    }
+    DevBuf<int> dNuis(1, s);
+    {
+        size_t tb = 0;
+        cub::DeviceSelect::Unique(nullptr, tb, sortedKeys.p, keys.p, dNuis.p, nRaw, s);
+        DevBuf<char> tmp(tb, s);
+        cub::DeviceSelect::Unique(tmp.p, tb, sortedKeys.p, keys.p, dNuis.p, nRaw, s); nl += 2;
+    }
+    int nuis = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&nuis, dNuis.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    DevBuf<int> rowPtr(J.totPose + 1, s);
+    k_rowptr<<<ceil_div(J.totPose + 1, TB), TB, 0, s>>>(keys.p, nuis, J.dPosePre.p, K, J.totPose, rowPtr.p); nl++;
+    // pattern to the host for the symbolic phase (overlaps with the Schur kernels below)
+    std::vector<u64> hKeys(nuis);
+    std::vector<int> hRowPtr(J.totPose + 1);
+    CUDA_CHECK(cudaMemcpyAsync(hKeys.data(), keys.p, sizeof(u64) * nuis, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(hRowPtr.data(), rowPtr.p, sizeof(int) * (J.totPose + 1), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    KERNEL_CHECK();
+    ctx.end(8.0 * nRaw, 0.0, nl);
+    nl = 0;
+
+    // ---- a9-a10: V^-1, S, E ----
+    ctx.begin("solve.schur");
+    DevBuf<double> Vinv(9 * (size_t)J.totFeat, s), S(36 * (size_t)nuis, s), E(6 * (size_t)J.totPose, s);
+    S.zero();
+    CUDA_CHECK(cudaMemcpyAsync(E.p, eP, sizeof(double) * 6 * (size_t)J.totPose, cudaMemcpyDeviceToDevice, s));
+    if (J.totFeat > 0) { k_vinv<<<ceil_div(J.totFeat, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, K, J.totFeat, Vinv.p); nl++; }
+    if (J.totU > 0) {
+        k_s_from_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, J.dPosePre.p, K, J.totU, keys.p, rowPtr.p, S.p); nl++;
+    }
+    if (J.totW > 0) {
+        k_schur<<<ceil_div(J.totW, 128), 128, 0, s>>>(J.d.p, J.dWPre.p, J.dFeatPre.p, J.dPosePre.p, K, J.totW,
+                                                     Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p); nl++;
+    }
+    KERNEL_CHECK();
+
+    // ---- symbolic on the host while the GPU accumulates S ----
+    std::vector<int> mvec(K), sOff(K + 1);
+    for (int k = 0; k < K; k++) { mvec[k] = J.h[k].m; sOff[k] = hRowPtr[J.posePre[k]]; }
+    sOff[K] = nuis;
+    BatchSymbolic sym;
+    try {
+        build_symbolic(K, mvec, J.posePre, hKeys, sOff, sym, (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+    } catch (const std::exception &e) { throw LsfmError(LSFM_ERR_ARG, std::string("symbolic: ") + e.what()); }
+    double schur_bytes = 152.0 * J.totW + 72.0 * J.totFeat + 288.0 * nuis + 296.0 * J.totU;
+    ctx.end(schur_bytes, 0.0, nl);
+    nl = 0;
+
+    // ---- numeric ----
+    ctx.begin("solve.cholesky");
+    int ns = (int)sym.sn.size();
+    DevBuf<SnodeDesc> dSn(ns, s); dSn.upload(sym.sn);
+    DevBuf<int> dStruct(sym.structIdx.size(), s); dStruct.upload(sym.structIdx);
+    DevBuf<int> dRel(sym.relIdx.size(), s); dRel.upload(sym.relIdx);
+    DevBuf<int> dChild(sym.childIdx.size(), s); dChild.upload(sym.childIdx);
+    DevBuf<int> dLevelSn(sym.levelSn.size(), s); dLevelSn.upload(sym.levelSn);
+    DevBuf<SlotMap> dSlot(sym.slot.size(), s); dSlot.upload(sym.slot);
+    DevBuf<int> dPoseSn(J.totPose, s); dPoseSn.upload(sym.poseSn);
+    DevBuf<int> dPoseLcol(J.totPose, s); dPoseLcol.upload(sym.poseLcol);
+    DevBuf<int> dPerm(J.totPose, s); dPerm.upload(sym.perm);
+    DevBuf<double> fronts((size_t)sym.frontDoubles, s);
+    fronts.zero();
+    DevBuf<double> xperm(6 * (size_t)J.totPose, s);
+    DevBuf<int> err(1, s); err.zero();
+    if (nuis > 0) { k_front_assemble<<<ceil_div(36ll * nuis, TB), TB, 0, s>>>(dSlot.p, nuis, dSn.p, S.p, fronts.p); nl++; }
+    k_front_rhs<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(dPoseSn.p, dPoseLcol.p, J.totPose, dSn.p, E.p, fronts.p); nl++;
+    int nLevels = (int)sym.levelPtr.size() - 1;
+    for (int l = 0; l < nLevels; l++) {
+        int cnt = sym.levelPtr[l + 1] - sym.levelPtr[l];
+        if (cnt == 0) continue;
+        k_front_factor<<<cnt, 256, 0, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p); nl++;
+    }
+    size_t shb = sizeof(double) * 6 * (size_t)(sym.maxFdim + 1);
+    if (shb > 48 * 1024)
+        CUDA_CHECK(cudaFuncSetAttribute(k_front_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
+    for (int l = nLevels - 1; l >= 0; l--) {
+        int cnt = sym.levelPtr[l + 1] - sym.levelPtr[l];
+        if (cnt == 0) continue;
+        k_front_backsolve<<<cnt, 128, shb, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dStruct.p, fronts.p, xperm.p); nl++;
+    }
+    k_unpermute<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(J.d.p, J.dPosePre.p, K, J.totPose, dPerm.p, xperm.p); nl++;
+    int herr = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    KERNEL_CHECK();
+    ctx.end(0.0, sym.flops, nl);
+    nl = 0;
+    if (herr) throw LsfmError(LSFM_ERR_NOT_SPD, "reduced camera system is not positive definite");
+
+    // ---- a13 ----
+    ctx.begin("solve.backsub");
+    if (J.totFeat > 0) { k_backsub<<<ceil_div(J.totFeat, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, K, J.totFeat, Vinv.p, eF); nl++; }
+    KERNEL_CHECK();
+    ctx.end(144.0 * J.totW + 96.0 * J.totFeat + 8.0 * (6.0 * J.totPose + 3.0 * J.totFeat), 0.0, nl);
+
+    if (dbg) {
+        int m0 = J.h[0].m, n0 = sOff[1];
+        dbg->rowptr.assign(hRowPtr.begin(), hRowPtr.begin() + m0 + 1);
+        dbg->colidx.resize(n0);
+        for (int i = 0; i < n0; i++) dbg->colidx[i] = (int)(hKeys[i] & ((1ull << 22) - 1));
+        dbg->S.resize(36 * (size_t)n0);
+        dbg->E.resize(6 * (size_t)m0);
+        CUDA_CHECK(cudaMemcpyAsync(dbg->S.data(), S.p, sizeof(double) * 36 * (size_t)n0, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(dbg->E.data(), E.p, sizeof(double) * 6 * (size_t)m0, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        dbg->perm.assign(sym.perm.begin(), sym.perm.begin() + m0);
+        dbg->chol_flops = sym.flops;
+    }
+}

@@ -1,0 +1,45 @@
+"""Drop-in file formats: our C++ reader/writers vs the reference's own (through the oracle)."""
+import ctypes as C
+import filecmp
+import os
+
+import numpy as np
+
+from linearsfm_b200 import _lib, api, synth
+from linearsfm_b200.localmap import write_localmap, read_localmap
+from util import assert_maps_match
+
+
+def test_reader_matches_reference(oracle, tmp_path):
+    maps = synth.make_stereo_scene(3, feats_per_frame=10, seed=5)
+    for i, lm in enumerate(maps):
+        p = str(tmp_path / f"localmap_{i + 1}.txt")
+        write_localmap(p, lm)
+        ref = oracle.load_localmap_stereo(p)
+        out = _lib.LsfmMap()
+        _lib.check(_lib.lib().lsfm_load_localmap_stereo(p.encode(), C.byref(out)))
+        got = api.from_c(out)
+        assert_maps_match(got, ref, tol_state=0, tol_info=0, what="reader")
+        assert_maps_match(got, lm, tol_state=0, tol_info=0, what="round trip")
+        assert_maps_match(read_localmap(p), lm, tol_state=0, tol_info=0, what="python reader")
+
+
+def test_reader_errors(tmp_path):
+    out = _lib.LsfmMap()
+    assert _lib.lib().lsfm_load_localmap_stereo(str(tmp_path / "nope.txt").encode(), C.byref(out)) == 5
+    p = tmp_path / "bad.txt"
+    p.write_text("1\n9\n-2 0.5\n")
+    assert _lib.lib().lsfm_load_localmap_stereo(str(p).encode(), C.byref(out)) == 6
+
+
+def test_writers_match_reference(oracle, tmp_path):
+    maps = synth.make_stereo_scene(4, feats_per_frame=10, seed=6)
+    fin, _, _ = oracle.run_tree_stereo(maps)
+    oracle.save_outputs(fin, st=str(tmp_path / "st_ref.txt"), pose=str(tmp_path / "p_ref.txt"),
+                        feat=str(tmp_path / "f_ref.txt"))
+    c, _keep = api.to_c(fin)
+    rc = _lib.lib().lsfm_save_outputs(C.byref(c), str(tmp_path / "st.txt").encode(),
+                                      str(tmp_path / "p.txt").encode(), str(tmp_path / "f.txt").encode())
+    assert rc == 0
+    for a in ("st", "p", "f"):
+        assert filecmp.cmp(tmp_path / f"{a}.txt", tmp_path / f"{a}_ref.txt", shallow=False), a

@@ -1,0 +1,48 @@
+"""Integer parity of the elimination ordering: the product's LSFM-ND routine (C++,
+linearsfm_b200/csrc/chol_symbolic.cpp) vs the oracle shim's independent implementation
+(oracle/cholmod_shim.c) on random and band+arrow block patterns."""
+import numpy as np
+import pytest
+
+from linearsfm_b200 import api
+
+
+def upper_csc(m, pairs):
+    cols = [set() for _ in range(m)]
+    for a, b in pairs:
+        lo, hi = min(a, b), max(a, b)
+        cols[hi].add(lo)
+    for j in range(m):
+        cols[j].add(j)
+    Ap = np.cumsum([0] + [len(c) for c in cols]).astype(np.int32)
+    Ai = np.array([r for c in cols for r in sorted(c)], np.int32)
+    return Ap, Ai
+
+
+def band_arrow(m, band, hubs, rng):
+    pairs = [(i, j) for i in range(m) for j in range(i + 1, min(m, i + band + 1))]
+    for h in hubs:
+        pairs += [(h, j) for j in range(m) if j != h]
+    extra = rng.integers(0, m, size=(m // 10, 2))
+    pairs += [tuple(x) for x in extra if x[0] != x[1]]
+    return pairs
+
+
+@pytest.mark.parametrize("m", [1, 2, 7, 32, 33, 40, 64, 100, 257, 1000, 3499])
+def test_ordering_matches_oracle(oracle, m):
+    rng = np.random.default_rng(m)
+    hubs = list(rng.choice(m, size=min(m, max(0, int(np.log2(m + 1)) * 2 - 2)), replace=False)) if m > 8 else []
+    Ap, Ai = upper_csc(m, band_arrow(m, 5, hubs, rng))
+    p_ref = oracle.shim_order(Ap, Ai)
+    p_got = api.block_ordering(Ap, Ai)
+    assert sorted(p_got.tolist()) == list(range(m))
+    assert np.array_equal(p_got, p_ref)
+
+
+@pytest.mark.parametrize("m,dens", [(50, 0.05), (50, 0.5), (200, 0.02), (200, 0.3), (600, 0.01)])
+def test_ordering_random(oracle, m, dens):
+    rng = np.random.default_rng(int(m * 1000 * dens))
+    mask = rng.random((m, m)) < dens
+    pairs = [(i, j) for i in range(m) for j in range(i + 1, m) if mask[i, j]]
+    Ap, Ai = upper_csc(m, pairs)
+    assert np.array_equal(api.block_ordering(Ap, Ai), oracle.shim_order(Ap, Ai))
