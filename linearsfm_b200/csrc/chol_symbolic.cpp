@@ -9,19 +9,21 @@
 // produces on the band+arrow structure of sequential map joining.
 #include "chol_symbolic.h"
 #include <algorithm>
-#include <cmath>
 #include <thread>
 #include <stdexcept>
 #include <string>
 
-static int isqrt_floor(int n)
-{
-    int r = (int)std::floor(std::sqrt((double)n));
-    while ((long long)r * r > n) r--;
-    while ((long long)(r + 1) * (r + 1) <= n) r++;
-    return r;
-}
-
+// LSFM-ND (spec, also in DESIGN.md):
+//   m <= 32: identity, one node.
+//   dissect(L) on an ascending vertex list:
+//     |L| <= 8            -> emit L (one node)
+//     A = first |L|/2 vertices, B = the rest; cross edges = edges of the graph between A and B;
+//     separator S = greedy vertex cover of the cross edges: repeatedly take the vertex with the
+//       most uncovered cross edges (tie: smallest index) until none is left;
+//     dissect(A \ S), dissect(B \ S), then emit S ascending (one node).
+// The map-joining index order is [End poses, Cur poses] recursively, so index bisection follows the
+// merge tree; the vertex cover puts the few "hub" poses (former frame origins, adjacent to a whole
+// sub-map) into the separators instead of their many neighbours.
 void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm,
                    std::vector<int> &nodes)
 {
@@ -33,18 +35,15 @@ void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm
         if (m > 0) nodes.push_back(m);
         return;
     }
-    int tau = std::max(16, std::min(m / 2, 10 * isqrt_floor(m)));
-    std::vector<char> dense(m, 0);
-    std::vector<int> rest;
-    rest.reserve(m);
-    for (int v = 0; v < m; v++) {
-        if (ptr[v + 1] - ptr[v] > tau) dense[v] = 1; else rest.push_back(v);
-    }
-    // explicit work stack of vertex lists; `emit` entries are separators waiting for their subtrees
     struct Item { std::vector<int> L; bool emit; };
     std::vector<Item> stack;
-    stack.push_back({std::move(rest), false});
-    std::vector<char> inB(m, 0);
+    {
+        std::vector<int> all(m);
+        for (int i = 0; i < m; i++) all[i] = i;
+        stack.push_back({std::move(all), false});
+    }
+    std::vector<char> side(m, 0);        // 1 = in A, 2 = in B, 3 = chosen for the separator
+    std::vector<int> cnt(m, 0);
     while (!stack.empty()) {
         Item it = std::move(stack.back());
         stack.pop_back();
@@ -56,27 +55,43 @@ void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm
             continue;
         }
         size_t h = L.size() / 2;
-        for (size_t i = h; i < L.size(); i++) inB[L[i]] = 1;
-        std::vector<int> keep, sep;
-        for (size_t i = 0; i < h; i++) {
-            int a = L[i];
-            bool hit = false;
-            for (int p = ptr[a]; p < ptr[a + 1]; p++) {
-                int w = adj[p];
-                if (!dense[w] && inB[w]) { hit = true; break; }
-            }
-            (hit ? sep : keep).push_back(a);
+        for (size_t i = 0; i < L.size(); i++) side[L[i]] = i < h ? 1 : 2;
+        long long uncovered = 0;
+        for (int v : L) {
+            int c = 0;
+            char other = side[v] == 1 ? 2 : 1;
+            for (int p = ptr[v]; p < ptr[v + 1]; p++) c += (side[adj[p]] == other);
+            cnt[v] = c;
+            uncovered += c;
         }
-        std::vector<int> B(L.begin() + h, L.end());
-        for (int b : B) inB[b] = 0;
-        // elimination order: keep-subtree, B-subtree, separator  => push in reverse
+        uncovered /= 2;
+        std::vector<int> sep;
+        while (uncovered > 0) {
+            int best = -1, bc = 0;
+            for (int v : L)
+                if (cnt[v] > bc) { bc = cnt[v]; best = v; }     // ascending scan: ties keep the smallest index
+            char other = side[best] == 1 ? 2 : 1;
+            for (int p = ptr[best]; p < ptr[best + 1]; p++) {
+                int w = adj[p];
+                if (side[w] == other) cnt[w]--;
+            }
+            uncovered -= bc;
+            cnt[best] = 0;
+            side[best] = 3;
+            sep.push_back(best);
+        }
+        std::sort(sep.begin(), sep.end());
+        std::vector<int> A, B;
+        for (size_t i = 0; i < L.size(); i++) {
+            int v = L[i];
+            if (side[v] == 1) A.push_back(v); else if (side[v] == 2) B.push_back(v);
+        }
+        for (int v : L) { side[v] = 0; cnt[v] = 0; }
+        // elimination order: A-subtree, B-subtree, separator  => push in reverse
         stack.push_back({std::move(sep), true});
         stack.push_back({std::move(B), false});
-        stack.push_back({std::move(keep), false});
+        stack.push_back({std::move(A), false});
     }
-    size_t before = perm.size();
-    for (int v = 0; v < m; v++) if (dense[v]) perm.push_back(v);
-    if (perm.size() > before) nodes.push_back((int)perm.size());
 }
 
 namespace {

@@ -88,14 +88,14 @@ static void cap_dbls(double **dst, const double *src, size_t n)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* LSFM-ND ordering (spec in DESIGN.md): naive reference implementation                       */
-/*   n <= 32                 : identity                                                        */
-/*   tau = max(16, min(n/2, 10*floor(sqrt(n))))                                                */
-/*   D = { v : deg(v) > tau } ordered last, ascending                                          */
-/*   R = rest ascending; dissect(R):                                                           */
+/* LSFM-ND ordering (spec in DESIGN.md): naive recursive reference implementation             */
+/*   n <= 32 : identity                                                                        */
+/*   dissect(L), L ascending:                                                                  */
 /*       |L| <= 8 : emit L                                                                     */
-/*       A = first floor(|L|/2), B = rest; S = { a in A adjacent to some b in B }              */
-/*       dissect(A \ S); dissect(B); emit S                                                    */
+/*       A = first floor(|L|/2), B = rest                                                      */
+/*       S = greedy vertex cover of the A-B cross edges: take the vertex with most uncovered   */
+/*           cross edges (tie: smallest index) until every cross edge is covered               */
+/*       dissect(A \ S); dissect(B \ S); emit S ascending                                      */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct { int n; int *ptr; int *adj; } graph_t;
 
@@ -122,69 +122,54 @@ static graph_t build_graph_upper(int n, const int *Ap, const int *Ai)
     return g;
 }
 
-static int isqrt_floor(int n)
-{
-    int r = (int)floor(sqrt((double)n));
-    while ((long)r * r > n) r--;
-    while ((long)(r + 1) * (r + 1) <= n) r++;
-    return r;
-}
+static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
 
-/* side[v] : scratch marks, must be 0 on entry and is restored to 0 */
-static void nd_dissect(const graph_t *g, const int *L, int len, char *side, int *out, int *nout)
+/* where[v] : 0 outside the current list, 1 = A, 2 = B, 3 = separator; restored to 0 on return */
+static void nd_dissect(const graph_t *g, const int *L, int len, char *where, int *out, int *nout)
 {
     if (len <= 0) return;
     if (len <= 8) { for (int i = 0; i < len; i++) out[(*nout)++] = L[i]; return; }
     int h = len / 2;
-    for (int i = h; i < len; i++) side[L[i]] = 2;               /* B */
-    int *keep = (int *)malloc(len * sizeof(int));
-    int *sep = (int *)malloc(len * sizeof(int));
-    int nk = 0, ns = 0;
-    for (int i = 0; i < h; i++) {
-        int a = L[i], hit = 0;
-        for (int p = g->ptr[a]; p < g->ptr[a + 1] && !hit; p++) hit = (side[g->adj[p]] == 2);
-        if (hit) sep[ns++] = a; else keep[nk++] = a;
+    for (int i = 0; i < len; i++) where[L[i]] = (i < h) ? 1 : 2;
+    int *sep = (int *)malloc(len * sizeof(int)), ns = 0;
+    for (;;) {
+        /* recount from scratch every round: O(|S| * edges), fine for an oracle */
+        int best = -1, bc = 0;
+        for (int i = 0; i < len; i++) {
+            int v = L[i];
+            if (where[v] == 3) continue;
+            char other = (where[v] == 1) ? 2 : 1;
+            int c = 0;
+            for (int p = g->ptr[v]; p < g->ptr[v + 1]; p++) c += (where[g->adj[p]] == other);
+            if (c > bc) { bc = c; best = v; }
+        }
+        if (best < 0) break;
+        where[best] = 3;
+        sep[ns++] = best;
     }
-    for (int i = h; i < len; i++) side[L[i]] = 0;
-    nd_dissect(g, keep, nk, side, out, nout);
-    nd_dissect(g, L + h, len - h, side, out, nout);
+    qsort(sep, ns, sizeof(int), cmp_int);
+    int *A = (int *)malloc(len * sizeof(int)), *B = (int *)malloc(len * sizeof(int)), na = 0, nb = 0;
+    for (int i = 0; i < len; i++) {
+        if (where[L[i]] == 1) A[na++] = L[i];
+        else if (where[L[i]] == 2) B[nb++] = L[i];
+    }
+    for (int i = 0; i < len; i++) where[L[i]] = 0;
+    nd_dissect(g, A, na, where, out, nout);
+    nd_dissect(g, B, nb, where, out, nout);
     for (int i = 0; i < ns; i++) out[(*nout)++] = sep[i];
-    free(keep); free(sep);
+    free(A); free(B); free(sep);
 }
 
 static void lsfm_nd_order(int n, const int *Ap, const int *Ai, int *perm)
 {
     if (n <= 32) { for (int i = 0; i < n; i++) perm[i] = i; return; }
     graph_t g = build_graph_upper(n, Ap, Ai);
-    int tau = 10 * isqrt_floor(n);
-    if (n / 2 < tau) tau = n / 2;
-    if (tau < 16) tau = 16;
-    int *R = (int *)malloc(n * sizeof(int)), nR = 0;
-    int *D = (int *)malloc(n * sizeof(int)), nD = 0;
-    for (int v = 0; v < n; v++) {
-        /* degree = number of DISTINCT neighbours; the reference patterns have no duplicates */
-        int deg = g.ptr[v + 1] - g.ptr[v];
-        if (deg > tau) D[nD++] = v; else R[nR++] = v;
-    }
-    /* dense vertices are removed from the graph seen by the dissection */
-    char *isD = (char *)calloc(n, 1);
-    for (int i = 0; i < nD; i++) isD[D[i]] = 1;
-    graph_t h; h.n = n; h.ptr = (int *)malloc((n + 1) * sizeof(int));
-    h.adj = (int *)malloc((g.ptr[n] ? g.ptr[n] : 1) * sizeof(int));
-    int q = 0;
-    for (int v = 0; v < n; v++) {
-        h.ptr[v] = q;
-        if (!isD[v])
-            for (int p = g.ptr[v]; p < g.ptr[v + 1]; p++)
-                if (!isD[g.adj[p]]) h.adj[q++] = g.adj[p];
-    }
-    h.ptr[n] = q;
-    char *side = (char *)calloc(n, 1);
+    int *L = (int *)malloc(n * sizeof(int));
+    for (int i = 0; i < n; i++) L[i] = i;
+    char *where = (char *)calloc(n, 1);
     int nout = 0;
-    nd_dissect(&h, R, nR, side, perm, &nout);
-    for (int i = 0; i < nD; i++) perm[nout++] = D[i];
-    free(side); free(isD); free(R); free(D);
-    free(g.ptr); free(g.adj); free(h.ptr); free(h.adj);
+    nd_dissect(&g, L, n, where, perm, &nout);
+    free(where); free(L); free(g.ptr); free(g.adj);
 }
 
 /* exported for the ordering parity test (block pattern in, permutation out) */
