@@ -99,6 +99,13 @@ int lsfm_run_stereo(const lsfm_map *maps, int num, lsfm_map *out);
  * rule of LinearSFMImp.cpp:1997 depends on the global output index).                           */
 int lsfm_tree_create_stereo(const lsfm_map *maps, int num, lsfm_tree **tree);
 int lsfm_tree_solve(lsfm_tree *tree, int verbose, int first_index, int max_levels);
+/* device time (ms, CUDA events on the library's stream) of the last lsfm_tree_solve            */
+double lsfm_tree_last_solve_ms(const lsfm_tree *tree);
+/* make the result of the last solve the new input set (no copy); append uploaded host maps     */
+int lsfm_tree_adopt_result(lsfm_tree *tree);
+/* input set := the maps of the last create/set_maps (still resident; no copy)                  */
+int lsfm_tree_reset(lsfm_tree *tree);
+int lsfm_tree_append_maps(lsfm_tree *tree, const lsfm_map *maps, int num);
 int lsfm_tree_result_count(const lsfm_tree *tree);
 int lsfm_tree_result_shape(const lsfm_tree *tree, int idx, lsfm_map *shape_only);
 int lsfm_tree_download(const lsfm_tree *tree, int idx, lsfm_map *out);

@@ -37,7 +37,9 @@ EXPORTS = [
     "lsfm_join_stereo_batch", "lsfm_solve_stereo", "lsfm_debug_last_solve", "lsfm_block_ordering",
     "lsfm_run_stereo", "lsfm_tree_create_stereo", "lsfm_tree_solve", "lsfm_tree_result_count",
     "lsfm_tree_result_shape", "lsfm_tree_download", "lsfm_tree_download_state", "lsfm_tree_set_maps",
-    "lsfm_tree_free", "lsfm_load_localmap_stereo", "lsfm_save_outputs", "lsfm_cli_main",
+    "lsfm_tree_free", "lsfm_tree_last_solve_ms", "lsfm_tree_adopt_result", "lsfm_tree_append_maps",
+    "lsfm_tree_reset",
+    "lsfm_load_localmap_stereo", "lsfm_save_outputs", "lsfm_cli_main",
 ]
 
 _lib = None
@@ -63,6 +65,11 @@ def lib():
         L.lsfm_tree_result_shape.argtypes = [C.c_void_p, C.c_int, C.POINTER(LsfmMap)]
         L.lsfm_tree_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(LsfmMap)]
         L.lsfm_tree_download_state.argtypes = [C.c_void_p, C.c_int, _pi, _pd]
+        L.lsfm_tree_last_solve_ms.restype = C.c_double
+        L.lsfm_tree_last_solve_ms.argtypes = [C.c_void_p]
+        L.lsfm_tree_adopt_result.argtypes = [C.c_void_p]
+        L.lsfm_tree_reset.argtypes = [C.c_void_p]
+        L.lsfm_tree_append_maps.argtypes = [C.c_void_p, C.POINTER(LsfmMap), C.c_int]
         L.lsfm_tree_set_maps.argtypes = [C.c_void_p, C.POINTER(LsfmMap), C.c_int]
         L.lsfm_tree_create_stereo.argtypes = [C.POINTER(LsfmMap), C.c_int, C.POINTER(C.c_void_p)]
         _lib = L

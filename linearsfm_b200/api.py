@@ -131,8 +131,27 @@ class Tree:
 
     def set_maps(self, maps):
         arr, keep = to_c_array(maps)
-        check(lib().lsfm_tree_set_maps(self._h, arr, C.c_int(len(maps))))
-        self.num = len(maps)
+        self.set_maps_c(arr, len(maps))
+
+    def set_maps_c(self, arr, num):
+        """arr: prebuilt (LsfmMap * num) array whose pointers stay alive in the caller."""
+        check(lib().lsfm_tree_set_maps(self._h, arr, C.c_int(num)))
+        self.num = num
+
+    def append_maps(self, maps):
+        arr, keep = to_c_array(maps)
+        check(lib().lsfm_tree_append_maps(self._h, arr, C.c_int(len(maps))))
+        self.num += len(maps)
+
+    def reset(self):
+        """input set := the maps of the last upload (still resident in HBM)."""
+        check(lib().lsfm_tree_reset(self._h))
+
+    def adopt_result(self):
+        check(lib().lsfm_tree_adopt_result(self._h))
+
+    def last_solve_ms(self) -> float:
+        return float(lib().lsfm_tree_last_solve_ms(self._h))
 
     def solve(self, verbose: bool = False, first_index: int = 0, max_levels: int = -1):
         check(lib().lsfm_tree_solve(self._h, C.c_int(1 if verbose else 0), C.c_int(first_index),

@@ -41,8 +41,11 @@ template <class F> int guarded(F &&f)
 } // namespace
 
 struct lsfm_tree {
-    std::vector<MapHandle> leaves;
+    std::vector<MapHandle> uploaded;   // what the last create/set_maps put in HBM
+    std::vector<MapHandle> leaves;     // current input set of lsfm_tree_solve
     std::vector<MapHandle> result;
+    double last_ms = 0.0;            // device time of the last solve (CUDA events on our stream)
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
 
 extern "C" {
@@ -243,7 +246,8 @@ int lsfm_tree_create_stereo(const lsfm_map *maps, int num, lsfm_tree **tree)
 {
     return guarded([&] {
         lsfm_tree *t = new lsfm_tree();
-        t->leaves = upload_maps(*g_ctx, maps, num, true);
+        t->uploaded = upload_maps(*g_ctx, maps, num, true);
+        t->leaves = t->uploaded;
         *tree = t;
     });
 }
@@ -252,18 +256,51 @@ int lsfm_tree_set_maps(lsfm_tree *tree, const lsfm_map *maps, int num)
 {
     return guarded([&] {
         tree->result.clear();
-        tree->leaves = upload_maps(*g_ctx, maps, num, true);
+        tree->leaves.clear();
+        tree->uploaded.clear();
+        tree->uploaded = upload_maps(*g_ctx, maps, num, true);
+        tree->leaves = tree->uploaded;
     });
+}
+
+int lsfm_tree_reset(lsfm_tree *tree)
+{
+    tree->result.clear();
+    tree->leaves = tree->uploaded;
+    return LSFM_OK;
 }
 
 int lsfm_tree_solve(lsfm_tree *tree, int verbose, int first_index, int max_levels)
 {
     return guarded([&] {
         tree->result.clear();
+        if (!tree->e0) { CUDA_CHECK(cudaEventCreate(&tree->e0)); CUDA_CHECK(cudaEventCreate(&tree->e1)); }
+        CUDA_CHECK(cudaEventRecord(tree->e0, g_ctx->stream));
         std::vector<MapHandle> top = solve_tree_stereo(*g_ctx, tree->leaves, verbose != 0, first_index, max_levels);
         if (max_levels < 0 && top.size() == 1) top[0] = final_rebase_stereo(*g_ctx, top[0]);
         tree->result = std::move(top);
-        CUDA_CHECK(cudaStreamSynchronize(g_ctx->stream));
+        CUDA_CHECK(cudaEventRecord(tree->e1, g_ctx->stream));
+        CUDA_CHECK(cudaEventSynchronize(tree->e1));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, tree->e0, tree->e1));
+        tree->last_ms = ms;
+    });
+}
+
+double lsfm_tree_last_solve_ms(const lsfm_tree *tree) { return tree->last_ms; }
+
+int lsfm_tree_adopt_result(lsfm_tree *tree)
+{
+    tree->leaves = std::move(tree->result);
+    tree->result.clear();
+    return LSFM_OK;
+}
+
+int lsfm_tree_append_maps(lsfm_tree *tree, const lsfm_map *maps, int num)
+{
+    return guarded([&] {
+        std::vector<MapHandle> h = upload_maps(*g_ctx, maps, num, true);
+        tree->leaves.insert(tree->leaves.end(), h.begin(), h.end());
     });
 }
 
@@ -299,6 +336,7 @@ void lsfm_tree_free(lsfm_tree *tree)
 {
     if (!tree) return;
     if (g_ctx) cudaStreamSynchronize(g_ctx->stream);
+    if (tree->e0) { cudaEventDestroy(tree->e0); cudaEventDestroy(tree->e1); }
     delete tree;
 }
 

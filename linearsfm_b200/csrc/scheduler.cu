@@ -29,7 +29,9 @@ std::vector<MapHandle> solve_tree_stereo(Context &ctx, std::vector<MapHandle> le
 {
     int L = 0;
     long long base = first_index;             // global index of level[0] at the current level
-    while (level.size() > 1 && (max_levels < 0 || L < max_levels)) {
+    // max_levels < 0: run to the root.  max_levels >= 0: run exactly that many levels, even on a
+    // single map (a leftover still goes through the re-base rule of its level).
+    while ((max_levels < 0 && level.size() > 1) || (max_levels >= 0 && L < max_levels && !level.empty())) {
         int count = (int)level.size();
         int npairs = count / 2;
         bool leftover = (count % 2) != 0;

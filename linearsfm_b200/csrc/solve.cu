@@ -426,7 +426,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     nl = 0;
 
     // ---- a9-a10: V^-1, S, E ----
-    ctx.begin("solve.schur");
+    ctx.begin("solve.schur_prep");
     DevBuf<double> Vinv(9 * (size_t)J.totFeat, s), S(36 * (size_t)nuis, s), E(6 * (size_t)J.totPose, s);
     S.zero();
     CUDA_CHECK(cudaMemcpyAsync(E.p, eP, sizeof(double) * 6 * (size_t)J.totPose, cudaMemcpyDeviceToDevice, s));
@@ -434,11 +434,19 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     if (J.totU > 0) {
         k_s_from_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, J.dPosePre.p, K, J.totU, keys.p, rowPtr.p, S.p); nl++;
     }
+    ctx.end(72.0 * J.totFeat * 2 + 576.0 * J.totU, 0.0, nl);
+    nl = 0;
+    ctx.begin("solve.schur");
     if (J.totW > 0) {
         k_schur<<<ceil_div(J.totW, 128), 128, 0, s>>>(J.d.p, J.dWPre.p, J.dFeatPre.p, J.dPosePre.p, K, J.totW,
                                                      Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p); nl++;
     }
     KERNEL_CHECK();
+    // algorithmic bytes of the Schur kernel: every W block + its feature's V^-1 and eF read once,
+    // S and E written once
+    ctx.end(152.0 * J.totW + 96.0 * J.totFeat + 288.0 * nuis + 48.0 * J.totPose, 0.0, nl);
+    nl = 0;
+    ctx.begin("solve.symbolic");
 
     // ---- symbolic on the host while the GPU accumulates S ----
     std::vector<int> mvec(K), sOff(K + 1);
@@ -448,8 +456,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     try {
         build_symbolic(K, mvec, J.posePre, hKeys, sOff, sym, (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
     } catch (const std::exception &e) { throw LsfmError(LSFM_ERR_ARG, std::string("symbolic: ") + e.what()); }
-    double schur_bytes = 152.0 * J.totW + 72.0 * J.totFeat + 288.0 * nuis + 296.0 * J.totU;
-    ctx.end(schur_bytes, 0.0, nl);
+    ctx.end(8.0 * nuis, 0.0, nl);
     nl = 0;
 
     // ---- numeric ----
