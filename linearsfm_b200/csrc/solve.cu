@@ -190,6 +190,194 @@ k_schur(const DMap *__restrict__ J, const int *__restrict__ wPre, const int *__r
     }
 }
 
+// Slow path for one W block (global atomics), used when a chunk sees too many distinct poses.
+__device__ __noinline__ void schur_block_slow(const DMap &M, int k, int a, const int *__restrict__ featPre,
+                                 const int *__restrict__ posePre, const double *__restrict__ Vinv,
+                                 const double *__restrict__ eF, const u64 *__restrict__ keys,
+                                 const int *__restrict__ rowPtr, double *__restrict__ S,
+                                 double *__restrict__ E)
+{
+    int f = M.feature[a], pa = M.photo[a];
+    double W[18], Vi[9], WV[18], ef[3], y[6];
+    sm::load<18>(M.W + 18 * (size_t)a, W);
+    sm::load<9>(Vinv + 9 * (size_t)(featPre[k] + f), Vi);
+    sm::mmt<6, 3, 3>(W, Vi, WV);
+    sm::load<3>(eF + 3 * (size_t)(featPre[k] + f), ef);
+    sm::mm<6, 3, 1>(WV, ef, y);
+    for (int q = 0; q < 6; q++) atomicAdd(E + 6 * (size_t)(posePre[k] + pa) + q, -y[q]);
+    for (int b = M.wPtr[f]; b < M.wPtr[f + 1]; b++) {
+        int pb = M.photo[b];
+        if (pb < pa) continue;
+        double Wb[18], P[36];
+        sm::load<18>(M.W + 18 * (size_t)b, Wb);
+        sm::mmt<6, 3, 6>(WV, Wb, P);
+        int slot = find_slot(keys, rowPtr, posePre[k] + pa, pair_key(k, pa, pb));
+        double *s = S + 36 * (size_t)slot;
+        for (int q = 0; q < 36; q++) atomicAdd(s + q, -P[q]);
+    }
+}
+
+// v2: one CTA per chunk of consecutive features of one join.  The distinct poses seen by the chunk
+// (<= SCH_CMAX: a handful of "hub" poses + the local observers) get a local index; thread t owns the
+// pose pair (i<=j) and keeps its 6x6 block of S in REGISTERS while the chunk's features stream
+// through shared memory (W and W V^-1 staged per feature, coalesced).  One flush of 36 atomics per
+// touched pair and chunk replaces 36 atomics per pair and FEATURE.
+constexpr int SCH_CMAX = 31;          // 31*32/2 = 496 pairs = 2 per thread of a 256-thread CTA
+constexpr int SCH_NB = 16;            // features staged per barrier
+constexpr int SCH_FCHUNK = 128;
+constexpr int SCH_THREADS = 256;
+constexpr int SCH_LD = 19;            // padded block stride (doubles): conflict-free 64-bit LDS
+
+struct SchurChunk { int k, f0, f1; };
+
+__global__ void __launch_bounds__(SCH_THREADS)
+k_schur_tiled(const DMap *__restrict__ J, const SchurChunk *__restrict__ chunks,
+              const int *__restrict__ featPre, const int *__restrict__ posePre,
+              const double *__restrict__ Vinv, const double *__restrict__ eF,
+              const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
+              double *__restrict__ S, double *__restrict__ E, int *__restrict__ dbgCount)
+{
+    extern __shared__ double smd[];
+    double *Wsm = smd;                                          // [NB][CMAX][LD]
+    double *WVsm = Wsm + SCH_NB * SCH_CMAX * SCH_LD;            // [NB][CMAX][LD]
+    double *efs = WVsm + SCH_NB * SCH_CMAX * SCH_LD;            // [NB][4]
+    unsigned *present = (unsigned *)(efs + SCH_NB * 4);         // [NB]
+    int *poses = (int *)(present + SCH_NB);                     // [CMAX]
+    int *nposes_s = poses + SCH_CMAX;                           // [1] (+pad)
+    unsigned *bitmap = (unsigned *)(nposes_s + 4);              // [words]
+    const SchurChunk ch = chunks[blockIdx.x];
+    const DMap &M = J[ch.k];
+    const int k = ch.k;
+    const int words = (M.m + 31) >> 5;
+    int *prefix = (int *)(bitmap + words);                      // [words]
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int w0 = M.wPtr[ch.f0], w1 = M.wPtr[ch.f1];
+
+    for (int i = tid; i < words; i += nt) bitmap[i] = 0u;
+    __syncthreads();
+    for (int j = w0 + tid; j < w1; j += nt) {
+        int p = M.photo[j];
+        atomicOr(&bitmap[p >> 5], 1u << (p & 31));
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < words; base += 32) {
+            int c = (base + lane < words) ? __popc(bitmap[base + lane]) : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (base + lane < words) prefix[base + lane] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) *nposes_s = run;
+    }
+    __syncthreads();
+    const int nposes = *nposes_s;
+    if (dbgCount && tid == 0) { atomicAdd(&dbgCount[0], 1); atomicAdd(&dbgCount[1], nposes > SCH_CMAX); atomicMax(&dbgCount[2], nposes); }
+    if (nposes == 0) return;
+    if (nposes > SCH_CMAX) {
+        for (int a = w0 + tid; a < w1; a += nt)
+            schur_block_slow(M, k, a, featPre, posePre, Vinv, eF, keys, rowPtr, S, E);
+        return;
+    }
+    for (int i = tid; i < words; i += nt) {
+        unsigned b = bitmap[i];
+        int r = prefix[i];
+        while (b) { int bit = __ffs(b) - 1; poses[r++] = i * 32 + bit; b &= b - 1; }
+    }
+    // Every thread owns two "pair slots" (2 x 256 = 512 >= 496).  With few distinct poses (lower
+    // tree levels) the npairs pose pairs are replicated `rep` times and replica r takes the
+    // features fb = r, r+rep, ... of each batch, so the CTA stays busy; replicas flush separately.
+    const int npairs = nposes * (nposes + 1) / 2;
+    const int rep = max(1, min(SCH_NB, (2 * SCH_THREADS) / npairs));
+    int pi[2], pj[2], pr0[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        pi[u] = -1; pj[u] = -1; pr0[u] = 0;
+        int q = tid + u * SCH_THREADS;
+        int r = q / npairs, t = q - r * npairs;
+        if (r < rep) {
+            int i = 0;
+            while (t >= nposes - i) { t -= nposes - i; i++; }
+            pi[u] = i; pj[u] = i + t; pr0[u] = r;
+        }
+    }
+    double acc[2][36], eacc[2][6];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+#pragma unroll
+        for (int q = 0; q < 36; q++) acc[u][q] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) eacc[u][q] = 0.0;
+    }
+    bool touched[2] = {false, false};
+
+    for (int fb0 = ch.f0; fb0 < ch.f1; fb0 += SCH_NB) {
+        const int nbf = min(SCH_NB, ch.f1 - fb0);
+        __syncthreads();                       // previous batch fully consumed (and poses[] visible)
+        if (tid < SCH_NB) present[tid] = 0u;
+        __syncthreads();
+        const int b0 = M.wPtr[fb0], b1 = M.wPtr[fb0 + nbf];
+        for (int e = tid; e < (b1 - b0) * 18; e += nt) {
+            int blk = b0 + e / 18, el = e % 18;
+            int f = M.feature[blk], fb = f - fb0, p = M.photo[blk];
+            int slot = prefix[p >> 5] + __popc(bitmap[p >> 5] & ((1u << (p & 31)) - 1u));
+            const double *Wb = M.W + 18 * (size_t)blk;
+            Wsm[(fb * SCH_CMAX + slot) * SCH_LD + el] = Wb[el];
+            const double *Wr = Wb + 3 * (el / 3);
+            const double *Vi = Vinv + 9 * (size_t)(featPre[k] + f) + 3 * (el % 3);
+            WVsm[(fb * SCH_CMAX + slot) * SCH_LD + el] = Wr[0] * Vi[0] + Wr[1] * Vi[1] + Wr[2] * Vi[2];
+            if (el == 0) atomicOr(&present[fb], 1u << slot);
+        }
+        for (int e = tid; e < nbf * 3; e += nt)
+            efs[(e / 3) * 4 + (e % 3)] = eF[3 * (size_t)(featPre[k] + fb0 + e / 3) + (e % 3)];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (pi[u] < 0) continue;
+            for (int fb = pr0[u]; fb < nbf; fb += rep) {
+                unsigned pr = present[fb];
+                if (((pr >> pi[u]) & (pr >> pj[u]) & 1u) == 0u) continue;
+                touched[u] = true;
+                const double *wv = WVsm + (fb * SCH_CMAX + pi[u]) * SCH_LD;
+                const double *w = Wsm + (fb * SCH_CMAX + pj[u]) * SCH_LD;
+                double b[18];
+#pragma unroll
+                for (int q = 0; q < 18; q++) b[q] = w[q];
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    double a0 = wv[3 * r], a1 = wv[3 * r + 1], a2 = wv[3 * r + 2];
+#pragma unroll
+                    for (int c = 0; c < 6; c++)
+                        acc[u][6 * r + c] += a0 * b[3 * c] + a1 * b[3 * c + 1] + a2 * b[3 * c + 2];
+                    if (pi[u] == pj[u]) {
+                        const double *ef = efs + fb * 4;
+                        eacc[u][r] += a0 * ef[0] + a1 * ef[1] + a2 * ef[2];
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        if (!touched[u]) continue;
+        int gi = poses[pi[u]], gj = poses[pj[u]];
+        int slot = find_slot(keys, rowPtr, posePre[k] + gi, pair_key(k, gi, gj));
+        double *sp = S + 36 * (size_t)slot;
+#pragma unroll
+        for (int q = 0; q < 36; q++) atomicAdd(sp + q, -acc[u][q]);
+        if (pi[u] == pj[u]) {
+            double *e = E + 6 * (size_t)(posePre[k] + gi);
+#pragma unroll
+            for (int q = 0; q < 6; q++) atomicAdd(e + q, -eacc[u][q]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // a11-a12: numeric block multifrontal Cholesky with the right-hand side carried as an extra row
 // ---------------------------------------------------------------------------------------------
@@ -438,8 +626,34 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     nl = 0;
     ctx.begin("solve.schur");
     if (J.totW > 0) {
-        k_schur<<<ceil_div(J.totW, 128), 128, 0, s>>>(J.d.p, J.dWPre.p, J.dFeatPre.p, J.dPosePre.p, K, J.totW,
-                                                     Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p); nl++;
+        static const bool use_v1 = getenv("LSFM_SCHUR_V1") != nullptr;
+        if (use_v1) {
+            k_schur<<<ceil_div(J.totW, 128), 128, 0, s>>>(J.d.p, J.dWPre.p, J.dFeatPre.p, J.dPosePre.p, K, J.totW,
+                                                         Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p); nl++;
+        } else {
+            std::vector<SchurChunk> chunks;
+            DevBuf<int> err_dbg(4, s);
+            err_dbg.zero();
+            int maxWords = 1;
+            for (int k = 0; k < K; k++) {
+                maxWords = std::max(maxWords, (J.h[k].m + 31) / 32);
+                for (int f0 = 0; f0 < J.h[k].n; f0 += SCH_FCHUNK)
+                    chunks.push_back({k, f0, std::min(J.h[k].n, f0 + SCH_FCHUNK)});
+            }
+            DevBuf<SchurChunk> dChunks(chunks.size(), s);
+            dChunks.upload(chunks);
+            size_t shb = sizeof(double) * (2 * SCH_NB * SCH_CMAX * SCH_LD + SCH_NB * 4) +
+                         sizeof(int) * (SCH_NB + SCH_CMAX + 4 + 2 * (size_t)maxWords) + 16;
+            if (shb > 48 * 1024)
+                CUDA_CHECK(cudaFuncSetAttribute(k_schur_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
+            k_schur_tiled<<<(int)chunks.size(), SCH_THREADS, shb, s>>>(J.d.p, dChunks.p, J.dFeatPre.p, J.dPosePre.p,
+                                                                       Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p,
+                                                                       getenv("LSFM_DEBUG") ? err_dbg.p : nullptr); nl++;
+            if (getenv("LSFM_DEBUG")) {
+                std::vector<int> h = err_dbg.to_host();
+                fprintf(stderr, "[schur] K=%d chunks=%d slow=%d max distinct poses=%d\n", K, h[0], h[1], h[2]);
+            }
+        }
     }
     KERNEL_CHECK();
     // algorithmic bytes of the Schur kernel: every W block + its feature's V^-1 and eF read once,
