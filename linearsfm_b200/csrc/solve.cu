@@ -74,6 +74,133 @@ __global__ void k_pat_emit(const DMap *__restrict__ J, const int *__restrict__ f
         for (int b = a; b < w1; b++) keys[o++] = pair_key(k, M.photo[a], M.photo[b]);
 }
 
+// Chunk-level exact dedupe (default path): one CTA per chunk of consecutive features builds the
+// chunk's local pose table (bitmap + popcount prefix) and a bitmap over the <= 496 local pose
+// pairs; a pair bit is set only if ONE feature is seen by both poses (the reference's smask rule,
+// LinearSFMImp.cpp:2156-2173), so the pattern stays bit-exact while ~100x fewer keys reach the sort.
+constexpr int PAT_CMAX = 31;
+constexpr int PAT_THREADS = 128;
+struct FeatChunk { int k, f0, f1; };
+
+__global__ void __launch_bounds__(PAT_THREADS)
+k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, int mode,
+            int *__restrict__ cnt, const int *__restrict__ scan, u64 *__restrict__ keys)
+{
+    extern __shared__ unsigned smu[];
+    const FeatChunk ch = chunks[blockIdx.x];
+    const DMap &M = J[ch.k];
+    const int words = (M.m + 31) >> 5;
+    unsigned *bitmap = smu;                          // [words]
+    int *prefix = (int *)(bitmap + words);           // [words]
+    unsigned *pairBits = (unsigned *)(prefix + words);   // [16]
+    int *poses = (int *)(pairBits + 16);             // [PAT_CMAX + 1]
+    int *misc = poses + PAT_CMAX + 1;                // [0] nposes, [1] raw count
+    int *featOff = misc + 2;                         // [PAT_THREADS + 1] (overflow path only)
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int w0 = M.wPtr[ch.f0], w1 = M.wPtr[ch.f1];
+    for (int i = tid; i < words; i += nt) bitmap[i] = 0u;
+    if (tid < 16) pairBits[tid] = 0u;
+    if (tid == 0) misc[1] = 0;
+    __syncthreads();
+    for (int j = w0 + tid; j < w1; j += nt) {
+        int p = M.photo[j];
+        atomicOr(&bitmap[p >> 5], 1u << (p & 31));
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < words; base += 32) {
+            int c = (base + lane < words) ? __popc(bitmap[base + lane]) : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (base + lane < words) prefix[base + lane] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) misc[0] = run;
+    }
+    __syncthreads();
+    const int nposes = misc[0];
+    if (nposes <= PAT_CMAX) {
+        for (int f = ch.f0 + tid; f < ch.f1; f += nt) {
+            int a0 = M.wPtr[f], a1 = M.wPtr[f + 1];
+            for (int a = a0; a < a1; a++) {
+                int pa = M.photo[a];
+                int sa = prefix[pa >> 5] + __popc(bitmap[pa >> 5] & ((1u << (pa & 31)) - 1u));
+                for (int b = a; b < a1; b++) {
+                    int pb = M.photo[b];
+                    int sb = prefix[pb >> 5] + __popc(bitmap[pb >> 5] & ((1u << (pb & 31)) - 1u));
+                    int i = min(sa, sb), j = max(sa, sb);
+                    int idx = i * nposes - (i * (i - 1)) / 2 + (j - i);
+                    atomicOr(&pairBits[idx >> 5], 1u << (idx & 31));
+                }
+            }
+        }
+        if (mode == 1)
+            for (int i = tid; i < words; i += nt) {
+                unsigned b = bitmap[i];
+                int r = prefix[i];
+                while (b) { int bit = __ffs(b) - 1; poses[r++] = i * 32 + bit; b &= b - 1; }
+            }
+        __syncthreads();
+        if (mode == 0) {
+            if (tid == 0) {
+                int c = 0;
+                for (int q = 0; q < 16; q++) c += __popc(pairBits[q]);
+                cnt[blockIdx.x] = c;
+            }
+            return;
+        }
+        const int o0 = scan[blockIdx.x];
+        const int npairs = nposes * (nposes + 1) / 2;
+        for (int t = tid; t < npairs; t += nt) {
+            if (!((pairBits[t >> 5] >> (t & 31)) & 1u)) continue;
+            int rank = __popc(pairBits[t >> 5] & ((1u << (t & 31)) - 1u));
+            for (int q = 0; q < (t >> 5); q++) rank += __popc(pairBits[q]);
+            int r = t, i = 0;
+            while (r >= nposes - i) { r -= nposes - i; i++; }
+            keys[o0 + rank] = pair_key(ch.k, poses[i], poses[i + r]);
+        }
+        return;
+    }
+    // overflow: too many distinct poses in this chunk -> raw per-feature pairs
+    int myf = ch.f0 + tid;
+    int kf = (myf < ch.f1) ? M.wPtr[myf + 1] - M.wPtr[myf] : 0;
+    int mine = kf * (kf + 1) / 2;
+    if (mode == 0) {
+        atomicAdd(&misc[1], mine);
+        __syncthreads();
+        if (tid == 0) cnt[blockIdx.x] = misc[1];
+        return;
+    }
+    featOff[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int q = 0; q < nt; q++) { int c = featOff[q]; featOff[q] = run; run += c; }
+    }
+    __syncthreads();
+    if (myf < ch.f1) {
+        int o = scan[blockIdx.x] + featOff[tid];
+        int a0 = M.wPtr[myf], a1 = M.wPtr[myf + 1];
+        for (int a = a0; a < a1; a++)
+            for (int b = a; b < a1; b++) keys[o++] = pair_key(ch.k, M.photo[a], M.photo[b]);
+    }
+}
+
+__global__ void k_pat_u(const DMap *__restrict__ J, const int *__restrict__ uPre, int K, int totU,
+                        u64 *__restrict__ keys)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totU) return;
+    int k = seg_find(uPre, K, g);
+    int b = g - uPre[k];
+    keys[g] = pair_key(k, J[k].Ui[b], J[k].Uj[b]);
+}
+
 // rowPtr[global pose] = first slot of that block row (keys are sorted by join,row,col)
 __global__ void k_rowptr(const u64 *__restrict__ keys, int n, const int *__restrict__ posePre, int K,
                          int totP, int *__restrict__ rowPtr)
@@ -228,7 +355,7 @@ constexpr int SCH_FCHUNK = 128;
 constexpr int SCH_THREADS = 256;
 constexpr int SCH_LD = 19;            // padded block stride (doubles): conflict-free 64-bit LDS
 
-struct SchurChunk { int k, f0, f1; };
+typedef FeatChunk SchurChunk;
 
 __global__ void __launch_bounds__(SCH_THREADS)
 k_schur_tiled(const DMap *__restrict__ J, const SchurChunk *__restrict__ chunks,
@@ -576,15 +703,49 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
 
     // ---- a8: pattern ----
     ctx.begin("solve.pattern");
-    int nItems = J.totFeat + J.totU;
-    DevBuf<int> pcnt(nItems + 1, s), pscan(nItems + 1, s);
-    k_pat_count<<<ceil_div(nItems + 1, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, K, J.totFeat, J.totU, pcnt.p); nl++;
-    exclusive_scan(ctx, pcnt.p, pscan.p, nItems + 1); nl += 2;
+    // feature chunks shared by the pattern and the Schur kernels
+    std::vector<FeatChunk> chunks;
+    int maxWords = 1;
+    for (int k = 0; k < K; k++) {
+        maxWords = std::max(maxWords, (J.h[k].m + 31) / 32);
+        for (int f0 = 0; f0 < J.h[k].n; f0 += SCH_FCHUNK)
+            chunks.push_back({k, f0, std::min(J.h[k].n, f0 + SCH_FCHUNK)});
+    }
+    const int nChunks = (int)chunks.size();
+    DevBuf<FeatChunk> dChunks(nChunks, s);
+    dChunks.upload(chunks);
     int nRaw = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&nRaw, pscan.p + nItems, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
-    DevBuf<u64> rawKeys(nRaw, s), sortedKeys(nRaw, s), keys(nRaw, s);
-    k_pat_emit<<<ceil_div(nItems, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, J.dUPre.p, K, J.totFeat, J.totU, pscan.p, rawKeys.p); nl++;
+    DevBuf<u64> rawKeys, sortedKeys, keys;
+    static const bool pat_v1 = getenv("LSFM_PATTERN_V1") != nullptr;
+    if (pat_v1) {
+        int nItems = J.totFeat + J.totU;
+        DevBuf<int> pcnt(nItems + 1, s), pscan(nItems + 1, s);
+        k_pat_count<<<ceil_div(nItems + 1, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, K, J.totFeat, J.totU, pcnt.p); nl++;
+        exclusive_scan(ctx, pcnt.p, pscan.p, nItems + 1); nl += 2;
+        CUDA_CHECK(cudaMemcpyAsync(&nRaw, pscan.p + nItems, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        rawKeys.alloc(nRaw, s); sortedKeys.alloc(nRaw, s); keys.alloc(nRaw, s);
+        k_pat_emit<<<ceil_div(nItems, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, J.dUPre.p, K, J.totFeat, J.totU, pscan.p, rawKeys.p); nl++;
+    } else {
+        DevBuf<int> pcnt(nChunks + 1, s), pscan(nChunks + 1, s);
+        pcnt.zero();
+        size_t shb = sizeof(int) * (2 * (size_t)maxWords + 16 + PAT_CMAX + 1 + 2 + PAT_THREADS + 1);
+        if (shb > 48 * 1024)
+            CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
+        int nChunkKeys = 0;
+        if (nChunks > 0) {
+            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 0, pcnt.p, nullptr, nullptr); nl++;
+            exclusive_scan(ctx, pcnt.p, pscan.p, nChunks + 1); nl += 2;
+            CUDA_CHECK(cudaMemcpyAsync(&nChunkKeys, pscan.p + nChunks, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+        nRaw = nChunkKeys + J.totU;
+        rawKeys.alloc(nRaw, s); sortedKeys.alloc(nRaw, s); keys.alloc(nRaw, s);
+        if (J.totU > 0) { k_pat_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, K, J.totU, rawKeys.p); nl++; }
+        if (nChunks > 0) {
+            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 1, nullptr, pscan.p, rawKeys.p + J.totU); nl++;
+        }
+    }
     {
         size_t tb = 0;
         cub::DeviceRadixSort::SortKeys(nullptr, tb, rawKeys.p, sortedKeys.p, nRaw, 0, 64, s);
@@ -631,17 +792,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             k_schur<<<ceil_div(J.totW, 128), 128, 0, s>>>(J.d.p, J.dWPre.p, J.dFeatPre.p, J.dPosePre.p, K, J.totW,
                                                          Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p); nl++;
         } else {
-            std::vector<SchurChunk> chunks;
             DevBuf<int> err_dbg(4, s);
             err_dbg.zero();
-            int maxWords = 1;
-            for (int k = 0; k < K; k++) {
-                maxWords = std::max(maxWords, (J.h[k].m + 31) / 32);
-                for (int f0 = 0; f0 < J.h[k].n; f0 += SCH_FCHUNK)
-                    chunks.push_back({k, f0, std::min(J.h[k].n, f0 + SCH_FCHUNK)});
-            }
-            DevBuf<SchurChunk> dChunks(chunks.size(), s);
-            dChunks.upload(chunks);
             size_t shb = sizeof(double) * (2 * SCH_NB * SCH_CMAX * SCH_LD + SCH_NB * 4) +
                          sizeof(int) * (SCH_NB + SCH_CMAX + 4 + 2 * (size_t)maxWords) + 16;
             if (shb > 48 * 1024)
