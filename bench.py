@@ -251,6 +251,7 @@ def main():
     roof = None
     stages = {}
     if world == 1:
+        step_resident()                      # re-warm the stream-ordered pool after the e2e uploads
         api.stats_reset(stage_timing=True)
         step_resident()
         st = api.stats()["stages"]

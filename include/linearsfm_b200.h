@@ -16,6 +16,8 @@
 #ifndef LINEARSFM_B200_H
 #define LINEARSFM_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -110,6 +112,12 @@ int lsfm_tree_result_count(const lsfm_tree *tree);
 int lsfm_tree_result_shape(const lsfm_tree *tree, int idx, lsfm_map *shape_only);
 int lsfm_tree_download(const lsfm_tree *tree, int idx, lsfm_map *out);
 int lsfm_tree_download_state(const lsfm_tree *tree, int idx, int *stno, double *stVal);
+/* Device-to-device hand-over of a whole map between ranks (multi-GPU tree levels): a map is
+ * packed into / unpacked from ONE contiguous device buffer whose layout depends only on its shape
+ * (m, n, nU, nW), so the buffer can be moved by NCCL send/recv or a peer copy as raw bytes.       */
+size_t lsfm_map_device_bytes(const lsfm_map *shape);
+int lsfm_tree_export_device(const lsfm_tree *tree, int idx, void *dst_device, size_t bytes);
+int lsfm_tree_append_device(lsfm_tree *tree, const lsfm_map *shape, const void *src_device, size_t bytes);
 /* replace leaf/result set by host maps (multi-GPU hand-over between ranks)                      */
 int lsfm_tree_set_maps(lsfm_tree *tree, const lsfm_map *maps, int num);
 void lsfm_tree_free(lsfm_tree *tree);

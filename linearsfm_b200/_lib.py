@@ -38,7 +38,7 @@ EXPORTS = [
     "lsfm_run_stereo", "lsfm_tree_create_stereo", "lsfm_tree_solve", "lsfm_tree_result_count",
     "lsfm_tree_result_shape", "lsfm_tree_download", "lsfm_tree_download_state", "lsfm_tree_set_maps",
     "lsfm_tree_free", "lsfm_tree_last_solve_ms", "lsfm_tree_adopt_result", "lsfm_tree_append_maps",
-    "lsfm_tree_reset",
+    "lsfm_tree_reset", "lsfm_map_device_bytes", "lsfm_tree_export_device", "lsfm_tree_append_device",
     "lsfm_load_localmap_stereo", "lsfm_save_outputs", "lsfm_cli_main",
 ]
 
@@ -69,6 +69,10 @@ def lib():
         L.lsfm_tree_last_solve_ms.argtypes = [C.c_void_p]
         L.lsfm_tree_adopt_result.argtypes = [C.c_void_p]
         L.lsfm_tree_reset.argtypes = [C.c_void_p]
+        L.lsfm_map_device_bytes.restype = C.c_size_t
+        L.lsfm_map_device_bytes.argtypes = [C.POINTER(LsfmMap)]
+        L.lsfm_tree_export_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.lsfm_tree_append_device.argtypes = [C.c_void_p, C.POINTER(LsfmMap), C.c_void_p, C.c_size_t]
         L.lsfm_tree_append_maps.argtypes = [C.c_void_p, C.POINTER(LsfmMap), C.c_int]
         L.lsfm_tree_set_maps.argtypes = [C.c_void_p, C.POINTER(LsfmMap), C.c_int]
         L.lsfm_tree_create_stereo.argtypes = [C.POINTER(LsfmMap), C.c_int, C.POINTER(C.c_void_p)]

@@ -143,6 +143,15 @@ class Tree:
         check(lib().lsfm_tree_append_maps(self._h, arr, C.c_int(len(maps))))
         self.num += len(maps)
 
+    def export_device(self, idx: int, dst_ptr: int, nbytes: int):
+        """pack result map `idx` into the contiguous device buffer at dst_ptr (D2D copies)."""
+        check(lib().lsfm_tree_export_device(self._h, C.c_int(idx), C.c_void_p(dst_ptr), C.c_size_t(nbytes)))
+
+    def append_device(self, shape: LsfmMap, src_ptr: int, nbytes: int):
+        """append a map packed by export_device (possibly on another GPU) to the input set."""
+        check(lib().lsfm_tree_append_device(self._h, C.byref(shape), C.c_void_p(src_ptr), C.c_size_t(nbytes)))
+        self.num += 1
+
     def reset(self):
         """input set := the maps of the last upload (still resident in HBM)."""
         check(lib().lsfm_tree_reset(self._h))

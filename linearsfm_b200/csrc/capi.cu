@@ -263,6 +263,62 @@ int lsfm_tree_set_maps(lsfm_tree *tree, const lsfm_map *maps, int num)
     });
 }
 
+static DMap shape_of(const lsfm_map *s)
+{
+    DMap d;
+    memset(&d, 0, sizeof(d));
+    d.Ref = s->Ref; d.FRef = s->FRef; d.m = s->m; d.n = s->n; d.nU = s->nU; d.nW = s->nW;
+    return d;
+}
+
+size_t lsfm_map_device_bytes(const lsfm_map *shape)
+{
+    DMap d = shape_of(shape);
+    return map_layout(d, nullptr);
+}
+
+int lsfm_tree_export_device(const lsfm_tree *tree, int idx, void *dst_device, size_t bytes)
+{
+    return guarded([&] {
+        if (idx < 0 || idx >= (int)tree->result.size()) throw LsfmError(LSFM_ERR_ARG, "bad result index");
+        const DMap &s = tree->result[idx].d;
+        DMap d = s;
+        size_t need = map_layout(d, (char *)dst_device);
+        if (bytes < need) throw LsfmError(LSFM_ERR_ARG, "export buffer too small");
+        cudaStream_t st = g_ctx->stream;
+        auto cp = [&](void *dst, const void *src, size_t b) {
+            if (b) CUDA_CHECK(cudaMemcpyAsync(dst, src, b, cudaMemcpyDeviceToDevice, st));
+        };
+        cp(d.poseNo, s.poseNo, sizeof(int) * s.m);
+        cp(d.poseVal, s.poseVal, sizeof(double) * 6 * (size_t)s.m);
+        cp(d.featNo, s.featNo, sizeof(int) * s.n);
+        cp(d.featVal, s.featVal, sizeof(double) * 3 * (size_t)s.n);
+        cp(d.U, s.U, sizeof(double) * 36 * (size_t)s.nU);
+        cp(d.Ui, s.Ui, sizeof(int) * s.nU);
+        cp(d.Uj, s.Uj, sizeof(int) * s.nU);
+        cp(d.W, s.W, sizeof(double) * 18 * (size_t)s.nW);
+        cp(d.photo, s.photo, sizeof(int) * s.nW);
+        cp(d.feature, s.feature, sizeof(int) * s.nW);
+        cp(d.V, s.V, sizeof(double) * 9 * (size_t)s.n);
+        cp(d.wPtr, s.wPtr, sizeof(int) * (s.n + 1));
+        CUDA_CHECK(cudaStreamSynchronize(st));     // the caller hands the buffer to NCCL on another stream
+    });
+}
+
+int lsfm_tree_append_device(lsfm_tree *tree, const lsfm_map *shape, const void *src_device, size_t bytes)
+{
+    return guarded([&] {
+        std::vector<DMap> shapes{shape_of(shape)};
+        std::vector<MapHandle> h = alloc_maps(*g_ctx, shapes);
+        DMap probe = shapes[0];
+        size_t need = map_layout(probe, nullptr);
+        if (bytes < need) throw LsfmError(LSFM_ERR_ARG, "import buffer too small");
+        CUDA_CHECK(cudaMemcpyAsync(h[0].arena->base, src_device, need, cudaMemcpyDeviceToDevice, g_ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(g_ctx->stream));
+        tree->leaves.push_back(h[0]);
+    });
+}
+
 int lsfm_tree_reset(lsfm_tree *tree)
 {
     tree->result.clear();

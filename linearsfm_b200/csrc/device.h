@@ -7,17 +7,78 @@
 #include <map>
 #include <string>
 
+// Caching device allocator.  Every allocation / free of the library happens in program order on ONE
+// stream, so a freed block may be handed out again immediately: the kernels that used it were
+// enqueued before the kernels of its next owner.  Blocks are never returned to the driver while the
+// context lives; a merge-tree solve repeats the same size sequence, so after the first solve no
+// cudaMalloc is issued at all.  (cudaMallocAsync showed 2x run-to-run variation of the whole solve.)
+struct DevicePool {
+    std::multimap<size_t, void *> free_;
+    std::map<void *, size_t> live_;
+    size_t reserved = 0;
+    static size_t round_up(size_t b)
+    {
+        if (b < 4096) return (b + 511) & ~(size_t)511;
+        if (b < (1u << 20)) return (b + 4095) & ~(size_t)4095;
+        if (b < (1u << 26)) return (b + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+        return (b + (1u << 24) - 1) & ~(size_t)((1u << 24) - 1);
+    }
+    void *alloc(size_t bytes)
+    {
+        size_t need = round_up(bytes ? bytes : 1);
+        auto it = free_.lower_bound(need);
+        // accept a cached block unless it wastes more than 25 % (+64 MB slack for the big arenas)
+        if (it != free_.end() && it->first <= need + need / 4 + (need >= (1u << 26) ? (1u << 26) : 0)) {
+            void *p = it->second;
+            live_[p] = it->first;
+            free_.erase(it);
+            return p;
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) {
+            // out of memory: drop the cache and retry once
+            cudaGetLastError();
+            release_cached();
+            e = cudaMalloc(&p, need);
+            if (e != cudaSuccess)
+                throw LsfmError(LSFM_ERR_CUDA, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        }
+        reserved += need;
+        live_[p] = need;
+        return p;
+    }
+    void free(void *p)
+    {
+        auto it = live_.find(p);
+        if (it == live_.end()) return;
+        free_.insert({it->second, p});
+        live_.erase(it);
+    }
+    void release_cached()
+    {
+        cudaDeviceSynchronize();
+        for (auto &kv : free_) { cudaFree(kv.second); reserved -= kv.first; }
+        free_.clear();
+    }
+    static DevicePool &get()
+    {
+        static DevicePool pool;
+        return pool;
+    }
+};
+
 struct Arena {
     char *base = nullptr;
     size_t bytes = 0, used = 0;
     cudaStream_t stream = 0;
     Arena(size_t nbytes, cudaStream_t s) : bytes(nbytes ? nbytes : 256), stream(s)
     {
-        CUDA_CHECK(cudaMallocAsync((void **)&base, bytes, stream));
+        base = (char *)DevicePool::get().alloc(bytes);
     }
     ~Arena()
     {
-        if (base) cudaFreeAsync(base, stream);
+        if (base) DevicePool::get().free(base);
     }
     Arena(const Arena &) = delete;
     Arena &operator=(const Arena &) = delete;
@@ -42,11 +103,11 @@ template <class T> struct DevBuf {
     {
         release();
         n = count; stream = s;
-        CUDA_CHECK(cudaMallocAsync((void **)&p, (count ? count : 1) * sizeof(T), s));
+        p = (T *)DevicePool::get().alloc((count ? count : 1) * sizeof(T));
     }
     void release()
     {
-        if (p) cudaFreeAsync(p, stream);
+        if (p) DevicePool::get().free(p);
         p = nullptr; n = 0;
     }
     ~DevBuf() { release(); }

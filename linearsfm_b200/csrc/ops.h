@@ -24,6 +24,7 @@ static inline double map_bytes(const DMap &d)
 
 // Allocate one arena holding `shapes.size()` maps with the given sizes; fills pointers of `out`.
 std::vector<MapHandle> alloc_maps(Context &ctx, std::vector<DMap> &shapes);
+size_t map_layout(DMap &shape, char *base);
 
 // a2-a5: re-express each map in the frame of pose `newRef[k]` (LinearSFMImp.cpp:349-1924).
 std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<MapHandle> &in,

@@ -488,6 +488,28 @@ std::vector<MapHandle> alloc_maps(Context &ctx, std::vector<DMap> &shapes)
     return out;
 }
 
+// Byte layout of ONE map inside an arena of its own (same order / padding as alloc_maps): assigns
+// the pointers of `s` relative to `base` and returns the size.  Used for device-to-device hand-over
+// of a whole map between ranks: both sides derive identical offsets from the shape alone.
+size_t map_layout(DMap &s, char *base)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *p = base + off; off += Arena::pad(bytes); return p; };
+    s.poseNo = (int *)take(sizeof(int) * s.m);
+    s.poseVal = (double *)take(sizeof(double) * 6 * (size_t)s.m);
+    s.featNo = (int *)take(sizeof(int) * s.n);
+    s.featVal = (double *)take(sizeof(double) * 3 * (size_t)s.n);
+    s.U = (double *)take(sizeof(double) * 36 * (size_t)s.nU);
+    s.Ui = (int *)take(sizeof(int) * s.nU);
+    s.Uj = (int *)take(sizeof(int) * s.nU);
+    s.W = (double *)take(sizeof(double) * 18 * (size_t)s.nW);
+    s.photo = (int *)take(sizeof(int) * s.nW);
+    s.feature = (int *)take(sizeof(int) * s.nW);
+    s.V = (double *)take(sizeof(double) * 9 * (size_t)s.n);
+    s.wPtr = (int *)take(sizeof(int) * (s.n + 1));
+    return off;
+}
+
 static void exclusive_scan(Context &ctx, const int *in, int *out, int n)
 {
     size_t tmp_bytes = 0;

@@ -112,11 +112,16 @@ def run_sharded(backend, num_maps: int, rank: int, world: int, device=None):
             if i + 1 < len(owners):
                 a, b = owners[i], owners[i + 1]
                 if rank == b:
-                    send_map(backend.get(0), a, device)
+                    if hasattr(backend, "send_first"):
+                        backend.send_first(a, device)          # device-to-device (NCCL)
+                    else:
+                        send_map(backend.get(0), a, device)
                     backend.set([])
                 elif rank == a:
-                    cur = recv_map(b, device)
-                    backend.append([cur])
+                    if hasattr(backend, "recv_append"):
+                        backend.recv_append(b, device)
+                    else:
+                        backend.append([recv_map(b, device)])
                     backend.solve_levels(i, 1)
             else:
                 a = owners[i]
@@ -154,12 +159,45 @@ class TreeBackend:
         return lm
 
     def set(self, maps):
-        self.tree.set_maps(maps)
-        self.n = len(maps)
+        if maps:
+            self.tree.set_maps(maps)       # replaces the uploaded leaf set
+        self.n = len(maps)                 # empty: the rank is done, keep its uploaded leaves resident
 
     def append(self, maps):
         self.tree.append_maps(maps)
         self.n += len(maps)
+
+    def send_first(self, dst, device):
+        """Hand the single held map to rank `dst` without leaving device memory: pack it into one
+        contiguous buffer (D2D copies on our stream) and NCCL-send the raw bytes."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from ._lib import lib
+        self.tree.solve(first_index=0, max_levels=0)          # input set -> result set (no work)
+        s = self.tree.result_shape(0)
+        nbytes = int(lib().lsfm_map_device_bytes(C.byref(s)))
+        head = torch.tensor([s.Ref, s.FRef, s.m, s.n, s.nU, s.nW, nbytes, 0], dtype=torch.int64, device=device)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.tree.export_device(0, buf.data_ptr(), nbytes)
+        dist.send(head, dst)
+        dist.send(buf, dst)
+        torch.cuda.synchronize(device)
+        self.tree.adopt_result()
+
+    def recv_append(self, src, device):
+        import torch
+        import torch.distributed as dist
+        from ._lib import LsfmMap
+        head = torch.zeros(8, dtype=torch.int64, device=device)
+        dist.recv(head, src)
+        h = [int(x) for x in head.cpu().tolist()]
+        buf = torch.empty(h[6], dtype=torch.uint8, device=device)
+        dist.recv(buf, src)
+        torch.cuda.synchronize(device)
+        shape = LsfmMap(Ref=h[0], FRef=h[1], m=h[2], n=h[3], nU=h[4], nW=h[5], r=6 * h[2] + 3 * h[3])
+        self.tree.append_device(shape, buf.data_ptr(), h[6])
+        self.n += 1
 
     def finish(self):
         self.tree.solve(first_index=0, max_levels=-1)

@@ -1,0 +1,46 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref).  Run in the build
+container (needs /root/reference to build the oracle):  python tests/golden/make_golden.py
+Each fixture stores the inputs and the reference's outputs of one operator / one whole tree so the
+GPU path can be checked on a box where the reference sources do not exist."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_oracle as ro  # noqa: E402
+from linearsfm_b200 import synth  # noqa: E402
+
+FIELDS = ("stno", "stVal", "U", "Ui", "Uj", "W", "photo", "feature", "V", "FBlock")
+
+
+def pack(prefix, lm, d):
+    for f in FIELDS:
+        d[f"{prefix}_{f}"] = getattr(lm, f)
+    d[f"{prefix}_meta"] = np.array([lm.Ref, lm.FRef, lm.m, lm.n], np.int64)
+
+
+def main():
+    ro.build()
+    maps = synth.make_stereo_scene(5, feats_per_frame=6, seed=424242)
+    d = {}
+    for i, lm in enumerate(maps):
+        pack(f"leaf{i}", lm, d)
+    t0 = ro.transform_stereo(maps[0], maps[1].Ref)
+    pack("tf0", t0, d)
+    j0 = ro.join_stereo(t0, maps[1])
+    pack("join0", j0, d)
+    t2 = ro.transform_stereo(maps[2], maps[3].Ref)
+    j1 = ro.join_stereo(t2, maps[3])
+    j1b = ro.transform_stereo(j1, j1.FRef)
+    pack("rebase1", j1b, d)
+    fin, _, _ = ro.run_tree_stereo(maps)
+    pack("final", fin, d)
+    np.savez_compressed(os.path.join(HERE, "stereo_n5.npz"), **d)
+    print("wrote stereo_n5.npz", {k: v.shape for k, v in list(d.items())[:3]}, "final m,n", fin.m, fin.n)
+
+
+if __name__ == "__main__":
+    main()
