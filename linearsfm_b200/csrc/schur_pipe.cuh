@@ -1,0 +1,245 @@
+// k_schur_pipe: register-tiled, software-pipelined Schur complement kernel (included by solve.cu).
+//
+//   S(p,q) -= sum_f W_pf V_f^-1 W_qf^T ,  E_p -= sum_f W_pf V_f^-1 eF_f      (LinearSFMImp.cpp:2246-2332)
+//
+// One CTA per chunk of SCH_FCHUNK consecutive features of one join.  The <= CMAX distinct poses the
+// chunk touches get local indices (bitmap over the join's poses + popcount prefix).  Each thread
+// owns two pose-pair slots and keeps their 6x6 blocks in REGISTERS for the whole chunk; the chunk's
+// features stream through shared memory in batches of NB:
+//     raw stage   : cp.async (LDGSTS) of the batch's contiguous W blocks / photo ids / V^-1 / eF into
+//                   a DOUBLE-BUFFERED raw area -- issued one batch ahead, so HBM latency overlaps
+//                   the arithmetic of the previous batch;
+//     re-layout   : raw -> [feature][local pose] padded tiles (stride 19 doubles: conflict-free
+//                   64-bit LDS), computing W V^-1 on the way;
+//     pair update : thread (i,j) adds W V^-1|_i * W^T|_j for every feature that sees both poses.
+// One flush of 36 FP64 atomics per touched pair and chunk.  Three instantiations trade registers /
+// shared memory for resident CTAs: (CMAX 8, 64 thr) x4-5 per SM for the lower tree levels,
+// (16, 128 thr) x2, (31, 256 thr) x1 for the top levels.
+#pragma once
+
+namespace schur_pipe {
+
+constexpr int LD = 19;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+template <int CMAX, int NB>
+struct Layout {
+    // all offsets in bytes, 16-byte aligned where cp.async needs it
+    static constexpr int MAXBLK = NB * CMAX;
+    static constexpr int rawW = 0;                                   // [2][MAXBLK*18] double
+    static constexpr int rawVi = rawW + 2 * MAXBLK * 18 * 8;         // [2][NB*9+1] double (+1: 16B pad)
+    static constexpr int rawEf = rawVi + 2 * (NB * 9 + 1) * 8;       // [2][NB*3+1] double
+    static constexpr int rawPh = rawEf + 2 * (NB * 3 + 1) * 8;       // [2][MAXBLK] int
+    static constexpr int Wsm = rawPh + 2 * MAXBLK * 4;               // [NB][CMAX][LD] double
+    static constexpr int WVsm = Wsm + NB * CMAX * LD * 8;            // [NB][CMAX][LD] double
+    static constexpr int present = WVsm + NB * CMAX * LD * 8;        // [2][NB] unsigned (by raw buffer)
+    static constexpr int poses = present + 2 * NB * 4;               // [CMAX+1] int
+    static constexpr int misc = poses + (CMAX + 1) * 4;              // [4] int
+    static constexpr int wptr = misc + 16;                           // [SCH_FCHUNK+1] int
+    static constexpr int bitmap = wptr + (SCH_FCHUNK + 1 + 3) / 4 * 16;   // [words] unsigned, then [words] int prefix
+    static size_t bytes(int words) { return (size_t)bitmap + 8 * (size_t)words + 16; }
+};
+
+template <int CMAX, int NB, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
+             const int *__restrict__ featPre, const int *__restrict__ posePre,
+             const double *__restrict__ Vinv, const double *__restrict__ eF,
+             const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
+             double *__restrict__ S, double *__restrict__ E)
+{
+    typedef Layout<CMAX, NB> L;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double *rawW = (double *)(smraw + L::rawW);
+    double *rawVi = (double *)(smraw + L::rawVi);
+    double *rawEf = (double *)(smraw + L::rawEf);
+    int *rawPh = (int *)(smraw + L::rawPh);
+    double *Wsm = (double *)(smraw + L::Wsm);
+    double *WVsm = (double *)(smraw + L::WVsm);
+    unsigned *present = (unsigned *)(smraw + L::present);
+    int *poses = (int *)(smraw + L::poses);
+    int *misc = (int *)(smraw + L::misc);
+    int *wptr = (int *)(smraw + L::wptr);
+    unsigned *bitmap = (unsigned *)(smraw + L::bitmap);
+
+    const FeatChunk ch = chunks[blockIdx.x];
+    const DMap &M = J[ch.k];
+    const int k = ch.k;
+    const int words = (M.m + 31) >> 5;
+    int *prefix = (int *)(bitmap + words);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nfeat = ch.f1 - ch.f0;
+
+    for (int i = tid; i <= nfeat; i += THREADS) wptr[i] = M.wPtr[ch.f0 + i];
+    for (int i = tid; i < words; i += THREADS) bitmap[i] = 0u;
+    __syncthreads();
+    const int w0 = wptr[0], w1 = wptr[nfeat];
+    for (int j = w0 + tid; j < w1; j += THREADS) {
+        int p = M.photo[j];
+        atomicOr(&bitmap[p >> 5], 1u << (p & 31));
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < words; base += 32) {
+            int c = (base + lane < words) ? __popc(bitmap[base + lane]) : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (base + lane < words) prefix[base + lane] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) misc[0] = run;
+    }
+    __syncthreads();
+    const int nposes = misc[0];
+    if (nposes == 0) return;
+    if (nposes > CMAX) {                 // not expected: the host picks CMAX from the measured maximum
+        for (int a = w0 + tid; a < w1; a += THREADS)
+            schur_block_slow(M, k, a, featPre, posePre, Vinv, eF, keys, rowPtr, S, E);
+        return;
+    }
+    for (int i = tid; i < words; i += THREADS) {
+        unsigned b = bitmap[i];
+        int r = prefix[i];
+        while (b) { int bit = __ffs(b) - 1; poses[r++] = i * 32 + bit; b &= b - 1; }
+    }
+    const int npairs = nposes * (nposes + 1) / 2;
+    const int rep = max(1, min(NB, (2 * THREADS) / npairs));
+    int pi[2], pj[2], pr0[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        pi[u] = -1; pj[u] = -1; pr0[u] = 0;
+        int q = tid + u * THREADS;
+        int r = q / npairs, t = q - r * npairs;
+        if (r < rep) {
+            int i = 0;
+            while (t >= nposes - i) { t -= nposes - i; i++; }
+            pi[u] = i; pj[u] = i + t; pr0[u] = r;
+        }
+    }
+    double acc[2][36], eacc[2][6];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+#pragma unroll
+        for (int q = 0; q < 36; q++) acc[u][q] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) eacc[u][q] = 0.0;
+    }
+    bool touched[2] = {false, false};
+
+    const double *Wg = M.W;
+    const int *Pg = M.photo;
+    const double *Vg = Vinv + 9 * (size_t)(featPre[k] + ch.f0);
+    const double *Eg = eF + 3 * (size_t)(featPre[k] + ch.f0);
+    const int nbatches = (nfeat + NB - 1) / NB;
+
+    // raw stage of batch `bi` into buffer `buf` (asynchronous)
+    auto issue = [&](int bi, int buf) {
+        const int fb0 = bi * NB, nbf = min(NB, nfeat - fb0);
+        const int b0 = wptr[fb0], nblk = wptr[fb0 + nbf] - b0;
+        double *dW = rawW + buf * (L::MAXBLK * 18);
+        const double *sW = Wg + 18 * (size_t)b0;
+        for (int c = tid; c < nblk * 9; c += THREADS) cp_async16(dW + 2 * c, sW + 2 * c);
+        int *dP = rawPh + buf * L::MAXBLK;
+        for (int c = tid; c < nblk; c += THREADS) cp_async4(dP + c, Pg + b0 + c);
+        double *dV = rawVi + buf * (NB * 9 + 1);
+        for (int c = tid; c < nbf * 9; c += THREADS) cp_async8(dV + c, Vg + 9 * (size_t)fb0 + c);
+        double *dE = rawEf + buf * (NB * 3 + 1);
+        for (int c = tid; c < nbf * 3; c += THREADS) cp_async8(dE + c, Eg + 3 * (size_t)fb0 + c);
+        cp_async_commit();
+    };
+
+    if (tid < 2 * NB) present[tid] = 0u;
+    issue(0, 0);
+    for (int bi = 0; bi < nbatches; bi++) {
+        const int buf = bi & 1;
+        const int fb0 = bi * NB, nbf = min(NB, nfeat - fb0);
+        const int b0 = wptr[fb0], nblk = wptr[fb0 + nbf] - b0;
+        cp_async_wait_all();
+        __syncthreads();                               // batch bi landed; previous pair update done
+        if (tid < NB) present[(buf ^ 1) * NB + tid] = 0u;      // for the next batch (set after its barrier)
+        if (bi + 1 < nbatches) issue(bi + 1, buf ^ 1);
+        // re-layout raw -> padded tiles, W V^-1 on the way
+        const double *rW = rawW + buf * (L::MAXBLK * 18);
+        const int *rP = rawPh + buf * L::MAXBLK;
+        const double *rV = rawVi + buf * (NB * 9 + 1);
+        for (int e = tid; e < nblk * 18; e += THREADS) {
+            int blk = e / 18, el = e - 18 * blk;
+            int gb = b0 + blk;
+            int fb = 0;
+#pragma unroll
+            for (int q = 1; q < NB; q++) fb += (q < nbf && wptr[fb0 + q] <= gb);
+            int p = rP[blk];
+            int slot = prefix[p >> 5] + __popc(bitmap[p >> 5] & ((1u << (p & 31)) - 1u));
+            const double *wr = rW + 18 * blk + 3 * (el / 3);
+            const double *vi = rV + 9 * fb + 3 * (el % 3);
+            Wsm[(fb * CMAX + slot) * LD + el] = rW[18 * blk + el];
+            WVsm[(fb * CMAX + slot) * LD + el] = wr[0] * vi[0] + wr[1] * vi[1] + wr[2] * vi[2];
+            if (el == 0) atomicOr(&present[buf * NB + fb], 1u << slot);
+        }
+        __syncthreads();
+        const double *rE = rawEf + buf * (NB * 3 + 1);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (pi[u] < 0) continue;
+            for (int fb = pr0[u]; fb < nbf; fb += rep) {
+                unsigned pr = present[buf * NB + fb];
+                if (((pr >> pi[u]) & (pr >> pj[u]) & 1u) == 0u) continue;
+                touched[u] = true;
+                const double *wv = WVsm + (fb * CMAX + pi[u]) * LD;
+                const double *w = Wsm + (fb * CMAX + pj[u]) * LD;
+                double b[18];
+#pragma unroll
+                for (int q = 0; q < 18; q++) b[q] = w[q];
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    double a0 = wv[3 * r], a1 = wv[3 * r + 1], a2 = wv[3 * r + 2];
+#pragma unroll
+                    for (int c = 0; c < 6; c++)
+                        acc[u][6 * r + c] += a0 * b[3 * c] + a1 * b[3 * c + 1] + a2 * b[3 * c + 2];
+                    if (pi[u] == pj[u]) {
+                        const double *ef = rE + 3 * fb;
+                        eacc[u][r] += a0 * ef[0] + a1 * ef[1] + a2 * ef[2];
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        if (!touched[u]) continue;
+        int gi = poses[pi[u]], gj = poses[pj[u]];
+        int slot = find_slot(keys, rowPtr, posePre[k] + gi, pair_key(k, gi, gj));
+        double *sp = S + 36 * (size_t)slot;
+#pragma unroll
+        for (int q = 0; q < 36; q++) atomicAdd(sp + q, -acc[u][q]);
+        if (pi[u] == pj[u]) {
+            double *e = E + 6 * (size_t)(posePre[k] + gi);
+#pragma unroll
+            for (int q = 0; q < 6; q++) atomicAdd(e + q, -eacc[u][q]);
+        }
+    }
+}
+
+} // namespace schur_pipe

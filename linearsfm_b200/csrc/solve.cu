@@ -84,7 +84,8 @@ struct FeatChunk { int k, f0, f1; };
 
 __global__ void __launch_bounds__(PAT_THREADS)
 k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, int mode,
-            int *__restrict__ cnt, const int *__restrict__ scan, u64 *__restrict__ keys)
+            int *__restrict__ cnt, const int *__restrict__ scan, u64 *__restrict__ keys,
+            int *__restrict__ maxNposes)
 {
     extern __shared__ unsigned smu[];
     const FeatChunk ch = chunks[blockIdx.x];
@@ -124,6 +125,7 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, in
     }
     __syncthreads();
     const int nposes = misc[0];
+    if (mode == 0 && tid == 0 && maxNposes) atomicMax(maxNposes, nposes);
     if (nposes <= PAT_CMAX) {
         for (int f = ch.f0 + tid; f < ch.f1; f += nt) {
             int a0 = M.wPtr[f], a1 = M.wPtr[f + 1];
@@ -344,6 +346,11 @@ __device__ __noinline__ void schur_block_slow(const DMap &M, int k, int a, const
     }
 }
 
+constexpr int SCH_FCHUNK = 128;        // features per chunk (pattern + Schur kernels)
+} // namespace
+#include "schur_pipe.cuh"
+namespace {
+
 // v2: one CTA per chunk of consecutive features of one join.  The distinct poses seen by the chunk
 // (<= SCH_CMAX: a handful of "hub" poses + the local observers) get a local index; thread t owns the
 // pose pair (i<=j) and keeps its 6x6 block of S in REGISTERS while the chunk's features stream
@@ -351,7 +358,6 @@ __device__ __noinline__ void schur_block_slow(const DMap &M, int k, int a, const
 // touched pair and chunk replaces 36 atomics per pair and FEATURE.
 constexpr int SCH_CMAX = 31;          // 31*32/2 = 496 pairs = 2 per thread of a 256-thread CTA
 constexpr int SCH_NB = 16;            // features staged per barrier
-constexpr int SCH_FCHUNK = 128;
 constexpr int SCH_THREADS = 256;
 constexpr int SCH_LD = 19;            // padded block stride (doubles): conflict-free 64-bit LDS
 
@@ -715,6 +721,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     DevBuf<FeatChunk> dChunks(nChunks, s);
     dChunks.upload(chunks);
     int nRaw = 0;
+    int maxNposes = 1 << 30;             // max distinct poses of any chunk (measured by k_pat_chunk)
+    DevBuf<int> dMaxNp(1, s);
     DevBuf<u64> rawKeys, sortedKeys, keys;
     static const bool pat_v1 = getenv("LSFM_PATTERN_V1") != nullptr;
     if (pat_v1) {
@@ -734,16 +742,18 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
         int nChunkKeys = 0;
         if (nChunks > 0) {
-            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 0, pcnt.p, nullptr, nullptr); nl++;
+            dMaxNp.zero();
+            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 0, pcnt.p, nullptr, nullptr, dMaxNp.p); nl++;
             exclusive_scan(ctx, pcnt.p, pscan.p, nChunks + 1); nl += 2;
             CUDA_CHECK(cudaMemcpyAsync(&nChunkKeys, pscan.p + nChunks, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaMemcpyAsync(&maxNposes, dMaxNp.p, sizeof(int), cudaMemcpyDeviceToHost, s));
             CUDA_CHECK(cudaStreamSynchronize(s));
         }
         nRaw = nChunkKeys + J.totU;
         rawKeys.alloc(nRaw, s); sortedKeys.alloc(nRaw, s); keys.alloc(nRaw, s);
         if (J.totU > 0) { k_pat_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, K, J.totU, rawKeys.p); nl++; }
         if (nChunks > 0) {
-            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 1, nullptr, pscan.p, rawKeys.p + J.totU); nl++;
+            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 1, nullptr, pscan.p, rawKeys.p + J.totU, nullptr); nl++;
         }
     }
     {
@@ -791,6 +801,21 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         if (use_v1) {
             k_schur<<<ceil_div(J.totW, 128), 128, 0, s>>>(J.d.p, J.dWPre.p, J.dFeatPre.p, J.dPosePre.p, K, J.totW,
                                                          Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p); nl++;
+        } else if (getenv("LSFM_SCHUR_V2") == nullptr) {
+            // pipelined kernel; instantiation chosen from the measured max #distinct poses per chunk
+            auto launch = [&](auto kern, size_t shb, int threads) {
+                if (shb > 48 * 1024)
+                    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
+                kern<<<nChunks, threads, shb, s>>>(J.d.p, dChunks.p, J.dFeatPre.p, J.dPosePre.p, Vinv.p, eF,
+                                                  keys.p, rowPtr.p, S.p, E.p);
+            };
+            if (maxNposes <= 8)
+                launch(schur_pipe::k_schur_pipe<8, 8, 64>, schur_pipe::Layout<8, 8>::bytes(maxWords), 64);
+            else if (maxNposes <= 16)
+                launch(schur_pipe::k_schur_pipe<16, 8, 128>, schur_pipe::Layout<16, 8>::bytes(maxWords), 128);
+            else
+                launch(schur_pipe::k_schur_pipe<31, 8, 256>, schur_pipe::Layout<31, 8>::bytes(maxWords), 256);
+            nl++;
         } else {
             DevBuf<int> err_dbg(4, s);
             err_dbg.zero();

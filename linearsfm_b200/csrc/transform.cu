@@ -427,6 +427,435 @@ k_wvcong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restr
     sm::warp_agg_atomic_add<36>(O.U + 36 * (size_t)pid, S, live);
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2 of the W/V congruence: "lanes = blocks".
+//   k_tf_featprep : one thread per feature  -> X', V', T_f scratch, the V part of W'(pos,f) and of
+//                   U'(pos,pos), output CSR/labels of the new (posID,f) block.
+//   k_tf_wblock   : one thread per OLD W block (a warp reads 32 consecutive 144-byte blocks = one
+//                   contiguous 4.6 KB span) -> D_p^T W D_f written to its slot; the per-feature sum
+//                   into W'(pos,f) by a warp-segmented shuffle reduction; the per-pose sums into
+//                   U'(p,pos) / U'(pos,pos) through a per-CTA shared-memory hash of 6x6 accumulators
+//                   that is flushed once per CTA (global FP64 atomics cost ~1e10/s, so they are
+//                   aggregated across the 1024 blocks a CTA walks).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_tf_featprep(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ featPre,
+              int K, int totFeat, const TfConst *__restrict__ tc, const int *__restrict__ fScan,
+              double *__restrict__ TfBuf)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = g < totFeat;
+    int k = live ? seg_find(featPre, K, g) : 0;
+    int f = live ? g - featPre[k] : 0;
+    const DMap &M = in[k];
+    const DMap &O = out[k];
+    const TfConst &c = tc[k];
+    double S[36];
+#pragma unroll
+    for (int i = 0; i < 36; i++) S[i] = 0.0;
+    if (live) {
+        const double *x = M.featVal + 3 * (size_t)f;
+        double d0[3] = {x[0] - c.t[0], x[1] - c.t[1], x[2] - c.t[2]};
+        double xn[3];
+        geom::mat3_vec(c.R, d0, xn);
+        double *y = O.featVal + 3 * (size_t)f;
+        y[0] = xn[0]; y[1] = xn[1]; y[2] = xn[2];
+        O.featNo[f] = M.featNo[f];
+        double d[3] = {xn[0] - c.tn[0], xn[1] - c.tn[1], xn[2] - c.tn[2]};
+        double Tf[9], v[3];
+        geom::mat3_vec(c.QA, d, v); Tf[0] = v[0]; Tf[3] = v[1]; Tf[6] = v[2];
+        geom::mat3_vec(c.QB, d, v); Tf[1] = v[0]; Tf[4] = v[1]; Tf[7] = v[2];
+        geom::mat3_vec(c.QG, d, v); Tf[2] = v[0]; Tf[5] = v[1]; Tf[8] = v[2];
+        sm::store<9>(TfBuf + 9 * (size_t)g, Tf);
+        double Q[9], V[9], VQ[9], VT[9], Vn[9], M1[9], M2[9];
+        sm::load<9>(c.Q, Q);
+        sm::load<9>(M.V + 9 * (size_t)f, V);
+        sm::mm<3, 3, 3>(V, Q, VQ);
+        sm::mm<3, 3, 3>(V, Tf, VT);
+        sm::mtm<3, 3, 3>(Q, VQ, Vn);
+        sm::mtm<3, 3, 3>(Tf, VQ, M1);
+        sm::mtm<3, 3, 3>(Tf, VT, M2);
+        sm::store<9>(O.V + 9 * (size_t)f, Vn);
+        int o0 = fScan[g] - fScan[featPre[k]];
+        O.wPtr[f] = o0;
+        O.photo[o0] = c.posID;
+        O.feature[o0] = f;
+        // the (posID,f) block starts as C_f^T V D_f = [-V'; M1]; k_tf_wblock adds the W terms
+        double *wp = O.W + 18 * (size_t)o0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) { wp[i] = -Vn[i]; wp[9 + i] = M1[i]; }
+        // C_f^T V C_f = [[V', -M1^T],[-M1, M2]]
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                S[6 * r + q] = Vn[3 * r + q];
+                S[6 * r + 3 + q] = -M1[3 * q + r];
+                S[6 * (r + 3) + q] = -M1[3 * r + q];
+                S[6 * (r + 3) + 3 + q] = M2[3 * r + q];
+            }
+    }
+    sm::warp_agg_atomic_add<36>(O.U + 36 * (size_t)c.posID, S, live);
+}
+
+constexpr int TW_THREADS = 128;
+constexpr int TW_TILES = 8;            // a CTA walks TW_TILES x 128 consecutive W blocks
+constexpr int TW_HASH = 64;            // per-CTA pose hash (slots of 36 doubles)
+
+__device__ __forceinline__ int tw_hash_slot(int *keys, int key)
+{
+    unsigned h = ((unsigned)key * 2654435761u) >> 26;          // 6 bits
+    for (int probe = 0; probe < TW_HASH; probe++) {
+        int cur = keys[h];
+        if (cur == key) return (int)h;
+        if (cur == -1) {
+            int prev = atomicCAS(&keys[h], -1, key);
+            if (prev == -1 || prev == key) return (int)h;
+        }
+        h = (h + 1) & (TW_HASH - 1);
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(TW_THREADS)
+k_tf_wblock(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ wPre,
+            const int *__restrict__ featPre, const int *__restrict__ posePre, int K, int totW,
+            const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj,
+            const double *__restrict__ TfBuf)
+{
+    __shared__ int hkeys[TW_HASH];
+    __shared__ double hvals[TW_HASH][36];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < TW_HASH; i += TW_THREADS) hkeys[i] = -1;
+    for (int i = tid; i < TW_HASH * 36; i += TW_THREADS) (&hvals[0][0])[i] = 0.0;
+    __syncthreads();
+
+    const long long base = (long long)blockIdx.x * TW_THREADS * TW_TILES;
+    for (int tile = 0; tile < TW_TILES; tile++) {
+        long long gl = base + (long long)tile * TW_THREADS + tid;
+        if (base + (long long)tile * TW_THREADS >= totW) break;       // CTA-uniform
+        bool live = gl < totW;
+        int g = live ? (int)gl : 0;
+        int k = live ? seg_find(wPre, K, g) : 0;
+        int j = g - wPre[k];
+        const DMap &M = in[k];
+        const DMap &O = out[k];
+        const TfConst &c = tc[k];
+        const int pid = c.posID;
+        int f = 0, p = 0, gf = -1 - lane;          // dead lanes get unique negative keys
+        bool isPos = false;
+        double wadd[18];                            // this block's share of W'(pos,f)
+        double G[36];                               // share of U'(pos,pos) (before symmetrising)
+        double A3[36];                              // share of U'(p,pos), already oriented for slot p
+#pragma unroll
+        for (int i = 0; i < 18; i++) wadd[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 36; i++) { G[i] = 0.0; A3[i] = 0.0; }
+        if (live) {
+            f = M.feature[j];
+            p = M.photo[j];
+            gf = featPre[k] + f;
+            isPos = (p == pid);
+            double Q[9], Tf[9], W[18], X[18], a1[18];
+            sm::load<9>(c.Q, Q);
+            sm::load<9>(TfBuf + 9 * (size_t)gf, Tf);
+            sm::load<18>(M.W + 18 * (size_t)j, W);
+            const PoseJac &J = pj[posePre[k] + p];
+            const double sgn = isPos ? -1.0 : 1.0;
+            sm::mm<6, 3, 3>(W, Q, X);                                   // W Q
+            jt_mul<3>(Q, sgn, J.b1, J.c1, isPos, X, a1);               // D_p^T W Q
+            if (isPos) {
+#pragma unroll
+                for (int i = 0; i < 18; i++) wadd[i] = a1[i];
+            } else {
+                // output slot: after the new (posID,f) block, skipping blocks folded into it
+                int w0 = M.wPtr[f], skip = 0;
+                for (int i = w0; i < j; i++) skip += (M.photo[i] == pid);
+                int o = O.wPtr[f] + 1 + (j - w0) - skip;
+                sm::store<18>(O.W + 18 * (size_t)o, a1);
+                O.photo[o] = p;
+                O.feature[o] = f;
+                jt_mul<3>(Q, -1.0, J.f2, J.g2, true, X, wadd);          // C_p^T W Q
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int q = 0; q < 3; q++) G[6 * r + q] = -wadd[3 * r + q];
+            }
+            double a3[18];
+            sm::mm<6, 3, 3>(W, Tf, X);                                  // W T_f
+            jt_mul<3>(Q, sgn, J.b1, J.c1, isPos, X, a3);               // D_p^T W T_f
+            if (!isPos) {
+                double a4[18];
+                jt_mul<3>(Q, -1.0, J.f2, J.g2, true, X, a4);            // C_p^T W T_f
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int q = 0; q < 3; q++) G[6 * r + 3 + q] = a4[3 * r + q];
+            }
+            // D_p^T W C_f = [-a1 | a3], oriented for slot p: as is (p<pid), transposed (p>pid), X+X^T (p==pid)
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int q = 0; q < 6; q++) {
+                    double xrq = (q < 3) ? -a1[3 * r + q] : a3[3 * r + q - 3];
+                    if (p < pid) A3[6 * r + q] = xrq;
+                    else if (p > pid) A3[6 * q + r] = xrq;
+                    else { A3[6 * r + q] += xrq; A3[6 * q + r] += xrq; }
+                }
+        }
+        // ---- W'(pos,f) += sum over the feature's blocks: warp-segmented reduction by feature ----
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int okey = __shfl_down_sync(0xffffffffu, gf, off);
+            bool take = (lane + off < 32) && (okey == gf);
+#pragma unroll
+            for (int i = 0; i < 18; i++) {
+                double ov = __shfl_down_sync(0xffffffffu, wadd[i], off);
+                if (take) wadd[i] += ov;
+            }
+        }
+        {
+            int pkey = __shfl_up_sync(0xffffffffu, gf, 1);
+            bool head = live && (lane == 0 || pkey != gf);
+            if (head) {
+                double *wp = O.W + 18 * (size_t)O.wPtr[f];
+#pragma unroll
+                for (int i = 0; i < 18; i++) atomicAdd(wp + i, wadd[i]);
+            }
+        }
+        // ---- U'(pos,pos) += G + G^T: warp sum when the whole warp is in one map ----
+        {
+            int k0 = __shfl_sync(0xffffffffu, live ? k : -1, 0);
+            bool uni = __all_sync(0xffffffffu, !live || k == k0) && k0 >= 0;
+            if (uni) {
+                int slot = -1;
+                if (lane == 0) slot = tw_hash_slot(hkeys, posePre[k0] + tc[k0].posID);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int q = r; q < 6; q++) {
+                        double s = sm::warp_sum(G[6 * r + q] + G[6 * q + r]);
+                        if (lane == 0) {
+                            if (slot >= 0) {
+                                atomicAdd(&hvals[slot][6 * r + q], s);
+                                if (q != r) atomicAdd(&hvals[slot][6 * q + r], s);
+                            } else {
+                                double *u = out[k0].U + 36 * (size_t)tc[k0].posID;
+                                atomicAdd(u + 6 * r + q, s);
+                                if (q != r) atomicAdd(u + 6 * q + r, s);
+                            }
+                        }
+                    }
+            } else if (live) {
+                double *u = O.U + 36 * (size_t)pid;
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int q = 0; q < 6; q++) atomicAdd(u + 6 * r + q, G[6 * r + q] + G[6 * q + r]);
+            }
+        }
+        // ---- U'(p,pos) += A3 through the CTA's pose hash ----
+        if (live) {
+            int slot = tw_hash_slot(hkeys, posePre[k] + p);
+            if (slot >= 0) {
+#pragma unroll
+                for (int i = 0; i < 36; i++) atomicAdd(&hvals[slot][i], A3[i]);
+            } else {
+                double *u = O.U + 36 * (size_t)p;
+#pragma unroll
+                for (int i = 0; i < 36; i++) atomicAdd(u + i, A3[i]);
+            }
+        }
+    }
+    __syncthreads();
+    // flush: one global atomic per accumulated value
+    for (int e = tid; e < TW_HASH * 36; e += TW_THREADS) {
+        int slot = e / 36, i = e - 36 * slot;
+        int key = hkeys[slot];
+        if (key < 0) continue;
+        int k = seg_find(posePre, K, key);
+        atomicAdd(out[k].U + 36 * (size_t)(key - posePre[k]) + i, hvals[slot][i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// v3 (default): the pose-major sums are taken out of the block-major kernel.
+//   U'(p,pos) and the W part of U'(pos,pos) only need, per pose p,
+//       SW_p = sum_f W_pf          SWT_p = sum_f W_pf T_f            (two 6x3 sums)
+//   because D_p / C_p / Q factor out of the sums:
+//       sum_f D_p^T W_pf C_f = [ -D_p^T SW_p Q | D_p^T SWT_p ],   same with C_p for U'(pos,pos).
+//   k_tf_wblock3  : block-major, coalesced: writes D_p^T W Q, segment-reduces C_p^T W Q into W'(pos,f),
+//                   emits (pose key, block index) pairs for the sort.
+//   cub radix sort of the pairs (keys = global pose index, <= 13 bits here)
+//   k_tf_posesum  : pose-major gather, one warp per chunk of a pose's blocks -> SW, SWT
+//   k_tf_posefin  : one thread per pose: applies the pose Jacobians once and adds the 6x6 blocks.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_tf_wblock3(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ wPre,
+             const int *__restrict__ featPre, const int *__restrict__ posePre, int K, int totW,
+             const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj,
+             int *__restrict__ sortKey, int *__restrict__ sortVal)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool live = g < totW;
+    int k = live ? seg_find(wPre, K, g) : 0;
+    int j = live ? g - wPre[k] : 0;
+    const DMap &M = in[k];
+    const DMap &O = out[k];
+    const TfConst &c = tc[k];
+    const int pid = c.posID;
+    int f = 0, gf = -1 - lane;
+    double wadd[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) wadd[i] = 0.0;
+    if (live) {
+        f = M.feature[j];
+        int p = M.photo[j];
+        gf = featPre[k] + f;
+        sortKey[g] = posePre[k] + p;
+        sortVal[g] = g;
+        bool isPos = (p == pid);
+        double Q[9], W[18], X[18];
+        sm::load<9>(c.Q, Q);
+        sm::load<18>(M.W + 18 * (size_t)j, W);
+        const PoseJac &J = pj[posePre[k] + p];
+        sm::mm<6, 3, 3>(W, Q, X);                                       // W Q
+        if (isPos) {
+            jt_mul<3>(Q, -1.0, J.b1, J.c1, true, X, wadd);              // D_pos^T W Q, folded into (posID,f)
+        } else {
+            double a1[18];
+            jt_mul<3>(Q, 1.0, J.b1, J.c1, false, X, a1);                // D_p^T W Q
+            int w0 = M.wPtr[f], skip = 0;
+            for (int i = w0; i < j; i++) skip += (M.photo[i] == pid);
+            int o = O.wPtr[f] + 1 + (j - w0) - skip;
+            sm::store<18>(O.W + 18 * (size_t)o, a1);
+            O.photo[o] = p;
+            O.feature[o] = f;
+            jt_mul<3>(Q, -1.0, J.f2, J.g2, true, X, wadd);              // C_p^T W Q
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int okey = __shfl_down_sync(0xffffffffu, gf, off);
+        bool take = (lane + off < 32) && (okey == gf);
+#pragma unroll
+        for (int i = 0; i < 18; i++) {
+            double ov = __shfl_down_sync(0xffffffffu, wadd[i], off);
+            if (take) wadd[i] += ov;
+        }
+    }
+    int pkey = __shfl_up_sync(0xffffffffu, gf, 1);
+    if (live && (lane == 0 || pkey != gf)) {
+        double *wp = O.W + 18 * (size_t)O.wPtr[f];
+#pragma unroll
+        for (int i = 0; i < 18; i++) atomicAdd(wp + i, wadd[i]);
+    }
+}
+
+__global__ void k_pose_start(const int *__restrict__ sortedKey, int totW, int totPose,
+                             int *__restrict__ poseStart)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > totPose) return;
+    int lo = 0, hi = totW;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (sortedKey[mid] < g) lo = mid + 1; else hi = mid; }
+    poseStart[g] = lo;
+}
+
+constexpr int PS_CHUNK = 256;          // blocks of one pose summed by one warp
+
+__global__ void k_pose_nchunks(const int *__restrict__ poseStart, int totPose, int *__restrict__ nch)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > totPose) return;
+    nch[g] = (g < totPose) ? (poseStart[g + 1] - poseStart[g] + PS_CHUNK - 1) / PS_CHUNK : 0;
+}
+
+// one warp per chunk (<= PS_CHUNK blocks of one pose): SW += W, SWT += W T_f
+__global__ void __launch_bounds__(128)
+k_tf_posesum(const DMap *__restrict__ in, const int *__restrict__ wPre, const int *__restrict__ featPre,
+             const int *__restrict__ posePre, int K, int totPose, const int *__restrict__ poseStart,
+             const int *__restrict__ chScan, const int *__restrict__ sortedVal,
+             const double *__restrict__ TfBuf, double *__restrict__ poseAcc)
+{
+    const int lane = threadIdx.x & 31;
+    int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= chScan[totPose]) return;
+    int gp = seg_find(chScan, totPose, wid);
+    int b0 = poseStart[gp] + (wid - chScan[gp]) * PS_CHUNK;
+    int b1 = min(b0 + PS_CHUNK, poseStart[gp + 1]);
+    int k = seg_find(posePre, K, gp);
+    const DMap &M = in[k];
+    double acc[36];
+#pragma unroll
+    for (int i = 0; i < 36; i++) acc[i] = 0.0;
+    for (int b = b0 + lane; b < b1; b += 32) {
+        int j = sortedVal[b] - wPre[k];
+        double W[18], Tf[9], WT[18];
+        sm::load<18>(M.W + 18 * (size_t)j, W);
+        sm::load<9>(TfBuf + 9 * (size_t)(featPre[k] + M.feature[j]), Tf);
+        sm::mm<6, 3, 3>(W, Tf, WT);
+#pragma unroll
+        for (int i = 0; i < 18; i++) { acc[i] += W[i]; acc[18 + i] += WT[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 36; i++) {
+        double s = sm::warp_sum(acc[i]);
+        if (lane == 0) atomicAdd(poseAcc + 36 * (size_t)gp + i, s);
+    }
+}
+
+// one thread per pose: U'(p,pos) += oriented [-D_p^T SW Q | D_p^T SWT];  U'(pos,pos) += G + G^T with
+// G = C_p^T [-SW Q | SWT]
+__global__ void __launch_bounds__(128)
+k_tf_posefin(DMap *__restrict__ out, const int *__restrict__ posePre, int K, int totPose,
+             const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj,
+             const double *__restrict__ poseAcc)
+{
+    int gp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= totPose) return;
+    int k = seg_find(posePre, K, gp);
+    int p = gp - posePre[k];
+    const TfConst &c = tc[k];
+    const int pid = c.posID;
+    const bool isPos = (p == pid);
+    double Q[9], SW[18], SWT[18], SWQ[18];
+    sm::load<9>(c.Q, Q);
+    sm::load<18>(poseAcc + 36 * (size_t)gp, SW);
+    sm::load<18>(poseAcc + 36 * (size_t)gp + 18, SWT);
+    sm::mm<6, 3, 3>(SW, Q, SWQ);
+    const PoseJac &J = pj[gp];
+    double a1[18], a3[18];
+    jt_mul<3>(Q, isPos ? -1.0 : 1.0, J.b1, J.c1, isPos, SWQ, a1);
+    jt_mul<3>(Q, isPos ? -1.0 : 1.0, J.b1, J.c1, isPos, SWT, a3);
+    double *u = out[k].U + 36 * (size_t)p;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            double xrq = (q < 3) ? -a1[3 * r + q] : a3[3 * r + q - 3];
+            if (p < pid) atomicAdd(u + 6 * r + q, xrq);
+            else if (p > pid) atomicAdd(u + 6 * q + r, xrq);
+            else { atomicAdd(u + 6 * r + q, xrq); atomicAdd(u + 6 * q + r, xrq); }
+        }
+    if (!isPos) {
+        double a2[18], a4[18];
+        jt_mul<3>(Q, -1.0, J.f2, J.g2, true, SWQ, a2);
+        jt_mul<3>(Q, -1.0, J.f2, J.g2, true, SWT, a4);
+        double *up = out[k].U + 36 * (size_t)pid;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                double grq = (q < 3) ? -a2[3 * r + q] : a4[3 * r + q - 3];
+                atomicAdd(up + 6 * r + q, grq);
+                atomicAdd(up + 6 * q + r, grq);
+            }
+    }
+}
+
 } // namespace
 
 void OpMaps::build(const std::vector<DMap> &maps, cudaStream_t s)
@@ -573,8 +1002,49 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
                                                      tc.p, pj.p, uScan.p); nl++;
     }
     if (A.totFeat > 0) {
-        k_wvcong<<<ceil_div(A.totFeat, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dFeatPre.p, A.dPosePre.p, K,
-                                                         A.totFeat, tc.p, pj.p, fScan.p); nl++;
+        static const bool tf_v1 = getenv("LSFM_TF_V1") != nullptr;
+        if (tf_v1) {
+            k_wvcong<<<ceil_div(A.totFeat, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dFeatPre.p, A.dPosePre.p, K,
+                                                             A.totFeat, tc.p, pj.p, fScan.p); nl++;
+        } else {
+            static const bool tf_v2 = getenv("LSFM_TF_V2") != nullptr;
+            DevBuf<double> TfBuf(9 * (size_t)A.totFeat, s);
+            k_tf_featprep<<<ceil_div(A.totFeat, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dFeatPre.p, K, A.totFeat,
+                                                                  tc.p, fScan.p, TfBuf.p); nl++;
+            if (A.totW > 0 && tf_v2) {
+                k_tf_wblock<<<ceil_div(A.totW, TW_THREADS * TW_TILES), TW_THREADS, 0, s>>>(
+                    A.d.p, B.d.p, A.dWPre.p, A.dFeatPre.p, A.dPosePre.p, K, A.totW, tc.p, pj.p, TfBuf.p); nl++;
+            } else if (A.totW > 0) {
+                const int totW = A.totW, totP = A.totPose;
+                DevBuf<int> sortKey(totW, s), sortVal(totW, s), sortedKey(totW, s), sortedVal(totW, s);
+                k_tf_wblock3<<<ceil_div(totW, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dWPre.p, A.dFeatPre.p,
+                                                               A.dPosePre.p, K, totW, tc.p, pj.p,
+                                                               sortKey.p, sortVal.p); nl++;
+                int bits = 1;
+                while ((1ll << bits) < (long long)totP + 1) bits++;
+                {
+                    size_t tb = 0;
+                    cub::DeviceRadixSort::SortPairs(nullptr, tb, sortKey.p, sortedKey.p, sortVal.p, sortedVal.p,
+                                                    totW, 0, bits, s);
+                    DevBuf<char> tmp(tb, s);
+                    cub::DeviceRadixSort::SortPairs(tmp.p, tb, sortKey.p, sortedKey.p, sortVal.p, sortedVal.p,
+                                                    totW, 0, bits, s); nl += 3;
+                }
+                DevBuf<int> poseStart(totP + 2, s), nch(totP + 2, s), chScan(totP + 2, s);
+                k_pose_start<<<ceil_div(totP + 1, TB), TB, 0, s>>>(sortedKey.p, totW, totP, poseStart.p); nl++;
+                k_pose_nchunks<<<ceil_div(totP + 1, TB), TB, 0, s>>>(poseStart.p, totP, nch.p); nl++;
+                exclusive_scan(ctx, nch.p, chScan.p, totP + 1); nl += 2;
+                DevBuf<double> poseAcc(36 * (size_t)totP, s);
+                poseAcc.zero();
+                long long maxChunks = (long long)totW / PS_CHUNK + totP + 1;
+                k_tf_posesum<<<ceil_div(maxChunks * 32, 128), 128, 0, s>>>(A.d.p, A.dWPre.p, A.dFeatPre.p,
+                                                                         A.dPosePre.p, K, totP, poseStart.p,
+                                                                         chScan.p, sortedVal.p, TfBuf.p,
+                                                                         poseAcc.p); nl++;
+                k_tf_posefin<<<ceil_div(totP, 128), 128, 0, s>>>(B.d.p, A.dPosePre.p, K, totP, tc.p, pj.p,
+                                                               poseAcc.p); nl++;
+            }
+        }
     }
     KERNEL_CHECK();
     ctx.end(bytes, 0.0, nl);
