@@ -154,6 +154,7 @@ int lsfm_join_stereo_batch(const lsfm_map *end, const lsfm_map *cur, int K, lsfm
         std::vector<MapHandle> E = upload_maps(*g_ctx, end, K, true);
         std::vector<MapHandle> C = upload_maps(*g_ctx, cur, K, true);
         std::vector<MapHandle> J = join_stereo_batch(*g_ctx, E, C);
+        g_ctx->check_errors();
         for (int k = 0; k < K; k++) download_map(*g_ctx, J[k], &out[k]);
     });
 }
@@ -189,6 +190,7 @@ int lsfm_solve_stereo(double *stVal, const double *eb, const double *ea, const d
         if (n) eF.upload(eb, 3 * (size_t)n);
         g_dbg = SolveDebug();
         solve_stereo_batch(*g_ctx, J, eP.p, eF.p, &g_dbg);
+        g_ctx->check_errors();
         g_dbg_valid = true;
         std::vector<int> tmpno(M.r);
         download_state(*g_ctx, h[0], tmpno.data(), stVal);
@@ -238,6 +240,7 @@ int lsfm_run_stereo(const lsfm_map *maps, int num, lsfm_map *out)
         std::vector<MapHandle> leaves = upload_maps(*g_ctx, maps, num, true);
         std::vector<MapHandle> top = solve_tree_stereo(*g_ctx, std::move(leaves), false, 0, -1);
         MapHandle root = final_rebase_stereo(*g_ctx, top[0]);
+        g_ctx->check_errors();
         download_map(*g_ctx, root, out);
     });
 }
@@ -340,6 +343,7 @@ int lsfm_tree_solve(lsfm_tree *tree, int verbose, int first_index, int max_level
         float ms = 0;
         CUDA_CHECK(cudaEventElapsedTime(&ms, tree->e0, tree->e1));
         tree->last_ms = ms;
+        g_ctx->check_errors();
     });
 }
 

@@ -109,6 +109,19 @@ const u64 M22 = (1ull << 22) - 1;
 void analyse_join(int m, const u64 *keys, int nk, JoinSym &J)
 {
     J.m = m;
+    if (m <= 32) {
+        // small joins (the thousands of joins of the lower tree levels): identity ordering, one
+        // dense supernode -- no graph needs to be built
+        J.perm.resize(m); J.iperm.resize(m);
+        for (int i = 0; i < m; i++) { J.perm[i] = i; J.iperm[i] = i; }
+        J.nodes = {0, m};
+        J.snOf.assign(m, 0);
+        J.structs.assign(1, {});
+        J.children.assign(1, {});
+        J.parent.assign(1, -1);
+        J.level.assign(1, 0);
+        return;
+    }
     // symmetric adjacency without self loops
     std::vector<int> ptr(m + 1, 0);
     for (int i = 0; i < nk; i++) {

@@ -162,6 +162,28 @@ struct Context {
     bool want_objective = false;
     int num_sms = 148;
 
+    // sticky device-side error flag (bit 0: non-positive pivot in the Cholesky); read by check_errors()
+    int *d_err = nullptr;
+    int *error_flag()
+    {
+        if (!d_err) {
+            d_err = (int *)DevicePool::get().alloc(sizeof(int));
+            CUDA_CHECK(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
+        }
+        return d_err;
+    }
+    void check_errors()
+    {
+        if (!d_err) return;
+        int h = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&h, d_err, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (h) {
+            CUDA_CHECK(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
+            throw LsfmError(LSFM_ERR_NOT_SPD, "reduced camera system is not positive definite");
+        }
+    }
+
     // event pool for stage timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string cur_stage;

@@ -9,8 +9,11 @@ struct OpMaps {
     int K = 0;
     std::vector<DMap> h;
     std::vector<int> posePre, featPre, uPre, wPre;     // K+1 prefix sums
-    DevBuf<DMap> d;
-    DevBuf<int> dPosePre, dFeatPre, dUPre, dWPre;
+    // descriptor array and the four prefix arrays live in ONE device blob filled by ONE H2D copy
+    template <class T> struct View { T *p = nullptr; };
+    DevBuf<char> blob;
+    View<DMap> d;
+    View<int> dPosePre, dFeatPre, dUPre, dWPre;
     int totPose = 0, totFeat = 0, totU = 0, totW = 0;
     void build(const std::vector<MapHandle> &maps, cudaStream_t s);
     void build(const std::vector<DMap> &maps, cudaStream_t s);

@@ -9,6 +9,8 @@
 // slice of the leaves reproduces exactly what the sequential scheduler would do with that slice.
 #include "scheduler.h"
 #include <cstdio>
+#include <cstdlib>
+#include <chrono>
 
 std::vector<MapHandle> transform_or_pass(Context &ctx, const std::vector<MapHandle> &in,
                                          const std::vector<int> &newRef)
@@ -52,25 +54,48 @@ std::vector<MapHandle> solve_tree_stereo(Context &ctx, std::vector<MapHandle> le
             printf("Join Level %d Local Map %lld\n", L, base + count);
             printf("Generate Level %d Local Map %lld\n\n", L + 1, base / 2 + npairs + 1);
         }
+        static const bool dbg = getenv("LSFM_DEBUG") != nullptr;
+        auto now = [&]() { if (dbg) cudaStreamSynchronize(ctx.stream); return std::chrono::steady_clock::now(); };
+        auto t0 = now();
         std::vector<MapHandle> Et = transform_or_pass(ctx, E, refs);
         E.clear();
+        auto t1 = now();
         std::vector<MapHandle> next = join_stereo_batch(ctx, Et, C);
         Et.clear(); C.clear();
+        auto t2 = now();
         if (leftover) next.push_back(level[count - 1]);
         level.clear();
         base /= 2;
         // re-base every output with even (index+1) whose Ref is ahead of its first frame (1997-2025)
         std::vector<MapHandle> rb;
         std::vector<int> rbRef, rbIdx;
+        std::vector<int> refAfter(next.size());
         for (size_t i = 0; i < next.size(); i++) {
             long long gi = base + (long long)i;
+            refAfter[i] = next[i].d.Ref;
             if ((gi + 1) % 2 == 0 && next[i].d.Ref > next[i].d.FRef) {
                 rb.push_back(next[i]); rbRef.push_back(next[i].d.FRef); rbIdx.push_back((int)i);
+                refAfter[i] = next[i].d.FRef;
             }
         }
+        // The even outputs are the End maps of the NEXT level; their Transform into the partner's
+        // frame (1964) is independent of the re-base of the odd outputs, so both go into one
+        // segmented launch set (the next level then finds End.Ref == Cur.Ref and passes through).
+        bool more = (max_levels < 0) ? (next.size() > 1) : (L + 1 < max_levels);
+        if (more)
+            for (size_t i = 0; i + 1 < next.size(); i += 2)
+                if (next[i].d.Ref != refAfter[i + 1]) {
+                    rb.push_back(next[i]); rbRef.push_back(refAfter[i + 1]); rbIdx.push_back((int)i);
+                }
         if (!rb.empty()) {
             std::vector<MapHandle> done = transform_stereo_batch(ctx, rb, rbRef);
             for (size_t j = 0; j < rbIdx.size(); j++) next[rbIdx[j]] = done[j];
+        }
+        if (dbg) {
+            auto t3 = now();
+            auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[level %2d] pairs %5d  transform %7.3f ms  join+solve %7.3f ms  rebase(%zu) %7.3f ms\n", L,
+                    npairs, ms(t0, t1), ms(t1, t2), rb.size(), ms(t2, t3));
         }
         level = std::move(next);
         L++;

@@ -204,9 +204,10 @@ __global__ void k_pat_u(const DMap *__restrict__ J, const int *__restrict__ uPre
 }
 
 // rowPtr[global pose] = first slot of that block row (keys are sorted by join,row,col)
-__global__ void k_rowptr(const u64 *__restrict__ keys, int n, const int *__restrict__ posePre, int K,
-                         int totP, int *__restrict__ rowPtr)
+__global__ void k_rowptr(const u64 *__restrict__ keys, const int *__restrict__ nPtr,
+                         const int *__restrict__ posePre, int K, int totP, int *__restrict__ rowPtr)
 {
+    const int n = *nPtr;
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g > totP) return;
     if (g == totP) { rowPtr[g] = n; return; }
@@ -769,17 +770,18 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         DevBuf<char> tmp(tb, s);
         cub::DeviceSelect::Unique(tmp.p, tb, sortedKeys.p, keys.p, dNuis.p, nRaw, s); nl += 2;
     }
+    // one synchronisation for everything the host needs: #blocks, keys (upper bound nRaw copied),
+    // row pointers
     int nuis = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&nuis, dNuis.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
     DevBuf<int> rowPtr(J.totPose + 1, s);
-    k_rowptr<<<ceil_div(J.totPose + 1, TB), TB, 0, s>>>(keys.p, nuis, J.dPosePre.p, K, J.totPose, rowPtr.p); nl++;
-    // pattern to the host for the symbolic phase (overlaps with the Schur kernels below)
-    std::vector<u64> hKeys(nuis);
+    k_rowptr<<<ceil_div(J.totPose + 1, TB), TB, 0, s>>>(keys.p, dNuis.p, J.dPosePre.p, K, J.totPose, rowPtr.p); nl++;
+    std::vector<u64> hKeys(nRaw);
     std::vector<int> hRowPtr(J.totPose + 1);
-    CUDA_CHECK(cudaMemcpyAsync(hKeys.data(), keys.p, sizeof(u64) * nuis, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(&nuis, dNuis.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (nRaw) CUDA_CHECK(cudaMemcpyAsync(hKeys.data(), keys.p, sizeof(u64) * nRaw, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(hRowPtr.data(), rowPtr.p, sizeof(int) * (J.totPose + 1), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
+    hKeys.resize(nuis);
     KERNEL_CHECK();
     ctx.end(8.0 * nRaw, 0.0, nl);
     nl = 0;
@@ -865,7 +867,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     DevBuf<double> fronts((size_t)sym.frontDoubles, s);
     fronts.zero();
     DevBuf<double> xperm(6 * (size_t)J.totPose, s);
-    DevBuf<int> err(1, s); err.zero();
+    struct { int *p; } err = {ctx.error_flag()};
     if (nuis > 0) { k_front_assemble<<<ceil_div(36ll * nuis, TB), TB, 0, s>>>(dSlot.p, nuis, dSn.p, S.p, fronts.p); nl++; }
     k_front_rhs<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(dPoseSn.p, dPoseLcol.p, J.totPose, dSn.p, E.p, fronts.p); nl++;
     int nLevels = (int)sym.levelPtr.size() - 1;
@@ -883,13 +885,10 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         k_front_backsolve<<<cnt, 128, shb, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dStruct.p, fronts.p, xperm.p); nl++;
     }
     k_unpermute<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(J.d.p, J.dPosePre.p, K, J.totPose, dPerm.p, xperm.p); nl++;
-    int herr = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
+    // the not-SPD flag is sticky in the context and checked once per API call (no sync here)
     KERNEL_CHECK();
     ctx.end(0.0, sym.flops, nl);
     nl = 0;
-    if (herr) throw LsfmError(LSFM_ERR_NOT_SPD, "reduced camera system is not positive definite");
 
     // ---- a13 ----
     ctx.begin("solve.backsub");

@@ -871,11 +871,23 @@ void OpMaps::build(const std::vector<DMap> &maps, cudaStream_t s)
         posePre[k + 1] = (int)tp; featPre[k + 1] = (int)tf; uPre[k + 1] = (int)tu; wPre[k + 1] = (int)tw;
     }
     totPose = (int)tp; totFeat = (int)tf; totU = (int)tu; totW = (int)tw;
-    d.alloc(K, s); d.upload(h);
-    dPosePre.alloc(K + 1, s); dPosePre.upload(posePre);
-    dFeatPre.alloc(K + 1, s); dFeatPre.upload(featPre);
-    dUPre.alloc(K + 1, s); dUPre.upload(uPre);
-    dWPre.alloc(K + 1, s); dWPre.upload(wPre);
+    // one blob: [DMap x K][posePre][featPre][uPre][wPre]  (each prefix K+1 ints, 16-byte aligned)
+    size_t oD = 0, szD = sizeof(DMap) * (size_t)K;
+    size_t szP = (sizeof(int) * (size_t)(K + 1) + 15) & ~(size_t)15;
+    size_t o1 = (szD + 15) & ~(size_t)15, o2 = o1 + szP, o3 = o2 + szP, o4 = o3 + szP, total = o4 + szP;
+    std::vector<char> host(total, 0);
+    if (K) memcpy(host.data() + oD, h.data(), szD);
+    memcpy(host.data() + o1, posePre.data(), sizeof(int) * (K + 1));
+    memcpy(host.data() + o2, featPre.data(), sizeof(int) * (K + 1));
+    memcpy(host.data() + o3, uPre.data(), sizeof(int) * (K + 1));
+    memcpy(host.data() + o4, wPre.data(), sizeof(int) * (K + 1));
+    blob.alloc(total, s);
+    blob.upload(host.data(), total);
+    d.p = (DMap *)(blob.p + oD);
+    dPosePre.p = (int *)(blob.p + o1);
+    dFeatPre.p = (int *)(blob.p + o2);
+    dUPre.p = (int *)(blob.p + o3);
+    dWPre.p = (int *)(blob.p + o4);
 }
 
 void OpMaps::build(const std::vector<MapHandle> &maps, cudaStream_t s)
