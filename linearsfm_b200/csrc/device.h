@@ -35,7 +35,9 @@ struct DevicePool {
             return p;
         }
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, need);
+        static const double limit_gb = getenv("LSFM_POOL_LIMIT_GB") ? atof(getenv("LSFM_POOL_LIMIT_GB")) : 0.0;
+        cudaError_t e = cudaErrorMemoryAllocation;
+        if (limit_gb <= 0.0 || (double)(reserved + need) <= limit_gb * 1e9) e = cudaMalloc(&p, need);
         if (e != cudaSuccess) {
             // out of memory: drop the cache and retry once
             cudaGetLastError();

@@ -93,6 +93,10 @@ std::vector<MapHandle> solve_tree_stereo(Context &ctx, std::vector<MapHandle> le
         }
         if (dbg) {
             auto t3 = now();
+            try { ctx.check_errors(); } catch (const LsfmError &e) {
+                fprintf(stderr, "[level %2d] %s\n", L, e.what());
+                throw;
+            }
             auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
             fprintf(stderr, "[level %2d] pairs %5d  transform %7.3f ms  join+solve %7.3f ms  rebase(%zu) %7.3f ms\n", L,
                     npairs, ms(t0, t1), ms(t1, t2), rb.size(), ms(t2, t3));
