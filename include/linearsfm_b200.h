@@ -70,6 +70,12 @@ int lsfm_transform_stereo(const lsfm_map *in, int Ref, lsfm_map *out);
 /* K independent transforms in one segmented launch set (what the scheduler uses per level).   */
 int lsfm_transform_stereo_batch(const lsfm_map *in, const int *Ref, int K, lsfm_map *out);
 
+/* void lmj_Transform_PF3DMono(LocalMapInfo& out, int Ref, int ScaP, int Fix) with m_GMap = *in
+ * (LinearSFMImp.h:216, LinearSFMImp.cpp:3173-6509).  Same Ref and ScaP returns a copy (3176).     */
+int lsfm_transform_mono(const lsfm_map *in, int Ref, int ScaP, int Fix, lsfm_map *out);
+int lsfm_transform_mono_batch(const lsfm_map *in, const int *Ref, const int *ScaP, const int *Fix, int K,
+                              lsfm_map *out);
+
 /* void lmj_LinearLS_PF3DStereo(LocalMapInfoStereo& End, LocalMapInfoStereo& Cur), result in
  * m_GMapS (LinearSFMImp.h:207, LinearSFMImp.cpp:2551-2978).  Inputs are NOT freed here.       */
 int lsfm_join_stereo(const lsfm_map *end, const lsfm_map *cur, lsfm_map *out);

@@ -88,6 +88,17 @@ def transform_stereo_batch(maps, refs):
     return [from_c(out[i]) for i in range(len(maps))]
 
 
+def transform_mono_batch(maps, refs, scaps, fixes):
+    arr, _keep = to_c_array(maps)
+    out = (LsfmMap * len(maps))()
+    n = len(maps)
+    r = (C.c_int * n)(*[int(x) for x in refs])
+    sc = (C.c_int * n)(*[int(x) for x in scaps])
+    fx = (C.c_int * n)(*[int(x) for x in fixes])
+    check(lib().lsfm_transform_mono_batch(arr, r, sc, fx, C.c_int(n), out))
+    return [from_c(out[i]) for i in range(n)]
+
+
 def join_stereo_batch(ends, curs):
     a, _k1 = to_c_array(ends)
     b, _k2 = to_c_array(curs)

@@ -159,6 +159,29 @@ int lsfm_join_stereo_batch(const lsfm_map *end, const lsfm_map *cur, int K, lsfm
     });
 }
 
+int lsfm_transform_mono_batch(const lsfm_map *in, const int *Ref, const int *ScaP, const int *Fix, int K,
+                              lsfm_map *out)
+{
+    return guarded([&] {
+        std::vector<MapHandle> h = upload_maps(*g_ctx, in, K, true);
+        std::vector<MapHandle> todo;
+        std::vector<int> r, sc, fx, where;
+        for (int k = 0; k < K; k++)
+            if (!(in[k].Ref == Ref[k] && in[k].ScaP == ScaP[k])) {          // LinearSFMImp.cpp:3176
+                todo.push_back(h[k]); r.push_back(Ref[k]); sc.push_back(ScaP[k]); fx.push_back(Fix[k]);
+                where.push_back(k);
+            }
+        std::vector<MapHandle> done = transform_mono_batch(*g_ctx, todo, r, sc, fx);
+        for (size_t j = 0; j < where.size(); j++) h[where[j]] = done[j];
+        for (int k = 0; k < K; k++) download_map(*g_ctx, h[k], &out[k]);
+    });
+}
+
+int lsfm_transform_mono(const lsfm_map *in, int Ref, int ScaP, int Fix, lsfm_map *out)
+{
+    return lsfm_transform_mono_batch(in, &Ref, &ScaP, &Fix, 1, out);
+}
+
 int lsfm_join_stereo(const lsfm_map *end, const lsfm_map *cur, lsfm_map *out)
 {
     return lsfm_join_stereo_batch(end, cur, 1, out);

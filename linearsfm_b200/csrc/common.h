@@ -58,6 +58,8 @@ struct DMap {
     int *photo, *feature;
     double *V;
     int *wPtr;
+    // monocular maps only (LocalMapInfo, LinearSFMImp.h:172-176)
+    int ScaP, Fix, Sign, FScaP, FFix;
 };
 
 static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }

@@ -60,6 +60,8 @@ std::vector<MapHandle> upload_maps(Context &ctx, const lsfm_map *maps, int K, bo
         memset(&d, 0, sizeof(d));
         d.Ref = maps[k].Ref; d.FRef = maps[k].FRef; d.m = maps[k].m; d.n = maps[k].n;
         d.nU = maps[k].nU; d.nW = maps[k].nW;
+        d.ScaP = maps[k].ScaP; d.Fix = maps[k].Fix; d.Sign = maps[k].Sign;
+        d.FScaP = maps[k].FScaP; d.FFix = maps[k].FFix;
     }
     std::vector<MapHandle> out = alloc_maps(ctx, shapes);
     if (K == 0) return out;
@@ -128,6 +130,7 @@ static void alloc_host_map(lsfm_map *o, const DMap &d)
     memset(o, 0, sizeof(*o));
     o->Ref = d.Ref; o->FRef = d.FRef; o->m = d.m; o->n = d.n; o->nU = d.nU; o->nW = d.nW;
     o->r = 6 * d.m + 3 * d.n;
+    o->ScaP = d.ScaP; o->Fix = d.Fix; o->Sign = d.Sign; o->FScaP = d.FScaP; o->FFix = d.FFix;
     auto A = [](size_t n, size_t sz) { return malloc((n * sz) ? (n * sz) : 1); };
     o->stno = (int *)A(o->r, sizeof(int));
     o->stVal = (double *)A(o->r, sizeof(double));

@@ -33,6 +33,14 @@ size_t map_layout(DMap &shape, char *base);
 std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<MapHandle> &in,
                                               const std::vector<int> &newRef);
 
+// a15: monocular frame transform (LinearSFMImp.cpp:3173-6509): Ref/ScaP/Fix of the target frame per map
+std::vector<MapHandle> transform_mono_batch(Context &ctx, const std::vector<MapHandle> &in,
+                                            const std::vector<int> &newRef, const std::vector<int> &newSca,
+                                            const std::vector<int> &newFix);
+// a16-a17: monocular join + solve (LinearSFMImp.cpp:7282-7874, 6756-7041)
+std::vector<MapHandle> join_mono_batch(Context &ctx, const std::vector<MapHandle> &End,
+                                       const std::vector<MapHandle> &Cur);
+
 // a6-a13: linear join of End[k] (already in Cur[k]'s frame) with Cur[k]
 // (LinearSFMImp.cpp:2551-2978 + 2119-2378). Returns the joint maps.
 std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHandle> &End,

@@ -230,3 +230,143 @@ def make_stereo_scene(num_maps: int, feats_per_frame: int = 128, seed: int = SEE
         "feat_X": np.einsum("ij,kj->ki", R0, Xw - p[0]),
     }
     return maps, truth
+
+
+# ---------------------------------------------------------------------------------------------
+# Monocular scene (SURVEY 8(d) "synthetic mono (RS-shape)", Appendix A.2 / C.3)
+# ---------------------------------------------------------------------------------------------
+def make_mono_scene(num_maps: int, feats_per_frame: int = 64, seed: int = SEED0 + 1,
+                    min_life: int = 3, max_life: int = 6, sigma: float = 0.3, f: float = 400.0,
+                    cx: float = 256.0, cy: float = 192.0, return_truth: bool = False):
+    """`num_maps` monocular local maps.  Map k (1-based) is built from the three frames k, k+1, k+2:
+    state = [pose k (= Ref, all zero), pose k+1 (= ScaP, translation component Fix pinned to Sign),
+    pose k+2, landmarks], in the frame of pose k and in units where |t_{k+1}[Fix]| = 1; consecutive
+    maps share two poses, as lmj_LinearLS_PF3DMono requires (LinearSFMImp.cpp:7383-7409).  The Ref
+    and ScaP slots are adjacent (slots 0 and 1), which the reference's Transform silently relies on
+    (SURVEY App. C.3).  Information = J' J / sigma^2 of the pixel observations (u, v) of every
+    landmark in the frames of the map where it is tracked, with the gauge parameters (pose k, and
+    component Fix of pose k+1) excluded, i.e. zero rows/columns."""
+    rng = np.random.default_rng(np.random.PCG64(seed))
+    N = int(num_maps)
+    nf = N + 2
+    p, ang, Rw = make_trajectory(nf, rng)
+    Fix = 0
+    L_total = nf * feats_per_frame
+    start = np.repeat(np.arange(nf), feats_per_frame)
+    life = rng.integers(min_life, max_life + 1, L_total)
+    end = np.minimum(start + life - 1, nf - 1)
+    depth = rng.uniform(4.0, 30.0, L_total)
+    th = rng.uniform(-np.deg2rad(25.0), np.deg2rad(25.0), L_total)
+    tv = rng.uniform(-np.deg2rad(18.0), np.deg2rad(18.0), L_total)
+    Xl = np.stack([depth, depth * np.tan(th), depth * np.tan(tv)], -1)
+    Xw = np.einsum("nji,nj->ni", Rw[start], Xl) + p[start]
+    gid = np.arange(1, L_total + 1, dtype=np.int64)
+
+    def proj(Xc):
+        return np.stack([cx - f * Xc[..., 1] / Xc[..., 0], cy - f * Xc[..., 2] / Xc[..., 0]], -1)
+
+    def jproj(Xc):
+        x, y, z = Xc[..., 0], Xc[..., 1], Xc[..., 2]
+        J = np.zeros(Xc.shape[:-1] + (2, 3))
+        J[..., 0, 0] = f * y / x ** 2; J[..., 0, 1] = -f / x
+        J[..., 1, 0] = f * z / x ** 2; J[..., 1, 2] = -f / x
+        return J
+
+    maps = []
+    truth_scale = np.zeros(N)
+    for k in range(N):
+        fr = [k, k + 1, k + 2]
+        # landmarks tracked in at least two of the three frames
+        vis = np.stack([(start <= j) & (end >= j) for j in fr], 0)        # [3, L]
+        sel = np.where(vis.sum(0) >= 2)[0]
+        n = sel.shape[0]
+        if n < 8:
+            raise ValueError("too few landmarks in a mono map; increase feats_per_frame")
+        R0, p0 = Rw[k], p[k]
+        rel_t = [R0 @ (p[j] - p0) for j in fr]
+        rel_R = [Rw[j] @ R0.T for j in fr]
+        s = 1.0 / abs(rel_t[1][Fix])
+        Sign = 1 if rel_t[1][Fix] >= 0 else -1
+        truth_scale[k] = s
+        X = (Xw[sel] - p0) @ R0.T * s                                     # [n,3] in frame k, scaled
+        poses = np.zeros((3, 6))
+        for c in (1, 2):
+            poses[c, :3] = rel_t[c] * s
+            poses[c, 3:] = np.array(ypr_from_rot(rel_R[c]))
+        # unknown vector: [pose1(6), pose2(6), X(3n)], gauge: pose1[Fix] fixed
+        nun = 12 + 3 * n
+        Jrows, rrows = [], []
+        H = np.zeros((nun, nun))
+        g = np.zeros(nun)
+        for c in range(3):
+            v = vis[c, sel]
+            idx = np.where(v)[0]
+            if idx.size == 0:
+                continue
+            if c == 0:
+                Xc = X[idx]
+                Jp = jproj(Xc)                                            # d z / d X
+                eps = rng.normal(0, sigma, (idx.size, 2))
+                for q, i in enumerate(idx):
+                    sl = slice(12 + 3 * i, 15 + 3 * i)
+                    H[sl, sl] += Jp[q].T @ Jp[q] / sigma ** 2
+                    g[sl] += Jp[q].T @ eps[q] / sigma ** 2
+            else:
+                t, a = poses[c, :3], poses[c, 3:]
+                R = rot_ypr(*a)
+                dA, dB, dG = drot_ypr(*a)
+                d = X[idx] - t
+                Xc = d @ R.T
+                Jp = jproj(Xc)
+                JX = Jp @ R                                               # [q,2,3]
+                Jang = np.stack([d @ dA.T, d @ dB.T, d @ dG.T], -1)       # [q,3,3]
+                JP = np.concatenate([-JX, Jp @ Jang], -1)                 # [q,2,6]
+                eps = rng.normal(0, sigma, (idx.size, 2))
+                po = 6 * (c - 1)
+                for q, i in enumerate(idx):
+                    sl = slice(12 + 3 * i, 15 + 3 * i)
+                    ps = slice(po, po + 6)
+                    H[ps, ps] += JP[q].T @ JP[q] / sigma ** 2
+                    H[ps, sl] += JP[q].T @ JX[q] / sigma ** 2
+                    H[sl, ps] += JX[q].T @ JP[q] / sigma ** 2
+                    H[sl, sl] += JX[q].T @ JX[q] / sigma ** 2
+                    g[ps] += JP[q].T @ eps[q] / sigma ** 2
+                    g[sl] += JX[q].T @ eps[q] / sigma ** 2
+        # gauge: component Fix of pose 1 is not a variable
+        H[Fix, :] = 0.0; H[:, Fix] = 0.0; g[Fix] = 0.0
+        Hs = H.copy(); Hs[Fix, Fix] = 1.0
+        delta = np.linalg.solve(Hs, g)
+        poses[1] += delta[:6]; poses[2] += delta[6:12]
+        Xe = X + delta[12:].reshape(n, 3)
+        # information blocks (evaluated at the truth; adequate for a synthetic input)
+        U = np.stack([H[0:6, 0:6], H[0:6, 6:12], H[6:12, 6:12]])
+        Ui = np.array([1, 1, 2], np.int32); Uj = np.array([1, 2, 2], np.int32)
+        Wb, ph, fe, FB = [], [], [], []
+        for i in range(n):
+            sl = slice(12 + 3 * i, 15 + 3 * i)
+            first = -1
+            for c in (1, 2):
+                blk = H[6 * (c - 1):6 * c, sl]
+                if vis[c, sel[i]]:
+                    if first < 0:
+                        first = len(Wb)
+                    Wb.append(blk); ph.append(c); fe.append(i)
+            FB.append(first)
+        V = np.stack([H[12 + 3 * i:15 + 3 * i, 12 + 3 * i:15 + 3 * i] for i in range(n)])
+        stno = np.concatenate([np.repeat([-(k + 1), -(k + 2), -(k + 3)], 6),
+                               np.repeat(gid[sel].astype(np.int32), 3)]).astype(np.int32)
+        stVal = np.concatenate([poses.reshape(-1), Xe.reshape(-1)])
+        stVal[6 + Fix] = Sign
+        lm = LocalMap(Ref=k + 1, stno=stno, stVal=stVal, m=3, n=int(n), U=U, Ui=Ui, Uj=Uj,
+                      W=np.array(Wb), photo=np.array(ph, np.int32), feature=np.array(fe, np.int32),
+                      V=V, FBlock=np.array(FB, np.int32), ScaP=k + 2, Fix=Fix, Sign=Sign,
+                      FScaP=k + 2, FFix=Fix)
+        maps.append(lm)
+    if not return_truth:
+        return maps
+    R0 = Rw[0]
+    s0 = truth_scale[0]
+    truth = {"pose_ids": np.arange(1, nf + 1), "pose_t": (p - p[0]) @ R0.T * s0,
+             "pose_R": np.einsum("kij,lj->kil", Rw, R0), "feat_ids": gid,
+             "feat_X": (Xw - p[0]) @ R0.T * s0}
+    return maps, truth
