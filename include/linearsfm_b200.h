@@ -81,6 +81,13 @@ int lsfm_transform_mono_batch(const lsfm_map *in, const int *Ref, const int *Sca
 int lsfm_join_stereo(const lsfm_map *end, const lsfm_map *cur, lsfm_map *out);
 int lsfm_join_stereo_batch(const lsfm_map *end, const lsfm_map *cur, int K, lsfm_map *out);
 
+/* void lmj_LinearLS_PF3DMono(LocalMapInfo& End, LocalMapInfo& Cur), result in m_GMap
+ * (LinearSFMImp.h:219, LinearSFMImp.cpp:7282-7874) incl. lmj_solveLinearSFMMono (6756-7041).      */
+int lsfm_join_mono(const lsfm_map *end, const lsfm_map *cur, lsfm_map *out);
+int lsfm_join_mono_batch(const lsfm_map *end, const lsfm_map *cur, int K, lsfm_map *out);
+/* void lmj_PF3D_Divide_ConquerMono(int nLocalMapCount) over m_LMset (LinearSFMImp.cpp:6511-6658)    */
+int lsfm_run_mono(const lsfm_map *maps, int num, lsfm_map *out);
+
 /* void lmj_solveLinearSFMStereo(double* stVal, double* eb, double* ea, double* U, double* W,
  *      double* V, int* Ui, int* Uj, int* photo, int* feature, int m, int n, int nU, int nW)
  * (LinearSFMImp.h:209, LinearSFMImp.cpp:2119-2378): same argument order and meaning; stVal[6m+3n]

@@ -107,6 +107,22 @@ def join_stereo_batch(ends, curs):
     return [from_c(out[i]) for i in range(len(ends))]
 
 
+def join_mono_batch(ends, curs):
+    a, _k1 = to_c_array(ends)
+    b, _k2 = to_c_array(curs)
+    out = (LsfmMap * len(ends))()
+    check(lib().lsfm_join_mono_batch(a, b, C.c_int(len(ends)), out))
+    return [from_c(out[i]) for i in range(len(ends))]
+
+
+def run_mono(maps) -> LocalMap:
+    """lmj_PF3D_Divide_ConquerMono (LinearSFMImp.cpp:6511): whole mono merge tree, host maps in/out."""
+    arr, _keep = to_c_array(maps)
+    out = LsfmMap()
+    check(lib().lsfm_run_mono(arr, C.c_int(len(maps)), C.byref(out)))
+    return from_c(out)
+
+
 def block_ordering(Ap, Ai) -> np.ndarray:
     Ap = _c(Ap, np.int32); Ai = _c(Ai, np.int32)
     m = Ap.shape[0] - 1

@@ -182,6 +182,33 @@ int lsfm_transform_mono(const lsfm_map *in, int Ref, int ScaP, int Fix, lsfm_map
     return lsfm_transform_mono_batch(in, &Ref, &ScaP, &Fix, 1, out);
 }
 
+int lsfm_join_mono_batch(const lsfm_map *end, const lsfm_map *cur, int K, lsfm_map *out)
+{
+    return guarded([&] {
+        std::vector<MapHandle> E = upload_maps(*g_ctx, end, K, true);
+        std::vector<MapHandle> C = upload_maps(*g_ctx, cur, K, true);
+        std::vector<MapHandle> J = join_mono_batch(*g_ctx, E, C);
+        g_ctx->check_errors();
+        for (int k = 0; k < K; k++) download_map(*g_ctx, J[k], &out[k]);
+    });
+}
+
+int lsfm_join_mono(const lsfm_map *end, const lsfm_map *cur, lsfm_map *out)
+{
+    return lsfm_join_mono_batch(end, cur, 1, out);
+}
+
+int lsfm_run_mono(const lsfm_map *maps, int num, lsfm_map *out)
+{
+    return guarded([&] {
+        if (num < 1) throw LsfmError(LSFM_ERR_ARG, "need at least one local map");
+        std::vector<MapHandle> leaves = upload_maps(*g_ctx, maps, num, true);
+        std::vector<MapHandle> top = solve_tree_mono(*g_ctx, std::move(leaves), false);
+        g_ctx->check_errors();
+        download_map(*g_ctx, top[0], out);
+    });
+}
+
 int lsfm_join_stereo(const lsfm_map *end, const lsfm_map *cur, lsfm_map *out)
 {
     return lsfm_join_stereo_batch(end, cur, 1, out);

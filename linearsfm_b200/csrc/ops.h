@@ -50,8 +50,11 @@ std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHand
 // (LinearSFMImp.cpp:2119-2378). eP: concatenated 6m per map, eF: concatenated 3n per map.
 // Writes poseVal/featVal of the maps in place.
 struct SolveDebug;   // optional capture of pattern / ordering for the parity tests
+// mono gauge (device arrays, one entry per join): local index of the all-zero Ref pose, local scalar
+// row of the pinned ScaP translation component, and its value Sign (LinearSFMImp.cpp:7797-7801)
+struct MonoGauge { const int *refPose; const int *fixScalar; const int *sign; };
 void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const double *eF,
-                        SolveDebug *dbg);
+                        SolveDebug *dbg, const MonoGauge *gauge = nullptr);
 
 struct SolveDebug {
     // for the first map of the batch only

@@ -117,3 +117,75 @@ MapHandle final_rebase_stereo(Context &ctx, const MapHandle &root)
     }
     return root;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Monocular merge tree: lmj_PF3D_Divide_ConquerMono, LinearSFMImp.cpp:6511-6658.  Same pairing and
+// re-base rule as stereo; the Transform takes (Ref, ScaP, Fix) of the partner / of the first frame,
+// and is skipped when both Ref and ScaP already match (3176).
+// ---------------------------------------------------------------------------------------------
+static std::vector<MapHandle> transform_mono_or_pass(Context &ctx, const std::vector<MapHandle> &in,
+                                                     const std::vector<int> &r, const std::vector<int> &sc,
+                                                     const std::vector<int> &fx)
+{
+    std::vector<MapHandle> todo;
+    std::vector<int> r2, s2, f2, where;
+    for (size_t i = 0; i < in.size(); i++)
+        if (!(in[i].d.Ref == r[i] && in[i].d.ScaP == sc[i])) {
+            todo.push_back(in[i]); r2.push_back(r[i]); s2.push_back(sc[i]); f2.push_back(fx[i]);
+            where.push_back((int)i);
+        }
+    std::vector<MapHandle> done = transform_mono_batch(ctx, todo, r2, s2, f2);
+    std::vector<MapHandle> out = in;
+    for (size_t j = 0; j < where.size(); j++) out[where[j]] = done[j];
+    return out;
+}
+
+std::vector<MapHandle> solve_tree_mono(Context &ctx, std::vector<MapHandle> level, bool verbose)
+{
+    int L = 0;
+    while (level.size() > 1) {
+        int count = (int)level.size();
+        int npairs = count / 2;
+        bool leftover = (count % 2) != 0;
+        std::vector<MapHandle> E(npairs), C(npairs);
+        std::vector<int> r(npairs), sc(npairs), fx(npairs);
+        for (int i = 0; i < npairs; i++) {
+            E[i] = level[2 * i];
+            C[i] = level[2 * i + 1];
+            r[i] = C[i].d.Ref; sc[i] = C[i].d.ScaP; fx[i] = C[i].d.Fix;          // 6549
+            if (verbose) {
+                printf("Join Level %d Local Map %d\n", L, 2 * i + 1);
+                printf("Join Level %d Local Map %d\n", L, 2 * i + 2);
+                printf("Generate Level %d Local Map %d\n\n", L + 1, i + 1);
+            }
+        }
+        if (verbose && leftover) {
+            printf("Join Level %d Local Map %d\n", L, count);
+            printf("Generate Level %d Local Map %d\n\n", L + 1, npairs + 1);
+        }
+        std::vector<MapHandle> Et = transform_mono_or_pass(ctx, E, r, sc, fx);
+        E.clear();
+        std::vector<MapHandle> next = join_mono_batch(ctx, Et, C);
+        Et.clear(); C.clear();
+        if (leftover) next.push_back(level[count - 1]);
+        level.clear();
+        std::vector<MapHandle> rb;
+        std::vector<int> rr, rs, rf, idx;
+        for (size_t i = 0; i < next.size(); i++)
+            if ((i + 1) % 2 == 0 && next[i].d.Ref > next[i].d.FRef) {           // 6576-6597
+                rb.push_back(next[i]); rr.push_back(next[i].d.FRef); rs.push_back(next[i].d.FScaP);
+                rf.push_back(next[i].d.FFix); idx.push_back((int)i);
+            }
+        if (!rb.empty()) {
+            std::vector<MapHandle> done = transform_mono_or_pass(ctx, rb, rr, rs, rf);
+            for (size_t j = 0; j < idx.size(); j++) next[idx[j]] = done[j];
+        }
+        level = std::move(next);
+        L++;
+    }
+    if (!level.empty() && level[0].d.Ref > level[0].d.FRef) {                    // 6613-6630
+        std::vector<MapHandle> in{level[0]};
+        level[0] = transform_mono_or_pass(ctx, in, {level[0].d.FRef}, {level[0].d.FScaP}, {level[0].d.FFix})[0];
+    }
+    return level;
+}

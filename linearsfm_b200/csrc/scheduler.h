@@ -8,3 +8,6 @@ std::vector<MapHandle> transform_or_pass(Context &ctx, const std::vector<MapHand
 std::vector<MapHandle> solve_tree_stereo(Context &ctx, std::vector<MapHandle> level, bool verbose,
                                          int first_index, int max_levels);
 MapHandle final_rebase_stereo(Context &ctx, const MapHandle &root);
+
+// mono merge tree incl. the final re-base (LinearSFMImp.cpp:6511-6658)
+std::vector<MapHandle> solve_tree_mono(Context &ctx, std::vector<MapHandle> level, bool verbose);

@@ -513,6 +513,58 @@ k_schur_tiled(const DMap *__restrict__ J, const SchurChunk *__restrict__ chunks,
 }
 
 // ---------------------------------------------------------------------------------------------
+// a17 (mono): gauge rows.  The reference deletes the six rows/columns of the zero pose and the
+// scalar row `Fix` from the CSC (pba_constructCSSGN, LinearSFMImp.cpp:7136-7170) and re-inserts
+// zeros afterwards (7010-7026).  Here the rows/columns stay in the block system but are replaced by
+// identity rows with a zero right-hand side -- same solution, block structure intact.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pat_diag(const int *__restrict__ posePre, int K, int totP, u64 *__restrict__ keys)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totP) return;
+    int k = seg_find(posePre, K, g);
+    int p = g - posePre[k];
+    keys[g] = pair_key(k, p, p);
+}
+
+__global__ void k_mono_gauge(const u64 *__restrict__ keys, int nuis, const int *__restrict__ refPose,
+                             const int *__restrict__ fixScalar, double *__restrict__ S)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nuis) return;
+    u64 key = keys[g];
+    int k = (int)(key >> 44), lo = (int)((key >> 22) & ((1u << 22) - 1)), hi = (int)(key & ((1u << 22) - 1));
+    int ref = refPose[k], fp = fixScalar[k] / 6, fr = fixScalar[k] % 6;
+    double *s = S + 36 * (size_t)g;
+    if (lo == ref || hi == ref) {
+        for (int q = 0; q < 36; q++) s[q] = 0.0;
+        if (lo == hi) for (int q = 0; q < 6; q++) s[7 * q] = 1.0;
+        return;
+    }
+    if (lo == fp) for (int q = 0; q < 6; q++) s[6 * fr + q] = 0.0;
+    if (hi == fp) for (int q = 0; q < 6; q++) s[6 * q + fr] = 0.0;
+    if (lo == fp && hi == fp) s[7 * fr] = 1.0;
+}
+
+__global__ void k_mono_gauge_rhs(const int *__restrict__ posePre, int K, const int *__restrict__ refPose,
+                                 const int *__restrict__ fixScalar, double *__restrict__ E)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double *e = E + 6 * (size_t)posePre[k];
+    for (int q = 0; q < 6; q++) e[6 * refPose[k] + q] = 0.0;
+    e[fixScalar[k]] = 0.0;
+}
+
+__global__ void k_mono_fix(DMap *__restrict__ J, int K, const int *__restrict__ fixScalar,
+                           const int *__restrict__ sign)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    J[k].poseVal[fixScalar[k]] = (double)sign[k];          // stVal[Fix] = Sign (7026)
+}
+
+// ---------------------------------------------------------------------------------------------
 // a11-a12: numeric block multifrontal Cholesky with the right-hand side carried as an extra row
 // ---------------------------------------------------------------------------------------------
 __global__ void k_front_assemble(const SlotMap *__restrict__ slot, int nslot,
@@ -701,7 +753,7 @@ void exclusive_scan(Context &ctx, const int *in, int *out, int n)
 } // namespace
 
 void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const double *eF,
-                        SolveDebug *dbg)
+                        SolveDebug *dbg, const MonoGauge *gauge)
 {
     const int K = J.K;
     cudaStream_t s = ctx.stream;
@@ -750,8 +802,12 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             CUDA_CHECK(cudaMemcpyAsync(&maxNposes, dMaxNp.p, sizeof(int), cudaMemcpyDeviceToHost, s));
             CUDA_CHECK(cudaStreamSynchronize(s));
         }
-        nRaw = nChunkKeys + J.totU;
+        nRaw = nChunkKeys + J.totU + (gauge ? J.totPose : 0);
         rawKeys.alloc(nRaw, s); sortedKeys.alloc(nRaw, s); keys.alloc(nRaw, s);
+        if (gauge) {   // mono: the zero pose has no block at all after the join; keep every diagonal
+            k_pat_diag<<<ceil_div(J.totPose, TB), TB, 0, s>>>(J.dPosePre.p, K, J.totPose,
+                                                            rawKeys.p + J.totU + nChunkKeys); nl++;
+        }
         if (J.totU > 0) { k_pat_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, K, J.totU, rawKeys.p); nl++; }
         if (nChunks > 0) {
             k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 1, nullptr, pscan.p, rawKeys.p + J.totU, nullptr); nl++;
@@ -839,6 +895,10 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     // S and E written once
     ctx.end(152.0 * J.totW + 96.0 * J.totFeat + 288.0 * nuis + 48.0 * J.totPose, 0.0, nl);
     nl = 0;
+    if (gauge && nuis > 0) {
+        k_mono_gauge<<<ceil_div(nuis, TB), TB, 0, s>>>(keys.p, nuis, gauge->refPose, gauge->fixScalar, S.p);
+        k_mono_gauge_rhs<<<ceil_div(K, TB), TB, 0, s>>>(J.dPosePre.p, K, gauge->refPose, gauge->fixScalar, E.p);
+    }
     ctx.begin("solve.symbolic");
 
     // ---- symbolic on the host while the GPU accumulates S ----
@@ -893,6 +953,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     // ---- a13 ----
     ctx.begin("solve.backsub");
     if (J.totFeat > 0) { k_backsub<<<ceil_div(J.totFeat, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, K, J.totFeat, Vinv.p, eF); nl++; }
+    if (gauge) { k_mono_fix<<<ceil_div(K, TB), TB, 0, s>>>(J.d.p, K, gauge->fixScalar, gauge->sign); nl++; }
     KERNEL_CHECK();
     ctx.end(144.0 * J.totW + 96.0 * J.totFeat + 8.0 * (6.0 * J.totPose + 3.0 * J.totFeat), 0.0, nl);
 

@@ -42,3 +42,35 @@ def test_mono_transform_joint(gpu, oracle, mono8):
     ref2 = oracle.transform_mono(j0, ref.Ref, ref.ScaP, ref.Fix)
     got2 = gpu.transform_mono_batch([j0], [ref.Ref], [ref.ScaP], [ref.Fix])[0]
     assert_maps_match(got2, ref2, what="mono transform of a joint map")
+
+
+def test_mono_join_leaf_pair(gpu, oracle, mono8):
+    e = oracle.transform_mono(mono8[0], mono8[1].Ref, mono8[1].ScaP, mono8[1].Fix)
+    ref = oracle.join_mono(e, mono8[1])
+    got = gpu.join_mono_batch([e], [mono8[1]])[0]
+    assert_maps_match(got, ref, what="mono leaf join")
+    check_meta(got, ref)
+
+
+def test_mono_join_level1(gpu, oracle, mono8):
+    j = []
+    for a in (0, 2):
+        e = oracle.transform_mono(mono8[a], mono8[a + 1].Ref, mono8[a + 1].ScaP, mono8[a + 1].Fix)
+        j.append(oracle.join_mono(e, mono8[a + 1]))
+    cur = oracle.transform_mono(j[1], j[1].FRef, j[1].FScaP, j[1].FFix)
+    end = oracle.transform_mono(j[0], cur.Ref, cur.ScaP, cur.Fix)
+    ref = oracle.join_mono(end, cur)
+    got = gpu.join_mono_batch([end], [cur])[0]
+    assert_maps_match(got, ref, tol_state=1e-8, tol_info=1e-9, what="mono level-1 join")
+    check_meta(got, ref)
+
+
+@pytest.mark.parametrize("n,fpf", [(2, 16), (3, 16), (5, 16), (8, 20), (13, 24), (40, 30)])
+def test_mono_tree(gpu, oracle, n, fpf):
+    maps = synth.make_mono_scene(n, feats_per_frame=fpf, seed=900 + n)
+    ref, _, _ = oracle.run_tree_mono(maps)
+    got = gpu.run_mono(maps)
+    assert_maps_match(got, ref, tol_state=1e-7, tol_info=1e-7, what=f"mono tree N={n}")
+    check_meta(got, ref)
+    from util import state_rel_err
+    assert state_rel_err(got, ref) <= 1e-6
