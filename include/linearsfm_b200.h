@@ -87,6 +87,7 @@ int lsfm_join_mono(const lsfm_map *end, const lsfm_map *cur, lsfm_map *out);
 int lsfm_join_mono_batch(const lsfm_map *end, const lsfm_map *cur, int K, lsfm_map *out);
 /* void lmj_PF3D_Divide_ConquerMono(int nLocalMapCount) over m_LMset (LinearSFMImp.cpp:6511-6658)    */
 int lsfm_run_mono(const lsfm_map *maps, int num, lsfm_map *out);
+int lsfm_run_mono_ex(const lsfm_map *maps, int num, int verbose, lsfm_map *out);   /* verbose: reference stdout lines */
 
 /* void lmj_solveLinearSFMStereo(double* stVal, double* eb, double* ea, double* U, double* W,
  *      double* V, int* Ui, int* Uj, int* photo, int* feature, int m, int n, int nU, int nW)
@@ -138,6 +139,8 @@ void lsfm_tree_free(lsfm_tree *tree);
 /* ---- files + CLI (drop-in process boundary) ------------------------------------------------- */
 /* lmj_readInformationStereo (LinearSFMImp.cpp:3044-3132)                                        */
 int lsfm_load_localmap_stereo(const char *path, lsfm_map *out);
+/* lmj_readInformationMono (LinearSFMImp.cpp:6660-6754): header `Ref ScaP Fix Sign r`           */
+int lsfm_load_localmap_mono(const char *path, lsfm_map *out);
 /* lmj_SaveStateVector (2102-2117) and lmj_SavePoses_3DPF (7876-7967); NULL = skip              */
 int lsfm_save_outputs(const lsfm_map *m, const char *state_path, const char *pose_path,
                       const char *feature_path);

@@ -34,7 +34,7 @@ EXPORTS = [
     "lsfm_init", "lsfm_shutdown", "lsfm_last_error", "lsfm_device_count", "lsfm_free_map",
     "lsfm_stats_reset", "lsfm_stats_json",
     "lsfm_transform_stereo", "lsfm_transform_stereo_batch", "lsfm_transform_mono", "lsfm_transform_mono_batch", "lsfm_join_stereo",
-    "lsfm_join_mono", "lsfm_join_mono_batch", "lsfm_run_mono",
+    "lsfm_join_mono", "lsfm_join_mono_batch", "lsfm_run_mono", "lsfm_run_mono_ex", "lsfm_load_localmap_mono",
     "lsfm_join_stereo_batch", "lsfm_solve_stereo", "lsfm_debug_last_solve", "lsfm_block_ordering",
     "lsfm_run_stereo", "lsfm_tree_create_stereo", "lsfm_tree_solve", "lsfm_tree_result_count",
     "lsfm_tree_result_shape", "lsfm_tree_download", "lsfm_tree_download_state", "lsfm_tree_set_maps",

@@ -198,12 +198,14 @@ int lsfm_join_mono(const lsfm_map *end, const lsfm_map *cur, lsfm_map *out)
     return lsfm_join_mono_batch(end, cur, 1, out);
 }
 
-int lsfm_run_mono(const lsfm_map *maps, int num, lsfm_map *out)
+int lsfm_run_mono(const lsfm_map *maps, int num, lsfm_map *out) { return lsfm_run_mono_ex(maps, num, 0, out); }
+
+int lsfm_run_mono_ex(const lsfm_map *maps, int num, int verbose, lsfm_map *out)
 {
     return guarded([&] {
         if (num < 1) throw LsfmError(LSFM_ERR_ARG, "need at least one local map");
         std::vector<MapHandle> leaves = upload_maps(*g_ctx, maps, num, true);
-        std::vector<MapHandle> top = solve_tree_mono(*g_ctx, std::move(leaves), false);
+        std::vector<MapHandle> top = solve_tree_mono(*g_ctx, std::move(leaves), verbose != 0);
         g_ctx->check_errors();
         download_map(*g_ctx, top[0], out);
     });

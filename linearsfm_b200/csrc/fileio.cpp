@@ -42,7 +42,7 @@ struct Tok {
     }
 };
 
-int load_stereo_impl(const char *path, lsfm_map *M, std::string &err)
+int load_map_impl(const char *path, lsfm_map *M, std::string &err, bool mono)
 {
     FILE *f = fopen(path, "rb");
     if (!f) { err = std::string("cannot open ") + path; return LSFM_ERR_IO; }
@@ -56,7 +56,12 @@ int load_stereo_impl(const char *path, lsfm_map *M, std::string &err)
     Tok t{buf.data(), buf.data() + got};
     memset(M, 0, sizeof(*M));
     M->Ref = (int)t.next_int();
-    M->FRef = M->Ref;                                   // LinearSFMImp.cpp:3053
+    M->FRef = M->Ref;                                   // LinearSFMImp.cpp:3053 / 6668
+    if (mono) {                                         // header Ref ScaP Fix Sign (6669-6676)
+        M->ScaP = (int)t.next_int(); M->FScaP = M->ScaP;
+        M->Fix = (int)t.next_int(); M->FFix = M->Fix;
+        M->Sign = (int)t.next_int();
+    }
     M->r = (int)t.next_int();
     if (t.fail || M->r < 0) { err = std::string(path) + ": bad header"; return LSFM_ERR_FORMAT; }
     auto A = [](size_t n, size_t s) { return malloc((n * s) ? (n * s) : 1); };
@@ -112,7 +117,12 @@ extern "C" {
 
 int lsfm_load_localmap_stereo(const char *path, lsfm_map *out)
 {
-    return load_stereo_impl(path, out, g_io_err);
+    return load_map_impl(path, out, g_io_err, false);
+}
+
+int lsfm_load_localmap_mono(const char *path, lsfm_map *out)
+{
+    return load_map_impl(path, out, g_io_err, true);
 }
 
 int lsfm_save_outputs(const lsfm_map *M, const char *st, const char *pose, const char *feat)
@@ -176,10 +186,7 @@ int lsfm_cli_main(int argc, char **argv)
     if (!hasPath) { printf("LinerSFM Error: Please Input Right File Path:\n"); return 0; }
     if (!hasNum) { printf("LinerSFM Error: Please Set Local Map Number:\n"); return 0; }
     if (!hasType) { printf("LinerSFM Error: Please Set Data Type:\n"); return 0; }
-    if (type == "Monocular") {
-        fprintf(stderr, "LinearSFM (B200): -type Monocular is not built in this round (stereo hot path only)\n");
-        return 0;
-    }
+    const bool mono = (type == "Monocular");
     if (num < 1) return 0;
     if (lsfm_init(0) != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0; }
 
@@ -191,7 +198,7 @@ int lsfm_cli_main(int argc, char **argv)
     auto work = [&](int tid) {
         for (int i = tid; i < num; i += nth) {
             std::string p = path + "/localmap_" + std::to_string(i + 1) + ".txt";
-            rc[i] = load_stereo_impl(p.c_str(), &maps[i], errs[i]);
+            rc[i] = load_map_impl(p.c_str(), &maps[i], errs[i], mono);
         }
     };
     std::vector<std::thread> th;
@@ -200,6 +207,21 @@ int lsfm_cli_main(int argc, char **argv)
     for (int i = 0; i < num; i++)
         if (rc[i] != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", errs[i].c_str()); return 0; }
 
+    if (mono) {
+        // CLinearSFMImp::runMono (LinearSFMImp.cpp:3136-3152)
+        lsfm_map outm;
+        auto tm0 = std::chrono::steady_clock::now();
+        if (lsfm_run_mono_ex(maps.data(), num, 1, &outm) != LSFM_OK) {
+            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+        }
+        double secm = std::chrono::duration<double>(std::chrono::steady_clock::now() - tm0).count();
+        printf("Total Used Time:  %lf  sec\n\n", secm);        // LinearSFMImp.cpp:6639 (incl. H2D/D2H here)
+        for (auto &m : maps) lsfm_free_map(&m);
+        if (!st.empty()) lsfm_save_outputs(&outm, st.c_str(), nullptr, nullptr);
+        if (!pose.empty() && !feat.empty()) lsfm_save_outputs(&outm, nullptr, pose.c_str(), feat.c_str());
+        lsfm_free_map(&outm);
+        return 0;
+    }
     lsfm_tree *tree = nullptr;
     if (lsfm_tree_create_stereo(maps.data(), num, &tree) != LSFM_OK) {
         fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;

@@ -43,3 +43,20 @@ def test_writers_match_reference(oracle, tmp_path):
     assert rc == 0
     for a in ("st", "p", "f"):
         assert filecmp.cmp(tmp_path / f"{a}.txt", tmp_path / f"{a}_ref.txt", shallow=False), a
+
+
+def test_mono_reader_matches_reference(oracle, tmp_path):
+    import ctypes as C
+    maps = synth.make_mono_scene(3, feats_per_frame=10, seed=8)
+    for i, lm in enumerate(maps):
+        p = str(tmp_path / f"localmap_{i + 1}.txt")
+        write_localmap(p, lm, mono=True)
+        out = oracle.RefMap()
+        assert oracle.lib().ref_load_localmap_mono(p.encode(), C.byref(out)) == 0
+        ref = oracle.from_c(out, free=False)
+        got_c = _lib.LsfmMap()
+        _lib.check(_lib.lib().lsfm_load_localmap_mono(p.encode(), C.byref(got_c)))
+        got = api.from_c(got_c)
+        assert_maps_match(got, ref, tol_state=0, tol_info=0, what="mono reader")
+        for k in ("ScaP", "Fix", "Sign", "FScaP", "FFix"):
+            assert getattr(got, k) == getattr(ref, k) == getattr(lm, k), k

@@ -1,0 +1,56 @@
+"""Drop-in process boundary: our LinearSFM executable vs the reference's own CLI binary
+(oracle/_ref/LinearSFM_ref = reference main + implementation TU + CHOLMOD shim) on the same
+localmap_<i>.txt files: same stdout progress lines, output files equal to the printed precision."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from linearsfm_b200 import _lib, synth
+from linearsfm_b200.localmap import write_localmap
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_CLI = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "LinearSFM_ref")
+
+
+def run_cli(exe, d, n, typ, tag):
+    out = {k: os.path.join(d, f"{tag}_{k}.txt") for k in ("p", "f", "st")}
+    r = subprocess.run([exe, "-path", d, "-num", str(n), "-type", typ, "-p", out["p"], "-f", out["f"],
+                        "-st", out["st"]], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    return r.stdout, out
+
+
+def load_table(path):
+    return np.array([[float(x) for x in line.split()] for line in open(path) if line.strip()])
+
+
+@pytest.mark.parametrize("typ,n", [("Stereo", 6), ("Monocular", 5)])
+def test_cli_dropin(gpu, tmp_path, typ, n):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("reference CLI binary not built")
+    mono = typ == "Monocular"
+    maps = synth.make_mono_scene(n, 16, seed=31) if mono else synth.make_stereo_scene(n, 12, seed=32)
+    import tempfile
+    d = tempfile.mkdtemp(prefix="lsfm", dir="/tmp")        # the reference builds paths in char[200] (Imp.cpp:121)
+    for i, lm in enumerate(maps):
+        write_localmap(os.path.join(d, f"localmap_{i + 1}.txt"), lm, mono=mono)
+    so_ref, f_ref = run_cli(REF_CLI, d, n, typ, "ref")
+    so_got, f_got = run_cli(_lib.CLI_PATH, d, n, typ, "got")
+    prog = lambda s: [l for l in s.splitlines() if l.startswith(("Join Level", "Generate Level"))]
+    assert prog(so_got) == prog(so_ref)
+    assert "Total Used Time:" in so_got
+    for k in ("p", "f", "st"):
+        a, b = load_table(f_got[k]), load_table(f_ref[k])
+        assert a.shape == b.shape, k
+        assert np.array_equal(a[:, 0], b[:, 0]), k                    # ids / stno
+        assert np.max(np.abs(a[:, 1:] - b[:, 1:])) <= 2e-6, k        # %lf prints 6 decimals
+
+
+def test_cli_errors(gpu):
+    r = subprocess.run([_lib.CLI_PATH, "-num", "3", "-type", "Stereo"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Please Input Right File Path" in r.stdout
+    r = subprocess.run([_lib.CLI_PATH, "-help"], capture_output=True, text=True)
+    assert "Linear SFM Solution General Options" in r.stdout
