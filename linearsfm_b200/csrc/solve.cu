@@ -85,7 +85,7 @@ struct FeatChunk { int k, f0, f1; };
 __global__ void __launch_bounds__(PAT_THREADS)
 k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, int mode,
             int *__restrict__ cnt, const int *__restrict__ scan, u64 *__restrict__ keys,
-            int *__restrict__ maxNposes)
+            int *__restrict__ maxNposes, int pat_cmax)
 {
     extern __shared__ unsigned smu[];
     const FeatChunk ch = chunks[blockIdx.x];
@@ -126,7 +126,7 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, in
     __syncthreads();
     const int nposes = misc[0];
     if (mode == 0 && tid == 0 && maxNposes) atomicMax(maxNposes, nposes);
-    if (nposes <= PAT_CMAX) {
+    if (nposes <= pat_cmax) {
         for (int f = ch.f0 + tid; f < ch.f1; f += nt) {
             int a0 = M.wPtr[f], a1 = M.wPtr[f + 1];
             for (int a = a0; a < a1; a++) {
@@ -790,13 +790,16 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     } else {
         DevBuf<int> pcnt(nChunks + 1, s), pscan(nChunks + 1, s);
         pcnt.zero();
+        // test hook: LSFM_FORCE_OVERFLOW=1 sends every chunk with > 4 poses down the overflow paths
+        static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
+        const int pat_cmax = force_ovf ? 4 : PAT_CMAX;
         size_t shb = sizeof(int) * (2 * (size_t)maxWords + 16 + PAT_CMAX + 1 + 2 + PAT_THREADS + 1);
         if (shb > 48 * 1024)
             CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
         int nChunkKeys = 0;
         if (nChunks > 0) {
             dMaxNp.zero();
-            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 0, pcnt.p, nullptr, nullptr, dMaxNp.p); nl++;
+            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 0, pcnt.p, nullptr, nullptr, dMaxNp.p, pat_cmax); nl++;
             exclusive_scan(ctx, pcnt.p, pscan.p, nChunks + 1); nl += 2;
             CUDA_CHECK(cudaMemcpyAsync(&nChunkKeys, pscan.p + nChunks, sizeof(int), cudaMemcpyDeviceToHost, s));
             CUDA_CHECK(cudaMemcpyAsync(&maxNposes, dMaxNp.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -810,7 +813,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         }
         if (J.totU > 0) { k_pat_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, K, J.totU, rawKeys.p); nl++; }
         if (nChunks > 0) {
-            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 1, nullptr, pscan.p, rawKeys.p + J.totU, nullptr); nl++;
+            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 1, nullptr, pscan.p, rawKeys.p + J.totU, nullptr, pat_cmax); nl++;
         }
     }
     {
@@ -867,7 +870,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
                 kern<<<nChunks, threads, shb, s>>>(J.d.p, dChunks.p, J.dFeatPre.p, J.dPosePre.p, Vinv.p, eF,
                                                   keys.p, rowPtr.p, S.p, E.p);
             };
-            if (maxNposes <= 8)
+            static const bool force_ovf2 = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
+            if (maxNposes <= 8 || force_ovf2)
                 launch(schur_pipe::k_schur_pipe<8, 8, 64>, schur_pipe::Layout<8, 8>::bytes(maxWords), 64);
             else if (maxNposes <= 16)
                 launch(schur_pipe::k_schur_pipe<16, 8, 128>, schur_pipe::Layout<16, 8>::bytes(maxWords), 128);

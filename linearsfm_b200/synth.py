@@ -237,7 +237,8 @@ def make_stereo_scene(num_maps: int, feats_per_frame: int = 128, seed: int = SEE
 # ---------------------------------------------------------------------------------------------
 def make_mono_scene(num_maps: int, feats_per_frame: int = 64, seed: int = SEED0 + 1,
                     min_life: int = 3, max_life: int = 6, sigma: float = 0.3, f: float = 400.0,
-                    cx: float = 256.0, cy: float = 192.0, return_truth: bool = False):
+                    cx: float = 256.0, cy: float = 192.0, return_truth: bool = False,
+                    style: str = "forward"):
     """`num_maps` monocular local maps.  Map k (1-based) is built from the three frames k, k+1, k+2:
     state = [pose k (= Ref, all zero), pose k+1 (= ScaP, translation component Fix pinned to Sign),
     pose k+2, landmarks], in the frame of pose k and in units where |t_{k+1}[Fix]| = 1; consecutive
@@ -249,17 +250,33 @@ def make_mono_scene(num_maps: int, feats_per_frame: int = 64, seed: int = SEED0 
     rng = np.random.default_rng(np.random.PCG64(seed))
     N = int(num_maps)
     nf = N + 2
-    p, ang, Rw = make_trajectory(nf, rng)
-    Fix = 0
     L_total = nf * feats_per_frame
     start = np.repeat(np.arange(nf), feats_per_frame)
     life = rng.integers(min_life, max_life + 1, L_total)
     end = np.minimum(start + life - 1, nf - 1)
-    depth = rng.uniform(4.0, 30.0, L_total)
-    th = rng.uniform(-np.deg2rad(25.0), np.deg2rad(25.0), L_total)
-    tv = rng.uniform(-np.deg2rad(18.0), np.deg2rad(18.0), L_total)
-    Xl = np.stack([depth, depth * np.tan(th), depth * np.tan(tv)], -1)
-    Xw = np.einsum("nji,nj->ni", Rw[start], Xl) + p[start]
+    if style == "aerial":
+        # RS-shape (aerial photogrammetry): the camera looks along +x at terrain ~100 units away and
+        # flies sideways (+y) with a baseline/depth ratio of 0.2 -- strong parallax, 60-80 % overlap.
+        B = 20.0
+        p = np.zeros((nf, 3))
+        p[:, 1] = B * np.arange(nf) + rng.normal(0, 0.5, nf)
+        p[:, 0] = rng.normal(0, 1.0, nf)
+        p[:, 2] = 3.0 * np.sin(np.arange(nf) * 0.3)
+        ang = np.stack([np.deg2rad(3.0) * np.sin(np.arange(nf) * 0.21 + 1.0),
+                        np.deg2rad(2.0) * np.sin(np.arange(nf) * 0.13), np.deg2rad(2.0) * np.sin(np.arange(nf) * 0.17)], -1)
+        Rw = rot_ypr(ang[:, 0], ang[:, 1], ang[:, 2])
+        Fix = 1
+        Xw = np.stack([rng.uniform(80.0, 120.0, L_total),
+                       p[start, 1] + 0.5 * (life - 1) * B + rng.uniform(-12.0, 12.0, L_total),
+                       rng.uniform(-45.0, 45.0, L_total)], -1)
+    else:
+        p, ang, Rw = make_trajectory(nf, rng)
+        Fix = 0
+        depth = rng.uniform(4.0, 30.0, L_total)
+        th = rng.uniform(-np.deg2rad(25.0), np.deg2rad(25.0), L_total)
+        tv = rng.uniform(-np.deg2rad(18.0), np.deg2rad(18.0), L_total)
+        Xl = np.stack([depth, depth * np.tan(th), depth * np.tan(tv)], -1)
+        Xw = np.einsum("nji,nj->ni", Rw[start], Xl) + p[start]
     gid = np.arange(1, L_total + 1, dtype=np.int64)
 
     def proj(Xc):

@@ -44,3 +44,27 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def main_mono():
+    ro.build()
+    maps = synth.make_mono_scene(5, feats_per_frame=8, seed=515151)
+    d = {}
+    meta = lambda lm: np.array([lm.Ref, lm.FRef, lm.m, lm.n, lm.ScaP, lm.Fix, lm.Sign, lm.FScaP, lm.FFix], np.int64)
+    def pk(prefix, lm):
+        for f in FIELDS:
+            d[f"{prefix}_{f}"] = getattr(lm, f)
+        d[f"{prefix}_meta"] = meta(lm)
+    for i, lm in enumerate(maps):
+        pk(f"leaf{i}", lm)
+    t0 = ro.transform_mono(maps[0], maps[1].Ref, maps[1].ScaP, maps[1].Fix)
+    pk("tf0", t0)
+    pk("join0", ro.join_mono(t0, maps[1]))
+    fin, _, _ = ro.run_tree_mono(maps)
+    pk("final", fin)
+    np.savez_compressed(os.path.join(HERE, "mono_n5.npz"), **d)
+    print("wrote mono_n5.npz final m,n", fin.m, fin.n)
+
+
+if __name__ == "__main__":
+    main_mono()

@@ -51,3 +51,35 @@ def test_gpu_matches_golden(gpu, gold):
     assert_maps_match(j0, load("join0", d), what="join0")
     fin = gpu.CLinearSFMImp().lmj_PF3D_Divide_ConquerStereo(leaves)
     assert_maps_match(fin, load("final", d), tol_state=1e-8, tol_info=1e-8, what="final")
+
+
+GM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mono_n5.npz")
+
+
+def load_mono(prefix, d):
+    mt = d[f"{prefix}_meta"]
+    return LocalMap(Ref=int(mt[0]), FRef=int(mt[1]), m=int(mt[2]), n=int(mt[3]), ScaP=int(mt[4]), Fix=int(mt[5]),
+                    Sign=int(mt[6]), FScaP=int(mt[7]), FFix=int(mt[8]),
+                    **{f: d[f"{prefix}_{f}"] for f in ("stno", "stVal", "U", "Ui", "Uj", "W", "photo",
+                                                       "feature", "V", "FBlock")})
+
+
+def test_oracle_reproduces_mono_golden(oracle):
+    d = np.load(GM)
+    leaves = [load_mono(f"leaf{i}", d) for i in range(5)]
+    t0 = oracle.transform_mono(leaves[0], leaves[1].Ref, leaves[1].ScaP, leaves[1].Fix)
+    assert_maps_match(t0, load_mono("tf0", d), tol_state=1e-13, tol_info=1e-12, what="mono tf0")
+    fin, _, _ = oracle.run_tree_mono(leaves)
+    assert_maps_match(fin, load_mono("final", d), tol_state=1e-10, tol_info=1e-10, what="mono final")
+
+
+@pytest.mark.gpu
+def test_gpu_matches_mono_golden(gpu):
+    d = np.load(GM)
+    leaves = [load_mono(f"leaf{i}", d) for i in range(5)]
+    t0 = gpu.transform_mono_batch([leaves[0]], [leaves[1].Ref], [leaves[1].ScaP], [leaves[1].Fix])[0]
+    assert_maps_match(t0, load_mono("tf0", d), what="mono tf0")
+    j0 = gpu.join_mono_batch([load_mono("tf0", d)], [leaves[1]])[0]
+    assert_maps_match(j0, load_mono("join0", d), what="mono join0")
+    fin = gpu.run_mono(leaves)
+    assert_maps_match(fin, load_mono("final", d), tol_state=1e-8, tol_info=1e-8, what="mono final")

@@ -70,7 +70,43 @@ def test_mono_tree(gpu, oracle, n, fpf):
     maps = synth.make_mono_scene(n, feats_per_frame=fpf, seed=900 + n)
     ref, _, _ = oracle.run_tree_mono(maps)
     got = gpu.run_mono(maps)
-    assert_maps_match(got, ref, tol_state=1e-7, tol_info=1e-7, what=f"mono tree N={n}")
+    # mono chains amplify rounding (tests/test_mono_conditioning.py): state to the north_star bound,
+    # information blocks a little looser
+    assert_maps_match(got, ref, tol_state=1e-6, tol_info=5e-6, what=f"mono tree N={n}")
     check_meta(got, ref)
     from util import state_rel_err
     assert state_rel_err(got, ref) <= 1e-6
+
+
+def test_mono_rs90_size(gpu, oracle):
+    # RS90_C shape: 88 local maps (BASELINE.json configs[0]), aerial-style synthetic scene
+    maps = synth.make_mono_scene(88, feats_per_frame=40, style="aerial", seed=90)
+    ref, _, _ = oracle.run_tree_mono(maps)
+    got = gpu.run_mono(maps)
+    from linearsfm_b200.localmap import maps_equal_int
+    from util import rel_err
+    assert not maps_equal_int(got, ref)
+    # The reference's mono pipeline amplifies a 1e-15 relative perturbation of its INPUT to ~4e-7 on
+    # the final state at this size (tests/test_mono_conditioning.py); 1e-5 is the meaningful bar here.
+    assert rel_err(got.stVal, ref.stVal) <= 1e-5
+
+
+def test_mono_parity_relative_to_reference_conditioning(gpu, oracle):
+    """Longer chains: the reference's own result moves by `sens` when its input is perturbed in the
+    last bit; the CUDA path must agree with the reference to within a small multiple of that."""
+    import copy
+    from util import rel_err
+    from linearsfm_b200.localmap import maps_equal_int
+    maps = synth.make_mono_scene(160, feats_per_frame=32, style="aerial", seed=160)
+    ref, _, _ = oracle.run_tree_mono(maps)
+    rng = np.random.default_rng(0)
+    pert = []
+    for m in maps:
+        m2 = copy.deepcopy(m)
+        m2.W = m2.W * (1 + 1e-15 * rng.standard_normal(m2.W.shape))
+        pert.append(m2)
+    ref2, _, _ = oracle.run_tree_mono(pert)
+    sens = rel_err(ref.stVal, ref2.stVal)
+    got = gpu.run_mono(maps)
+    assert not maps_equal_int(got, ref)
+    assert rel_err(got.stVal, ref.stVal) <= max(1e-6, 30 * sens), (rel_err(got.stVal, ref.stVal), sens)
