@@ -3,14 +3,16 @@
 //   S(p,q) -= sum_f W_pf V_f^-1 W_qf^T ,  E_p -= sum_f W_pf V_f^-1 eF_f      (LinearSFMImp.cpp:2246-2332)
 //
 // One CTA per chunk of SCH_FCHUNK consecutive features of one join.  The <= CMAX distinct poses the
-// chunk touches get local indices (bitmap over the join's poses + popcount prefix).  Each thread
-// owns two pose-pair slots and keeps their 6x6 blocks in REGISTERS for the whole chunk; the chunk's
-// features stream through shared memory in batches of NB:
-//     raw stage   : cp.async (LDGSTS) of the batch's contiguous W blocks / photo ids / V^-1 / eF into
-//                   a DOUBLE-BUFFERED raw area -- issued one batch ahead, so HBM latency overlaps
-//                   the arithmetic of the previous batch;
-//     re-layout   : raw -> [feature][local pose] padded tiles (stride 19 doubles: conflict-free
-//                   64-bit LDS), computing W V^-1 on the way;
+// chunk touches have local indices; the pattern kernel (k_pat_chunk, pass 0) already built that
+// table and left it in chunkInfo (pose list) and blkInfo (per W block: feature-in-chunk << 8 | local
+// pose), so the prologue here is two small loads.  Each thread owns two pose-pair slots and keeps
+// their 6x6 blocks in REGISTERS for the whole chunk; the chunk's features stream through shared
+// memory in batches of NB:
+//     raw stage   : cp.async (LDGSTS) of the batch's contiguous W blocks / block infos / V^-1 / eF
+//                   into a DOUBLE-BUFFERED raw area -- issued one batch ahead, so HBM latency
+//                   overlaps the arithmetic of the previous batch;
+//     re-layout   : one thread per (block, row): raw -> [feature][local pose] padded tiles (stride 19
+//                   doubles: conflict-free 64-bit LDS), computing the row of W V^-1 on the way;
 //     pair update : thread (i,j) adds W V^-1|_i * W^T|_j for every feature that sees both poses.
 // One flush of 36 FP64 atomics per touched pair and chunk.  Three instantiations trade registers /
 // shared memory for resident CTAs: (CMAX 8, 64 thr) x4-5 per SM for the lower tree levels,
@@ -46,21 +48,22 @@ struct Layout {
     static constexpr int rawW = 0;                                   // [2][MAXBLK*18] double
     static constexpr int rawVi = rawW + 2 * MAXBLK * 18 * 8;         // [2][NB*9+1] double (+1: 16B pad)
     static constexpr int rawEf = rawVi + 2 * (NB * 9 + 1) * 8;       // [2][NB*3+1] double
-    static constexpr int rawPh = rawEf + 2 * (NB * 3 + 1) * 8;       // [2][MAXBLK] int
+    static constexpr int rawPh = rawEf + 2 * (NB * 3 + 1) * 8;       // [2][MAXBLK] int (block infos)
     static constexpr int Wsm = rawPh + 2 * MAXBLK * 4;               // [NB][CMAX][LD] double
     static constexpr int WVsm = Wsm + NB * CMAX * LD * 8;            // [NB][CMAX][LD] double
     static constexpr int present = WVsm + NB * CMAX * LD * 8;        // [2][NB] unsigned (by raw buffer)
     static constexpr int poses = present + 2 * NB * 4;               // [CMAX+1] int
     static constexpr int misc = poses + (CMAX + 1) * 4;              // [4] int
     static constexpr int wptr = misc + 16;                           // [SCH_FCHUNK+1] int
-    static constexpr int bitmap = wptr + (SCH_FCHUNK + 1 + 3) / 4 * 16;   // [words] unsigned, then [words] int prefix
-    static size_t bytes(int words) { return (size_t)bitmap + 8 * (size_t)words + 16; }
+    static constexpr int end = wptr + (SCH_FCHUNK + 1 + 3) / 4 * 16;
+    static size_t bytes() { return (size_t)end + 16; }
 };
 
 template <int CMAX, int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
-             const int *__restrict__ featPre, const int *__restrict__ posePre,
+             const int *__restrict__ chunkInfo, const int *__restrict__ blkInfo, int pat_cmax,
+             const int *__restrict__ wPre, const int *__restrict__ featPre, const int *__restrict__ posePre,
              const double *__restrict__ Vinv, const double *__restrict__ eF,
              const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
              double *__restrict__ S, double *__restrict__ E)
@@ -77,52 +80,23 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     int *poses = (int *)(smraw + L::poses);
     int *misc = (int *)(smraw + L::misc);
     int *wptr = (int *)(smraw + L::wptr);
-    unsigned *bitmap = (unsigned *)(smraw + L::bitmap);
-
     const FeatChunk ch = chunks[blockIdx.x];
     const DMap &M = J[ch.k];
     const int k = ch.k;
-    const int words = (M.m + 31) >> 5;
-    int *prefix = (int *)(bitmap + words);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int nfeat = ch.f1 - ch.f0;
+    const int *ci = chunkInfo + CHUNK_INFO_INTS * (size_t)blockIdx.x;
 
     for (int i = tid; i <= nfeat; i += THREADS) wptr[i] = M.wPtr[ch.f0 + i];
-    for (int i = tid; i < words; i += THREADS) bitmap[i] = 0u;
+    if (tid < CMAX) poses[tid] = ci[tid];
+    const int nposes = ci[31];
     __syncthreads();
     const int w0 = wptr[0], w1 = wptr[nfeat];
-    for (int j = w0 + tid; j < w1; j += THREADS) {
-        int p = M.photo[j];
-        atomicOr(&bitmap[p >> 5], 1u << (p & 31));
-    }
-    __syncthreads();
-    if (warp == 0) {
-        int run = 0;
-        for (int base = 0; base < words; base += 32) {
-            int c = (base + lane < words) ? __popc(bitmap[base + lane]) : 0;
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (base + lane < words) prefix[base + lane] = run + incl - c;
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) misc[0] = run;
-    }
-    __syncthreads();
-    const int nposes = misc[0];
     if (nposes == 0) return;
-    if (nposes > CMAX) {                 // not expected: the host picks CMAX from the measured maximum
+    if (nposes > CMAX || nposes > pat_cmax) {   // not expected: the host picks CMAX from the measured maximum
         for (int a = w0 + tid; a < w1; a += THREADS)
             schur_block_slow(M, k, a, featPre, posePre, Vinv, eF, keys, rowPtr, S, E);
         return;
-    }
-    for (int i = tid; i < words; i += THREADS) {
-        unsigned b = bitmap[i];
-        int r = prefix[i];
-        while (b) { int bit = __ffs(b) - 1; poses[r++] = i * 32 + bit; b &= b - 1; }
     }
     const int npairs = nposes * (nposes + 1) / 2;
     const int rep = max(1, min(NB, (2 * THREADS) / npairs));
@@ -149,7 +123,7 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     bool touched[2] = {false, false};
 
     const double *Wg = M.W;
-    const int *Pg = M.photo;
+    const int *Pg = blkInfo + wPre[k];
     const double *Vg = Vinv + 9 * (size_t)(featPre[k] + ch.f0);
     const double *Eg = eF + 3 * (size_t)(featPre[k] + ch.f0);
     const int nbatches = (nfeat + NB - 1) / NB;
@@ -180,23 +154,24 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         __syncthreads();                               // batch bi landed; previous pair update done
         if (tid < NB) present[(buf ^ 1) * NB + tid] = 0u;      // for the next batch (set after its barrier)
         if (bi + 1 < nbatches) issue(bi + 1, buf ^ 1);
-        // re-layout raw -> padded tiles, W V^-1 on the way
+        // re-layout raw -> padded tiles, one thread per (block, row); the row of W V^-1 on the way
         const double *rW = rawW + buf * (L::MAXBLK * 18);
         const int *rP = rawPh + buf * L::MAXBLK;
         const double *rV = rawVi + buf * (NB * 9 + 1);
-        for (int e = tid; e < nblk * 18; e += THREADS) {
-            int blk = e / 18, el = e - 18 * blk;
-            int gb = b0 + blk;
-            int fb = 0;
-#pragma unroll
-            for (int q = 1; q < NB; q++) fb += (q < nbf && wptr[fb0 + q] <= gb);
-            int p = rP[blk];
-            int slot = prefix[p >> 5] + __popc(bitmap[p >> 5] & ((1u << (p & 31)) - 1u));
-            const double *wr = rW + 18 * blk + 3 * (el / 3);
-            const double *vi = rV + 9 * fb + 3 * (el % 3);
-            Wsm[(fb * CMAX + slot) * LD + el] = rW[18 * blk + el];
-            WVsm[(fb * CMAX + slot) * LD + el] = wr[0] * vi[0] + wr[1] * vi[1] + wr[2] * vi[2];
-            if (el == 0) atomicOr(&present[buf * NB + fb], 1u << slot);
+        for (int e = tid; e < nblk * 6; e += THREADS) {
+            int blk = e / 6, r = e - 6 * blk;
+            int info = rP[blk];
+            int fb = (info >> 8) - fb0, slot = info & 255;
+            const double *wr = rW + 18 * blk + 3 * r;
+            const double *vi = rV + 9 * fb;
+            double w0_ = wr[0], w1_ = wr[1], w2_ = wr[2];
+            double *dw = Wsm + (fb * CMAX + slot) * LD + 3 * r;
+            double *dv = WVsm + (fb * CMAX + slot) * LD + 3 * r;
+            dw[0] = w0_; dw[1] = w1_; dw[2] = w2_;
+            dv[0] = w0_ * vi[0] + w1_ * vi[1] + w2_ * vi[2];
+            dv[1] = w0_ * vi[3] + w1_ * vi[4] + w2_ * vi[5];
+            dv[2] = w0_ * vi[6] + w1_ * vi[7] + w2_ * vi[8];
+            if (r == 0) atomicOr(&present[buf * NB + fb], 1u << slot);
         }
         __syncthreads();
         const double *rE = rawEf + buf * (NB * 3 + 1);

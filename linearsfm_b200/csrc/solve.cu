@@ -12,6 +12,7 @@
 #include "small_mat.cuh"
 #include <cub/cub.cuh>
 #include <thread>
+#include <chrono>
 
 namespace {
 
@@ -81,11 +82,15 @@ __global__ void k_pat_emit(const DMap *__restrict__ J, const int *__restrict__ f
 constexpr int PAT_CMAX = 31;
 constexpr int PAT_THREADS = 128;
 struct FeatChunk { int k, f0, f1; };
+// Per chunk, written by pass 0 and reused by pass 1 and by the Schur kernel:
+//   [0..30] local pose table (ascending pose index), [31] #distinct poses, [32..47] pair bitmap
+constexpr int CHUNK_INFO_INTS = 48;
 
 __global__ void __launch_bounds__(PAT_THREADS)
 k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, int mode,
             int *__restrict__ cnt, const int *__restrict__ scan, u64 *__restrict__ keys,
-            int *__restrict__ maxNposes, int pat_cmax)
+            int *__restrict__ maxNposes, int pat_cmax, int *__restrict__ chunkInfo,
+            int *__restrict__ blkInfo, const int *__restrict__ wPre)
 {
     extern __shared__ unsigned smu[];
     const FeatChunk ch = chunks[blockIdx.x];
@@ -98,6 +103,25 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, in
     int *misc = poses + PAT_CMAX + 1;                // [0] nposes, [1] raw count
     int *featOff = misc + 2;                         // [PAT_THREADS + 1] (overflow path only)
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    int *ci = chunkInfo + CHUNK_INFO_INTS * (size_t)blockIdx.x;
+    if (mode == 1 && ci[31] <= pat_cmax) {
+        // pass 1: emit the chunk's distinct pairs from what pass 0 left behind (no second look at W)
+        const int nposes = ci[31];
+        if (tid < PAT_CMAX) poses[tid] = ci[tid];
+        if (tid < 16) pairBits[tid] = (unsigned)ci[32 + tid];
+        __syncthreads();
+        const int o0 = scan[blockIdx.x];
+        const int npairs = nposes * (nposes + 1) / 2;
+        for (int t = tid; t < npairs; t += nt) {
+            if (!((pairBits[t >> 5] >> (t & 31)) & 1u)) continue;
+            int rank = __popc(pairBits[t >> 5] & ((1u << (t & 31)) - 1u));
+            for (int q = 0; q < (t >> 5); q++) rank += __popc(pairBits[q]);
+            int r = t, i = 0;
+            while (r >= nposes - i) { r -= nposes - i; i++; }
+            keys[o0 + rank] = pair_key(ch.k, poses[i], poses[i + r]);
+        }
+        return;
+    }
     const int w0 = M.wPtr[ch.f0], w1 = M.wPtr[ch.f1];
     for (int i = tid; i < words; i += nt) bitmap[i] = 0u;
     if (tid < 16) pairBits[tid] = 0u;
@@ -125,13 +149,15 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, in
     }
     __syncthreads();
     const int nposes = misc[0];
-    if (mode == 0 && tid == 0 && maxNposes) atomicMax(maxNposes, nposes);
-    if (nposes <= pat_cmax) {
+    if (mode == 0 && tid == 0) { atomicMax(maxNposes, nposes); ci[31] = nposes; }
+    if (nposes <= pat_cmax) {      // mode 0 only (mode 1 took the early exit above)
+        int *bi = blkInfo + wPre[ch.k];
         for (int f = ch.f0 + tid; f < ch.f1; f += nt) {
             int a0 = M.wPtr[f], a1 = M.wPtr[f + 1];
             for (int a = a0; a < a1; a++) {
                 int pa = M.photo[a];
                 int sa = prefix[pa >> 5] + __popc(bitmap[pa >> 5] & ((1u << (pa & 31)) - 1u));
+                bi[a] = ((f - ch.f0) << 8) | sa;
                 for (int b = a; b < a1; b++) {
                     int pb = M.photo[b];
                     int sb = prefix[pb >> 5] + __popc(bitmap[pb >> 5] & ((1u << (pb & 31)) - 1u));
@@ -141,30 +167,17 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, in
                 }
             }
         }
-        if (mode == 1)
-            for (int i = tid; i < words; i += nt) {
-                unsigned b = bitmap[i];
-                int r = prefix[i];
-                while (b) { int bit = __ffs(b) - 1; poses[r++] = i * 32 + bit; b &= b - 1; }
-            }
-        __syncthreads();
-        if (mode == 0) {
-            if (tid == 0) {
-                int c = 0;
-                for (int q = 0; q < 16; q++) c += __popc(pairBits[q]);
-                cnt[blockIdx.x] = c;
-            }
-            return;
+        for (int i = tid; i < words; i += nt) {
+            unsigned b = bitmap[i];
+            int r = prefix[i];
+            while (b) { int bit = __ffs(b) - 1; ci[r++] = i * 32 + bit; b &= b - 1; }
         }
-        const int o0 = scan[blockIdx.x];
-        const int npairs = nposes * (nposes + 1) / 2;
-        for (int t = tid; t < npairs; t += nt) {
-            if (!((pairBits[t >> 5] >> (t & 31)) & 1u)) continue;
-            int rank = __popc(pairBits[t >> 5] & ((1u << (t & 31)) - 1u));
-            for (int q = 0; q < (t >> 5); q++) rank += __popc(pairBits[q]);
-            int r = t, i = 0;
-            while (r >= nposes - i) { r -= nposes - i; i++; }
-            keys[o0 + rank] = pair_key(ch.k, poses[i], poses[i + r]);
+        __syncthreads();
+        if (tid < 16) ci[32 + tid] = (int)pairBits[tid];
+        if (tid == 0) {
+            int c = 0;
+            for (int q = 0; q < 16; q++) c += __popc(pairBits[q]);
+            cnt[blockIdx.x] = c;
         }
         return;
     }
@@ -776,6 +789,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     int nRaw = 0;
     int maxNposes = 1 << 30;             // max distinct poses of any chunk (measured by k_pat_chunk)
     DevBuf<int> dMaxNp(1, s);
+    DevBuf<int> chunkInfo((size_t)CHUNK_INFO_INTS * std::max(nChunks, 1), s), blkInfo((size_t)std::max(J.totW, 1), s);
+    int pat_cmax_used = PAT_CMAX;
     DevBuf<u64> rawKeys, sortedKeys, keys;
     static const bool pat_v1 = getenv("LSFM_PATTERN_V1") != nullptr;
     if (pat_v1) {
@@ -793,13 +808,15 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         // test hook: LSFM_FORCE_OVERFLOW=1 sends every chunk with > 4 poses down the overflow paths
         static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
         const int pat_cmax = force_ovf ? 4 : PAT_CMAX;
+        pat_cmax_used = pat_cmax;
         size_t shb = sizeof(int) * (2 * (size_t)maxWords + 16 + PAT_CMAX + 1 + 2 + PAT_THREADS + 1);
         if (shb > 48 * 1024)
             CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
         int nChunkKeys = 0;
         if (nChunks > 0) {
             dMaxNp.zero();
-            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 0, pcnt.p, nullptr, nullptr, dMaxNp.p, pat_cmax); nl++;
+            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 0, pcnt.p, nullptr, nullptr, dMaxNp.p, pat_cmax,
+                                                          chunkInfo.p, blkInfo.p, J.dWPre.p); nl++;
             exclusive_scan(ctx, pcnt.p, pscan.p, nChunks + 1); nl += 2;
             CUDA_CHECK(cudaMemcpyAsync(&nChunkKeys, pscan.p + nChunks, sizeof(int), cudaMemcpyDeviceToHost, s));
             CUDA_CHECK(cudaMemcpyAsync(&maxNposes, dMaxNp.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -813,7 +830,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         }
         if (J.totU > 0) { k_pat_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, K, J.totU, rawKeys.p); nl++; }
         if (nChunks > 0) {
-            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 1, nullptr, pscan.p, rawKeys.p + J.totU, nullptr, pat_cmax); nl++;
+            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 1, nullptr, pscan.p, rawKeys.p + J.totU, nullptr, pat_cmax,
+                                                          chunkInfo.p, blkInfo.p, J.dWPre.p); nl++;
         }
     }
     {
@@ -862,21 +880,21 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         if (use_v1) {
             k_schur<<<ceil_div(J.totW, 128), 128, 0, s>>>(J.d.p, J.dWPre.p, J.dFeatPre.p, J.dPosePre.p, K, J.totW,
                                                          Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p); nl++;
-        } else if (getenv("LSFM_SCHUR_V2") == nullptr) {
+        } else if (getenv("LSFM_SCHUR_V2") == nullptr && !pat_v1) {   // (the old pattern path leaves no chunkInfo)
             // pipelined kernel; instantiation chosen from the measured max #distinct poses per chunk
             auto launch = [&](auto kern, size_t shb, int threads) {
                 if (shb > 48 * 1024)
                     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
-                kern<<<nChunks, threads, shb, s>>>(J.d.p, dChunks.p, J.dFeatPre.p, J.dPosePre.p, Vinv.p, eF,
-                                                  keys.p, rowPtr.p, S.p, E.p);
+                kern<<<nChunks, threads, shb, s>>>(J.d.p, dChunks.p, chunkInfo.p, blkInfo.p, pat_cmax_used, J.dWPre.p,
+                                                  J.dFeatPre.p, J.dPosePre.p, Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p);
             };
             static const bool force_ovf2 = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
             if (maxNposes <= 8 || force_ovf2)
-                launch(schur_pipe::k_schur_pipe<8, 8, 64>, schur_pipe::Layout<8, 8>::bytes(maxWords), 64);
+                launch(schur_pipe::k_schur_pipe<8, 8, 64>, schur_pipe::Layout<8, 8>::bytes(), 64);
             else if (maxNposes <= 16)
-                launch(schur_pipe::k_schur_pipe<16, 8, 128>, schur_pipe::Layout<16, 8>::bytes(maxWords), 128);
+                launch(schur_pipe::k_schur_pipe<16, 8, 128>, schur_pipe::Layout<16, 8>::bytes(), 128);
             else
-                launch(schur_pipe::k_schur_pipe<31, 8, 256>, schur_pipe::Layout<31, 8>::bytes(maxWords), 256);
+                launch(schur_pipe::k_schur_pipe<31, 8, 256>, schur_pipe::Layout<31, 8>::bytes(), 256);
             nl++;
         } else {
             DevBuf<int> err_dbg(4, s);
@@ -910,9 +928,17 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     for (int k = 0; k < K; k++) { mvec[k] = J.h[k].m; sOff[k] = hRowPtr[J.posePre[k]]; }
     sOff[K] = nuis;
     BatchSymbolic sym;
+    static const bool dbg_time = getenv("LSFM_DEBUG") != nullptr;
+    auto tsym0 = std::chrono::steady_clock::now();
     try {
         build_symbolic(K, mvec, J.posePre, hKeys, sOff, sym, (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
     } catch (const std::exception &e) { throw LsfmError(LSFM_ERR_ARG, std::string("symbolic: ") + e.what()); }
+    if (dbg_time) {
+        double hms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tsym0).count();
+        bool schur_done = cudaStreamQuery(s) == cudaSuccess;
+        fprintf(stderr, "    [symbolic] K=%d totPose=%d nuis=%d host %.3f ms, Schur kernel %s when it finished\n", K,
+                J.totPose, nuis, hms, schur_done ? "ALREADY DONE (GPU idle)" : "still running");
+    }
     ctx.end(8.0 * nuis, 0.0, nl);
     nl = 0;
 

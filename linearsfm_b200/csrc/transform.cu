@@ -218,16 +218,19 @@ __device__ __forceinline__ void add_block(double *dst, const double *P, bool tra
         for (int q = 0; q < 6; q++) atomicAdd(dst + 6 * r + q, transpose ? P[6 * q + r] : P[6 * r + q]);
 }
 
-// one thread per old U block (LinearSFMImp.cpp:725-1266). U blocks are few (nU << nW).
+// one thread per old U block (LinearSFMImp.cpp:725-1266). U blocks are few (nU << nW), but EVERY
+// block adds into the (pos,pos) slot of its map: that sum is reduced across the warp first
+// (warp_agg_atomic_add), otherwise the root map's 38k blocks serialise on 36 addresses.
 __global__ void __launch_bounds__(128)
 k_ucong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ uPre,
         const int *__restrict__ posePre, int K, int totU, const TfConst *__restrict__ tc,
         const PoseJac *__restrict__ pj, const int *__restrict__ uScan)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= totU) return;
-    int k = seg_find(uPre, K, g);
-    int b = g - uPre[k];
+    bool active = g < totU;                     // no early return: the warp stays converged
+    int gg = active ? g : totU - 1;
+    int k = seg_find(uPre, K, gg);
+    int b = gg - uPre[k];
     const DMap &M = in[k];
     const TfConst &c = tc[k];
     int pid = c.posID;
@@ -243,8 +246,15 @@ k_ucong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restri
     // C_i^T I C_j -> (pos,pos)
     sm::mtm<6, 6, 6>(J2i, I, T);
     sm::mm<6, 6, 6>(T, J2j, P);
-    add_block(Un + 36 * (size_t)pid, P, false);
-    if (i != j) add_block(Un + 36 * (size_t)pid, P, true);
+    {
+        double Q[36];
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int q = 0; q < 6; q++) Q[6 * r + q] = P[6 * r + q] + (i != j ? P[6 * q + r] : 0.0);
+        sm::warp_agg_atomic_add<36>(Un + 36 * (size_t)pid, Q, active);
+    }
+    if (!active) return;
     // C_i^T I D_j -> (pos,j), stored in slot j
     sm::mm<6, 6, 6>(T, J1j, P);
     if (j >= pid) add_block(Un + 36 * (size_t)j, P, false);
