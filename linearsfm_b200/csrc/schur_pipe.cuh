@@ -22,6 +22,8 @@
 namespace schur_pipe {
 
 constexpr int LD = 19;
+// lower-triangle entries of a diagonal pair's accumulator block that carry its share of E
+__device__ constexpr int EIDX[6] = {6, 12, 13, 18, 19, 20};
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -41,26 +43,28 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
-template <int CMAX, int NB>
+// Batches are sized by a BLOCK budget, not a feature count: a batch takes consecutive features
+// while their blocks fit into MAXBLK (a feature has <= CMAX <= MAXBLK blocks) and up to NBMAX features.  The lower tree levels (2-4 blocks per feature) therefore run a
+// chunk in 4-6 batches instead of 16, the top levels (~14 blocks per feature) in ~8.
+template <int CMAX, int MAXBLK, int NBMAX>
 struct Layout {
     // all offsets in bytes, 16-byte aligned where cp.async needs it
-    static constexpr int MAXBLK = NB * CMAX;
     static constexpr int rawW = 0;                                   // [2][MAXBLK*18] double
-    static constexpr int rawVi = rawW + 2 * MAXBLK * 18 * 8;         // [2][NB*9+1] double (+1: 16B pad)
-    static constexpr int rawEf = rawVi + 2 * (NB * 9 + 1) * 8;       // [2][NB*3+1] double
-    static constexpr int rawPh = rawEf + 2 * (NB * 3 + 1) * 8;       // [2][MAXBLK] int (block infos)
-    static constexpr int Wsm = rawPh + 2 * MAXBLK * 4;               // [NB][CMAX][LD] double
-    static constexpr int WVsm = Wsm + NB * CMAX * LD * 8;            // [NB][CMAX][LD] double
-    static constexpr int present = WVsm + NB * CMAX * LD * 8;        // [2][NB] unsigned (by raw buffer)
-    static constexpr int poses = present + 2 * NB * 4;               // [CMAX+1] int
-    static constexpr int misc = poses + (CMAX + 1) * 4;              // [4] int
-    static constexpr int wptr = misc + 16;                           // [SCH_FCHUNK+1] int
-    static constexpr int end = wptr + (SCH_FCHUNK + 1 + 3) / 4 * 16;
+    static constexpr int rawVi = rawW + 2 * MAXBLK * 18 * 8;         // [2][NBMAX*9+1] double (+1: 16B pad)
+    static constexpr int rawEf = rawVi + 2 * (NBMAX * 9 + 1) * 8;    // [2][NBMAX*3+1] double
+    static constexpr int rawPh = rawEf + 2 * (NBMAX * 3 + 1) * 8;    // [2][MAXBLK] int (block infos)
+    static constexpr int Wsm = rawPh + 2 * MAXBLK * 4;               // [MAXBLK][LD] double
+    static constexpr int WVsm = Wsm + MAXBLK * LD * 8;               // [MAXBLK][LD] double
+    static constexpr int present = WVsm + MAXBLK * LD * 8;           // [2][NBMAX] unsigned (by raw buffer)
+    static constexpr int poses = present + 2 * NBMAX * 4;            // [CMAX+1] int
+    static constexpr int wptr = poses + (CMAX + 1 + 3) / 4 * 16;     // [SCH_FCHUNK+1] int
+    static constexpr int blkOf = wptr + (SCH_FCHUNK + 1 + 3) / 4 * 16;   // [NBMAX][32] unsigned char
+    static constexpr int end = blkOf + NBMAX * 32;
     static size_t bytes() { return (size_t)end + 16; }
 };
 
-template <int CMAX, int NB, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+template <int CMAX, int MAXBLK, int NBMAX, int THREADS, int SLOTS>
+__global__ void __launch_bounds__(THREADS, (SLOTS == 1 ? 512 : 256) / THREADS)
 k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
              const int *__restrict__ chunkInfo, const int *__restrict__ blkInfo, int pat_cmax,
              const int *__restrict__ wPre, const int *__restrict__ featPre, const int *__restrict__ posePre,
@@ -68,7 +72,9 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
              const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
              double *__restrict__ S, double *__restrict__ E)
 {
-    typedef Layout<CMAX, NB> L;
+    static_assert(MAXBLK >= 2 * CMAX && MAXBLK <= 255, "block budget");
+    typedef Layout<CMAX, MAXBLK, NBMAX> L;
+    constexpr int QBLK = MAXBLK;           // a batch ends at the last feature whose blocks still fit
     extern __shared__ __align__(16) unsigned char smraw[];
     double *rawW = (double *)(smraw + L::rawW);
     double *rawVi = (double *)(smraw + L::rawVi);
@@ -78,8 +84,8 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     double *WVsm = (double *)(smraw + L::WVsm);
     unsigned *present = (unsigned *)(smraw + L::present);
     int *poses = (int *)(smraw + L::poses);
-    int *misc = (int *)(smraw + L::misc);
     int *wptr = (int *)(smraw + L::wptr);
+    unsigned char *blkOf = (unsigned char *)(smraw + L::blkOf);
     const FeatChunk ch = chunks[blockIdx.x];
     const DMap &M = J[ch.k];
     const int k = ch.k;
@@ -99,120 +105,158 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         return;
     }
     const int npairs = nposes * (nposes + 1) / 2;
-    const int rep = max(1, min(NB, (2 * THREADS) / npairs));
-    int pi[2], pj[2], pr0[2];
+    const int rep = max(1, min(NBMAX, (SLOTS * THREADS) / npairs));
+    // pair slots of one replica: the nposes diagonal pairs first (so they share warps: they run a
+    // different body), then the off-diagonal pairs (i<j) row by row
+    int pi[SLOTS], pj[SLOTS], pr0[SLOTS];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < SLOTS; u++) {
         pi[u] = -1; pj[u] = -1; pr0[u] = 0;
         int q = tid + u * THREADS;
         int r = q / npairs, t = q - r * npairs;
         if (r < rep) {
-            int i = 0;
-            while (t >= nposes - i) { t -= nposes - i; i++; }
-            pi[u] = i; pj[u] = i + t; pr0[u] = r;
+            pr0[u] = r;
+            if (t < nposes) { pi[u] = t; pj[u] = t; }
+            else {
+                t -= nposes;
+                int i = 0;
+                while (t >= nposes - 1 - i) { t -= nposes - 1 - i; i++; }
+                pi[u] = i; pj[u] = i + 1 + t;
+            }
         }
     }
-    double acc[2][36], eacc[2][6];
+    // acc: the 6x6 block.  Diagonal pairs only accumulate the upper triangle (the block is
+    // symmetric) and keep their share of E in six otherwise unused lower-triangle entries.
+    double acc[SLOTS][36];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < SLOTS; u++) {
 #pragma unroll
         for (int q = 0; q < 36; q++) acc[u][q] = 0.0;
-#pragma unroll
-        for (int q = 0; q < 6; q++) eacc[u][q] = 0.0;
     }
-    bool touched[2] = {false, false};
+    bool touched[SLOTS];
+#pragma unroll
+    for (int u = 0; u < SLOTS; u++) touched[u] = false;
 
     const double *Wg = M.W;
     const int *Pg = blkInfo + wPre[k];
     const double *Vg = Vinv + 9 * (size_t)(featPre[k] + ch.f0);
     const double *Eg = eF + 3 * (size_t)(featPre[k] + ch.f0);
-    const int nbatches = (nfeat + NB - 1) / NB;
 
-    // raw stage of batch `bi` into buffer `buf` (asynchronous)
-    auto issue = [&](int bi, int buf) {
-        const int fb0 = bi * NB, nbf = min(NB, nfeat - fb0);
-        const int b0 = wptr[fb0], nblk = wptr[fb0 + nbf] - b0;
-        double *dW = rawW + buf * (L::MAXBLK * 18);
+    // end of the batch that starts at feature fa (uniform across the CTA)
+    auto batch_end = [&](int fa) {
+        int target = wptr[fa] + QBLK;
+        int lo = fa + 1, hi = min(nfeat, fa + NBMAX);
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (wptr[mid] <= target) lo = mid; else hi = mid - 1; }
+        return lo;
+    };
+    // raw stage of the batch [fa, fe) into buffer `buf` (asynchronous)
+    auto issue = [&](int fa, int fe, int buf) {
+        const int nbf = fe - fa;
+        const int b0 = wptr[fa], nblk = wptr[fe] - b0;
+        double *dW = rawW + buf * (MAXBLK * 18);
         const double *sW = Wg + 18 * (size_t)b0;
         for (int c = tid; c < nblk * 9; c += THREADS) cp_async16(dW + 2 * c, sW + 2 * c);
-        int *dP = rawPh + buf * L::MAXBLK;
+        int *dP = rawPh + buf * MAXBLK;
         for (int c = tid; c < nblk; c += THREADS) cp_async4(dP + c, Pg + b0 + c);
-        double *dV = rawVi + buf * (NB * 9 + 1);
-        for (int c = tid; c < nbf * 9; c += THREADS) cp_async8(dV + c, Vg + 9 * (size_t)fb0 + c);
-        double *dE = rawEf + buf * (NB * 3 + 1);
-        for (int c = tid; c < nbf * 3; c += THREADS) cp_async8(dE + c, Eg + 3 * (size_t)fb0 + c);
+        double *dV = rawVi + buf * (NBMAX * 9 + 1);
+        for (int c = tid; c < nbf * 9; c += THREADS) cp_async8(dV + c, Vg + 9 * (size_t)fa + c);
+        double *dE = rawEf + buf * (NBMAX * 3 + 1);
+        for (int c = tid; c < nbf * 3; c += THREADS) cp_async8(dE + c, Eg + 3 * (size_t)fa + c);
         cp_async_commit();
     };
 
-    if (tid < 2 * NB) present[tid] = 0u;
-    issue(0, 0);
-    for (int bi = 0; bi < nbatches; bi++) {
+    for (int i = tid; i < 2 * NBMAX; i += THREADS) present[i] = 0u;
+    int fa = 0, fe = batch_end(0);
+    issue(fa, fe, 0);
+    for (int bi = 0; fa < nfeat; bi++) {
         const int buf = bi & 1;
-        const int fb0 = bi * NB, nbf = min(NB, nfeat - fb0);
-        const int b0 = wptr[fb0], nblk = wptr[fb0 + nbf] - b0;
+        const int nbf = fe - fa;
+        const int b0 = wptr[fa], nblk = wptr[fe] - b0;
+        const int fa2 = fe, fe2 = (fa2 < nfeat) ? batch_end(fa2) : fa2;
         cp_async_wait_all();
-        __syncthreads();                               // batch bi landed; previous pair update done
-        if (tid < NB) present[(buf ^ 1) * NB + tid] = 0u;      // for the next batch (set after its barrier)
-        if (bi + 1 < nbatches) issue(bi + 1, buf ^ 1);
-        // re-layout raw -> padded tiles, one thread per (block, row); the row of W V^-1 on the way
-        const double *rW = rawW + buf * (L::MAXBLK * 18);
-        const int *rP = rawPh + buf * L::MAXBLK;
-        const double *rV = rawVi + buf * (NB * 9 + 1);
+        __syncthreads();                               // this batch landed; previous pair update done
+        for (int i = tid; i < NBMAX; i += THREADS) present[(buf ^ 1) * NBMAX + i] = 0u;   // for the next batch
+        if (fa2 < nfeat) issue(fa2, fe2, buf ^ 1);
+        // re-layout raw -> padded rows, one thread per (block, row); the row of W V^-1 on the way
+        const double *rW = rawW + buf * (MAXBLK * 18);
+        const int *rP = rawPh + buf * MAXBLK;
+        const double *rV = rawVi + buf * (NBMAX * 9 + 1);
         for (int e = tid; e < nblk * 6; e += THREADS) {
             int blk = e / 6, r = e - 6 * blk;
             int info = rP[blk];
-            int fb = (info >> 8) - fb0, slot = info & 255;
+            int fb = (info >> 8) - fa, slot = info & 255;
             const double *wr = rW + 18 * blk + 3 * r;
             const double *vi = rV + 9 * fb;
             double w0_ = wr[0], w1_ = wr[1], w2_ = wr[2];
-            double *dw = Wsm + (fb * CMAX + slot) * LD + 3 * r;
-            double *dv = WVsm + (fb * CMAX + slot) * LD + 3 * r;
+            double *dw = Wsm + blk * LD + 3 * r;
+            double *dv = WVsm + blk * LD + 3 * r;
             dw[0] = w0_; dw[1] = w1_; dw[2] = w2_;
             dv[0] = w0_ * vi[0] + w1_ * vi[1] + w2_ * vi[2];
             dv[1] = w0_ * vi[3] + w1_ * vi[4] + w2_ * vi[5];
             dv[2] = w0_ * vi[6] + w1_ * vi[7] + w2_ * vi[8];
-            if (r == 0) atomicOr(&present[buf * NB + fb], 1u << slot);
+            if (r == 0) {
+                blkOf[fb * 32 + slot] = (unsigned char)blk;
+                atomicOr(&present[buf * NBMAX + fb], 1u << slot);
+            }
         }
         __syncthreads();
-        const double *rE = rawEf + buf * (NB * 3 + 1);
+        const double *rE = rawEf + buf * (NBMAX * 3 + 1);
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < SLOTS; u++) {
             if (pi[u] < 0) continue;
             for (int fb = pr0[u]; fb < nbf; fb += rep) {
-                unsigned pr = present[buf * NB + fb];
+                unsigned pr = present[buf * NBMAX + fb];
                 if (((pr >> pi[u]) & (pr >> pj[u]) & 1u) == 0u) continue;
                 touched[u] = true;
-                const double *wv = WVsm + (fb * CMAX + pi[u]) * LD;
-                const double *w = Wsm + (fb * CMAX + pj[u]) * LD;
+                const double *wv = WVsm + (int)blkOf[fb * 32 + pi[u]] * LD;
+                const double *w = Wsm + (int)blkOf[fb * 32 + pj[u]] * LD;
                 double b[18];
 #pragma unroll
                 for (int q = 0; q < 18; q++) b[q] = w[q];
+                if (pi[u] == pj[u]) {
+                    const double *ef = rE + 3 * fb;
+                    const double e0 = ef[0], e1 = ef[1], e2 = ef[2];
 #pragma unroll
-                for (int r = 0; r < 6; r++) {
-                    double a0 = wv[3 * r], a1 = wv[3 * r + 1], a2 = wv[3 * r + 2];
+                    for (int r = 0; r < 6; r++) {
+                        double a0 = wv[3 * r], a1 = wv[3 * r + 1], a2 = wv[3 * r + 2];
 #pragma unroll
-                    for (int c = 0; c < 6; c++)
-                        acc[u][6 * r + c] += a0 * b[3 * c] + a1 * b[3 * c + 1] + a2 * b[3 * c + 2];
-                    if (pi[u] == pj[u]) {
-                        const double *ef = rE + 3 * fb;
-                        eacc[u][r] += a0 * ef[0] + a1 * ef[1] + a2 * ef[2];
+                        for (int c = r; c < 6; c++)
+                            acc[u][6 * r + c] = fma(a2, b[3 * c + 2], fma(a1, b[3 * c + 1], fma(a0, b[3 * c], acc[u][6 * r + c])));
+                        acc[u][EIDX[r]] = fma(a2, e2, fma(a1, e1, fma(a0, e0, acc[u][EIDX[r]])));
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double a0 = wv[3 * r], a1 = wv[3 * r + 1], a2 = wv[3 * r + 2];
+#pragma unroll
+                        for (int c = 0; c < 6; c++)     // three chained FMAs (not mul/fma/fma + add)
+                            acc[u][6 * r + c] = fma(a2, b[3 * c + 2], fma(a1, b[3 * c + 1], fma(a0, b[3 * c], acc[u][6 * r + c])));
                     }
                 }
             }
         }
+        fa = fa2; fe = fe2;
     }
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < SLOTS; u++) {
         if (!touched[u]) continue;
         int gi = poses[pi[u]], gj = poses[pj[u]];
         int slot = find_slot(keys, rowPtr, posePre[k] + gi, pair_key(k, gi, gj));
         double *sp = S + 36 * (size_t)slot;
-#pragma unroll
-        for (int q = 0; q < 36; q++) atomicAdd(sp + q, -acc[u][q]);
         if (pi[u] == pj[u]) {
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = r; c < 6; c++) {
+                    atomicAdd(sp + 6 * r + c, -acc[u][6 * r + c]);
+                    if (c > r) atomicAdd(sp + 6 * c + r, -acc[u][6 * r + c]);
+                }
             double *e = E + 6 * (size_t)(posePre[k] + gi);
 #pragma unroll
-            for (int q = 0; q < 6; q++) atomicAdd(e + q, -eacc[u][q]);
+            for (int q = 0; q < 6; q++) atomicAdd(e + q, -acc[u][EIDX[q]]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 36; q++) atomicAdd(sp + q, -acc[u][q]);
         }
     }
 }

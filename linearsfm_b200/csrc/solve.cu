@@ -890,11 +890,11 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             };
             static const bool force_ovf2 = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
             if (maxNposes <= 8 || force_ovf2)
-                launch(schur_pipe::k_schur_pipe<8, 8, 64>, schur_pipe::Layout<8, 8>::bytes(), 64);
+                launch(schur_pipe::k_schur_pipe<8, 64, 32, 128, 1>, schur_pipe::Layout<8, 64, 32>::bytes(), 128);
             else if (maxNposes <= 16)
-                launch(schur_pipe::k_schur_pipe<16, 8, 128>, schur_pipe::Layout<16, 8>::bytes(), 128);
+                launch(schur_pipe::k_schur_pipe<16, 128, 32, 256, 1>, schur_pipe::Layout<16, 128, 32>::bytes(), 256);
             else
-                launch(schur_pipe::k_schur_pipe<31, 8, 256>, schur_pipe::Layout<31, 8>::bytes(), 256);
+                launch(schur_pipe::k_schur_pipe<31, 248, 32, 512, 1>, schur_pipe::Layout<31, 248, 32>::bytes(), 512);
             nl++;
         } else {
             DevBuf<int> err_dbg(4, s);
