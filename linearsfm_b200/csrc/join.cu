@@ -149,34 +149,31 @@ __global__ void k_join_u(const DMap *__restrict__ E, const DMap *__restrict__ C,
     }
 }
 
-// one thread per joint feature: V merge, W copy, eF, eP contributions (2747-2930)
-__global__ void __launch_bounds__(128)
-k_join_feat(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__restrict__ J,
-            const int *__restrict__ featPreJ, const int *__restrict__ posePreJ, int K, int totJ,
-            const int *__restrict__ curOfJoint, const int *__restrict__ wScan,
-            double *__restrict__ eP, double *__restrict__ eF)
+// one thread per joint feature: V merge, labels, CSR start, the V part of eF, and the feature's two
+// estimates (End side, Cur side) for the solver's d vectors (2747-2930)
+__global__ void __launch_bounds__(256)
+k_join_featinit(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__restrict__ J,
+                const int *__restrict__ featPreJ, int K, int totJ, const int *__restrict__ curOfJoint,
+                const int *__restrict__ wScan, double *__restrict__ eF, double *__restrict__ xhat)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = g < totJ;
-    int k = live ? seg_find(featPreJ, K, g) : 0;
-    int jf = live ? g - featPreJ[k] : 0;
+    if (g >= totJ) return;
+    int k = seg_find(featPreJ, K, g);
+    int jf = g - featPreJ[k];
     const DMap &Em = E[k];
     const DMap &Cm = C[k];
     const DMap &Jm = J[k];
-    int m1 = Em.m;
-    int c = live ? curOfJoint[g] : -1;
-    bool hasE = live && jf < Em.n;
+    int c = curOfJoint[g];
+    bool hasE = jf < Em.n;
     double ef[3] = {0.0, 0.0, 0.0};
     double V[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) V[i] = 0.0;
     double xe[3] = {0, 0, 0}, xc[3] = {0, 0, 0};
-    int e0 = 0, ke = 0, c0 = 0, kc = 0, o0 = 0;
     if (hasE) {
         sm::load<9>(Em.V + 9 * (size_t)jf, V);
         sm::load<3>(Em.featVal + 3 * (size_t)jf, xe);
         sm::mm<3, 3, 1>(V, xe, ef);
-        e0 = Em.wPtr[jf]; ke = Em.wPtr[jf + 1] - e0;
         Jm.featNo[jf] = Em.featNo[jf];
     }
     if (c >= 0) {
@@ -187,41 +184,118 @@ k_join_feat(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__rest
 #pragma unroll
         for (int i = 0; i < 9; i++) V[i] += Vc[i];
         ef[0] += t[0]; ef[1] += t[1]; ef[2] += t[2];
-        c0 = Cm.wPtr[c]; kc = Cm.wPtr[c + 1] - c0;
         if (!hasE) Jm.featNo[jf] = Cm.featNo[c];
     }
-    if (live) {
-        sm::store<9>(Jm.V + 9 * (size_t)jf, V);
-        o0 = wScan[g] - wScan[featPreJ[k]];
-        Jm.wPtr[jf] = o0;
-    }
-    int kt = ke + kc;
-    int kmax = __reduce_max_sync(0xffffffffu, kt);
-    for (int jj = 0; jj < kmax; jj++) {
-        bool act = jj < kt;
-        double y[6];
-        int p = 0;
-        if (act) {
-            bool fromE = jj < ke;
-            const DMap &S = fromE ? Em : Cm;
-            int sb = fromE ? e0 + jj : c0 + (jj - ke);
-            double W[18];
-            sm::load<18>(S.W + 18 * (size_t)sb, W);
-            sm::store<18>(Jm.W + 18 * (size_t)(o0 + jj), W);
-            int sp = S.photo[sb];
-            p = sp + (fromE ? 0 : m1);
-            Jm.photo[o0 + jj] = p;
-            Jm.feature[o0 + jj] = jf;
-            const double *xf = fromE ? xe : xc;
-            sm::mm<6, 3, 1>(W, xf, y);                           // eP_p += W xhat_f
-            double xp[6], t[3];
-            sm::load<6>(S.poseVal + 6 * (size_t)sp, xp);
-            sm::mtm<3, 6, 1>(W, xp, t);                           // eF_f += W^T xhat_p
-            ef[0] += t[0]; ef[1] += t[1]; ef[2] += t[2];
+    sm::store<9>(Jm.V + 9 * (size_t)jf, V);
+    Jm.wPtr[jf] = wScan[g] - wScan[featPreJ[k]];
+    sm::store<3>(eF + 3 * (size_t)g, ef);
+    double *x = xhat + 6 * (size_t)g;
+    x[0] = xe[0]; x[1] = xe[1]; x[2] = xe[2]; x[3] = xc[0]; x[4] = xc[1]; x[5] = xc[2];
+}
+
+// one thread per SOURCE W block (End's blocks, then Cur's, of every join): its slot in the joint map
+// (per joint feature: End blocks, then Cur blocks), the integer labels, and the slot itself for the
+// value copy that runs later (k_join_w).  Only integers: this is all the S pattern needs.
+__global__ void __launch_bounds__(256)
+k_join_ints(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__restrict__ J,
+            const int *__restrict__ wPreJ, const int *__restrict__ featPreJ,
+            const int *__restrict__ featPreC, int K, int totW, const int *__restrict__ jointOfCur,
+            const int *__restrict__ wScan, int *__restrict__ dstOf)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totW) return;
+    int k = seg_find(wPreJ, K, g);
+    int b = g - wPreJ[k];
+    const DMap &Em = E[k];
+    bool fromE = b < Em.nW;
+    const DMap &S = fromE ? Em : C[k];
+    int sb = fromE ? b : b - Em.nW;
+    int f = S.feature[sb];
+    int jf = fromE ? f : jointOfCur[featPreC[k] + f];
+    int before = (!fromE && jf < Em.n) ? Em.wPtr[jf + 1] - Em.wPtr[jf] : 0;
+    int gj = featPreJ[k] + jf;
+    int o = (wScan[gj] - wScan[featPreJ[k]]) + before + (sb - S.wPtr[f]);
+    J[k].photo[o] = S.photo[sb] + (fromE ? 0 : Em.m);
+    J[k].feature[o] = jf;
+    dstOf[g] = o;
+}
+
+// W value copy + the W part of eF (eF_f += W_pf^T xhat_p, 2830-2930), one thread per source block.
+// A warp whose 32 blocks come from one source map reads them as ONE contiguous 4.6 KB span
+// (coalesced), scatters whole blocks to their joint slots (runs of consecutive slots) and passes
+// each lane its own block through shared memory for the 6x3 product; the per-feature sums are
+// reduced across the lanes of a feature before the atomics.
+__global__ void __launch_bounds__(128)
+k_join_w(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__restrict__ J,
+         const int *__restrict__ wPreJ, const int *__restrict__ featPreJ,
+         const int *__restrict__ featPreC, int K, int totW, const int *__restrict__ jointOfCur,
+         const int *__restrict__ dstOf, double *__restrict__ eF)
+{
+    __shared__ double tile[4][32 * 19];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = g < totW;
+    int gg = live ? g : totW - 1;
+    int k = seg_find(wPreJ, K, gg);
+    int b = gg - wPreJ[k];
+    const DMap &Em = E[k];
+    bool fromE = b < Em.nW;
+    const DMap &S = fromE ? Em : C[k];
+    int sb = fromE ? b : b - Em.nW;
+    int f = S.feature[sb];
+    int p = S.photo[sb];
+    int jf = fromE ? f : jointOfCur[featPreC[k] + f];
+    int gj = featPreJ[k] + jf;
+    int o = dstOf[gg];
+    int k0 = __shfl_sync(full, k, 0);
+    int e0 = __shfl_sync(full, (int)fromE, 0);
+    bool uni = __all_sync(full, live && k == k0 && (int)fromE == e0);
+    double W[18];
+    double *dst = J[k].W;
+    if (uni) {
+        const double *src = S.W + 18 * (size_t)(sb - lane);       // the warp's first block
+        double *tw = tile[warp];
+#pragma unroll
+        for (int it = 0; it < 18; it++) {
+            int e = it * 32 + lane;
+            int blk = e / 18, el = e - 18 * blk;
+            double v = src[e];
+            int ob = __shfl_sync(full, o, blk);
+            dst[18 * (size_t)ob + el] = v;
+            tw[blk * 19 + el] = v;
         }
-        sm::warp_agg_atomic_add<6>(eP + 6 * (size_t)(posePreJ[k] + p), y, act);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 18; q++) W[q] = tw[lane * 19 + q];
+    } else if (live) {
+        sm::load<18>(S.W + 18 * (size_t)sb, W);
+        sm::store<18>(dst + 18 * (size_t)o, W);
     }
-    if (live) sm::store<3>(eF + 3 * (size_t)g, ef);
+    double t[3] = {0.0, 0.0, 0.0};
+    int key = -1 - lane;                       // dead lanes get unique keys
+    if (live) {
+        double xp[6];
+        sm::load<6>(S.poseVal + 6 * (size_t)p, xp);
+        sm::mtm<3, 6, 1>(W, xp, t);
+        key = 2 * gj + (fromE ? 0 : 1);    // End and Cur runs of one feature stay separate segments: a key
+                                            // must never reappear after a different one (a,b,a would be double counted)
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int okey = __shfl_down_sync(full, key, off);
+        bool take = (lane + off < 32) && (okey == key);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double ov = __shfl_down_sync(full, t[i], off);
+            if (take) t[i] += ov;
+        }
+    }
+    int pkey = __shfl_up_sync(full, key, 1);
+    if (live && (lane == 0 || pkey != key)) {
+        double *e = eF + 3 * (size_t)gj;
+        atomicAdd(e, t[0]); atomicAdd(e + 1, t[1]); atomicAdd(e + 2, t[2]);
+    }
 }
 
 __global__ void k_wptr_end(DMap *__restrict__ J, int K)
@@ -380,22 +454,45 @@ std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHand
                                                             curOfJoint.p, wCnt.p); nl++;
     exclusive_scan(ctx, wCnt.p, wScan.p, J.totFeat + 1); nl += 2;
 
-    DevBuf<double> eP(6 * (size_t)J.totPose, s), eF(3 * (size_t)J.totFeat, s);
+    // eP: only the U part here; the W xhat_f part is folded into the reduced right-hand side by the
+    // solver through the per-feature d vectors (SolveExtra, k_vinv)
+    DevBuf<double> eP(6 * (size_t)J.totPose, s), eF(3 * (size_t)J.totFeat, s), xhat(6 * (size_t)J.totFeat, s);
+    DevBuf<int> dstOf(std::max(J.totW, 1), s);
     eP.zero();
     k_join_pose<<<ceil_div(J.totPose, TB), TB, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dPosePre.p, K, J.totPose); nl++;
     if (J.totU > 0) {
         k_join_u<<<ceil_div(J.totU, 128), 128, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dUPre.p, J.dPosePre.p, K, J.totU, eP.p); nl++;
     }
     if (J.totFeat > 0) {
-        k_join_feat<<<ceil_div(J.totFeat, 128), 128, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dFeatPre.p, J.dPosePre.p, K,
-                                                            J.totFeat, curOfJoint.p, wScan.p, eP.p, eF.p); nl++;
+        k_join_featinit<<<ceil_div(J.totFeat, TB), TB, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dFeatPre.p, K, J.totFeat,
+                                                              curOfJoint.p, wScan.p, eF.p, xhat.p); nl++;
+    }
+    if (J.totW > 0) {
+        k_join_ints<<<ceil_div(J.totW, TB), TB, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dWPre.p, J.dFeatPre.p, C.dFeatPre.p, K,
+                                                       J.totW, jointOfCur.p, wScan.p, dstOf.p); nl++;
     }
     k_wptr_end<<<ceil_div(K, TB), TB, 0, s>>>(J.d.p, K); nl++;
+    std::vector<int> hSplit(K);
+    for (int k = 0; k < K; k++) hSplit[k] = E.h[k].m;
+    DevBuf<int> dSplit(K, s);
+    dSplit.upload(hSplit);
     KERNEL_CHECK();
-    ctx.end(bytes, 0.0, nl);
+    const double valueBytes = 288.0 * J.totW + 24.0 * J.totFeat;
+    ctx.end(bytes - valueBytes, 0.0, nl);
 
-    // ---- a8-a13 ----
-    solve_stereo_batch(ctx, J, eP.p, eF.p, nullptr);
+    // ---- a8-a13; the W value copy is queued by the solver once the pattern is with the host ----
+    SolveExtra ex;
+    ex.xhat = xhat.p;
+    ex.split = dSplit.p;
+    ex.after_pattern = [&]() {
+        ctx.begin("join.values");
+        if (J.totW > 0)
+            k_join_w<<<ceil_div(J.totW, 128), 128, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dWPre.p, J.dFeatPre.p, C.dFeatPre.p, K,
+                                                          J.totW, jointOfCur.p, dstOf.p, eF.p);
+        KERNEL_CHECK();
+        ctx.end(valueBytes, 0.0, 1);
+    };
+    solve_stereo_batch(ctx, J, eP.p, eF.p, nullptr, nullptr, &ex);
 
     if (ctx.want_objective) {
         ctx.begin("objective");

@@ -3,6 +3,7 @@
 #pragma once
 #include "device.h"
 #include <vector>
+#include <functional>
 
 // Device view of the maps an operator works on: descriptor array + prefix sums of their sizes.
 struct OpMaps {
@@ -53,8 +54,21 @@ struct SolveDebug;   // optional capture of pattern / ordering for the parity te
 // mono gauge (device arrays, one entry per join): local index of the all-zero Ref pose, local scalar
 // row of the pinned ScaP translation component, and its value Sign (LinearSFMImp.cpp:7797-7801)
 struct MonoGauge { const int *refPose; const int *fixScalar; const int *sign; };
+// Optional hooks of the stereo join (join.cu):
+//   after_pattern : called once the S pattern is on its way to the host; queues device work that
+//                   the pattern did not need (the join's W/V value copy and eF), so that it overlaps
+//                   the host symbolic phase.
+//   xhat[6 totFeat]: per joint feature the End-side and Cur-side estimates (zeros where absent);
+//   split[K]       : number of End poses of every join (joint pose p < split -> End side).
+//   With these, eP holds only the U part of the reference's eP and the Schur kernel folds the
+//   W xhat_f part into the reduced right-hand side (see k_vinv in solve.cu).
+struct SolveExtra {
+    std::function<void()> after_pattern;
+    const double *xhat = nullptr;
+    const int *split = nullptr;
+};
 void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const double *eF,
-                        SolveDebug *dbg, const MonoGauge *gauge = nullptr);
+                        SolveDebug *dbg, const MonoGauge *gauge = nullptr, const SolveExtra *ex = nullptr);
 
 struct SolveDebug {
     // for the first map of the batch only

@@ -1,6 +1,7 @@
 // k_schur_pipe: register-tiled, software-pipelined Schur complement kernel (included by solve.cu).
 //
-//   S(p,q) -= sum_f W_pf V_f^-1 W_qf^T ,  E_p -= sum_f W_pf V_f^-1 eF_f      (LinearSFMImp.cpp:2246-2332)
+//   S(p,q) -= sum_f W_pf V_f^-1 W_qf^T ,  E_p -= sum_f W_pf d_f      (LinearSFMImp.cpp:2246-2332;
+//   d_f = V_f^-1 eF_f - xhat_f of the pose's side of the join, see k_vinv)
 //
 // One CTA per chunk of SCH_FCHUNK consecutive features of one join.  The <= CMAX distinct poses the
 // chunk touches have local indices; the pattern kernel (k_pat_chunk, pass 0) already built that
@@ -51,8 +52,8 @@ struct Layout {
     // all offsets in bytes, 16-byte aligned where cp.async needs it
     static constexpr int rawW = 0;                                   // [2][MAXBLK*18] double
     static constexpr int rawVi = rawW + 2 * MAXBLK * 18 * 8;         // [2][NBMAX*9+1] double (+1: 16B pad)
-    static constexpr int rawEf = rawVi + 2 * (NBMAX * 9 + 1) * 8;    // [2][NBMAX*3+1] double
-    static constexpr int rawPh = rawEf + 2 * (NBMAX * 3 + 1) * 8;    // [2][MAXBLK] int (block infos)
+    static constexpr int rawEf = rawVi + 2 * (NBMAX * 9 + 1) * 8;    // [2][NBMAX*6] double (d vectors)
+    static constexpr int rawPh = rawEf + 2 * (NBMAX * 6) * 8;        // [2][MAXBLK] int (block infos)
     static constexpr int Wsm = rawPh + 2 * MAXBLK * 4;               // [MAXBLK][LD] double
     static constexpr int WVsm = Wsm + MAXBLK * LD * 8;               // [MAXBLK][LD] double
     static constexpr int present = WVsm + MAXBLK * LD * 8;           // [2][NBMAX] unsigned (by raw buffer)
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(THREADS, (SLOTS == 1 ? 512 : 256) / THREADS)
 k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
              const int *__restrict__ chunkInfo, const int *__restrict__ blkInfo, int pat_cmax,
              const int *__restrict__ wPre, const int *__restrict__ featPre, const int *__restrict__ posePre,
-             const double *__restrict__ Vinv, const double *__restrict__ eF,
+             const double *__restrict__ Vinv, const double *__restrict__ dvec, const int *__restrict__ split,
              const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
              double *__restrict__ S, double *__restrict__ E)
 {
@@ -101,7 +102,7 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     if (nposes == 0) return;
     if (nposes > CMAX || nposes > pat_cmax) {   // not expected: the host picks CMAX from the measured maximum
         for (int a = w0 + tid; a < w1; a += THREADS)
-            schur_block_slow(M, k, a, featPre, posePre, Vinv, eF, keys, rowPtr, S, E);
+            schur_block_slow(M, k, a, featPre, posePre, Vinv, dvec, split, keys, rowPtr, S, E);
         return;
     }
     const int npairs = nposes * (nposes + 1) / 2;
@@ -134,13 +135,17 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         for (int q = 0; q < 36; q++) acc[u][q] = 0.0;
     }
     bool touched[SLOTS];
+    int sideOff[SLOTS];          // diagonal pairs: which of the feature's two d vectors (End / Cur side)
 #pragma unroll
-    for (int u = 0; u < SLOTS; u++) touched[u] = false;
+    for (int u = 0; u < SLOTS; u++) {
+        touched[u] = false;
+        sideOff[u] = (split && pi[u] >= 0 && poses[pi[u]] >= split[k]) ? 3 : 0;
+    }
 
     const double *Wg = M.W;
     const int *Pg = blkInfo + wPre[k];
     const double *Vg = Vinv + 9 * (size_t)(featPre[k] + ch.f0);
-    const double *Eg = eF + 3 * (size_t)(featPre[k] + ch.f0);
+    const double *Eg = dvec + 6 * (size_t)(featPre[k] + ch.f0);
 
     // end of the batch that starts at feature fa (uniform across the CTA)
     auto batch_end = [&](int fa) {
@@ -160,8 +165,8 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         for (int c = tid; c < nblk; c += THREADS) cp_async4(dP + c, Pg + b0 + c);
         double *dV = rawVi + buf * (NBMAX * 9 + 1);
         for (int c = tid; c < nbf * 9; c += THREADS) cp_async8(dV + c, Vg + 9 * (size_t)fa + c);
-        double *dE = rawEf + buf * (NBMAX * 3 + 1);
-        for (int c = tid; c < nbf * 3; c += THREADS) cp_async8(dE + c, Eg + 3 * (size_t)fa + c);
+        double *dE = rawEf + buf * (NBMAX * 6);
+        for (int c = tid; c < nbf * 6; c += THREADS) cp_async8(dE + c, Eg + 6 * (size_t)fa + c);
         cp_async_commit();
     };
 
@@ -200,7 +205,7 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
             }
         }
         __syncthreads();
-        const double *rE = rawEf + buf * (NBMAX * 3 + 1);
+        const double *rE = rawEf + buf * (NBMAX * 6);
 #pragma unroll
         for (int u = 0; u < SLOTS; u++) {
             if (pi[u] < 0) continue;
@@ -214,7 +219,7 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
 #pragma unroll
                 for (int q = 0; q < 18; q++) b[q] = w[q];
                 if (pi[u] == pj[u]) {
-                    const double *ef = rE + 3 * fb;
+                    const double *ef = rE + 6 * fb + sideOff[u];
                     const double e0 = ef[0], e1 = ef[1], e2 = ef[2];
 #pragma unroll
                     for (int r = 0; r < 6; r++) {
@@ -222,7 +227,7 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
 #pragma unroll
                         for (int c = r; c < 6; c++)
                             acc[u][6 * r + c] = fma(a2, b[3 * c + 2], fma(a1, b[3 * c + 1], fma(a0, b[3 * c], acc[u][6 * r + c])));
-                        acc[u][EIDX[r]] = fma(a2, e2, fma(a1, e1, fma(a0, e0, acc[u][EIDX[r]])));
+                        acc[u][EIDX[r]] = fma(b[3 * r + 2], e2, fma(b[3 * r + 1], e1, fma(b[3 * r], e0, acc[u][EIDX[r]])));
                     }
                 } else {
 #pragma unroll

@@ -24,57 +24,8 @@ __host__ __device__ inline u64 pair_key(int k, int a, int b)
 }
 
 // ---------------------------------------------------------------------------------------------
-// a8: block pattern of S.  A feature whose observer list equals the previous feature's adds no
-// new pairs (consecutive features almost always share their observers), so only "changed" features
-// emit their k(k+1)/2 pairs; sort + unique gives the reference's row-major CRS order.
+// a8: block pattern of S
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool same_observers(const DMap &M, int f)
-{
-    if (f == 0) return false;
-    int a0 = M.wPtr[f - 1], a1 = M.wPtr[f], b1 = M.wPtr[f + 1];
-    if (a1 - a0 != b1 - a1) return false;
-    for (int i = 0; i < a1 - a0; i++)
-        if (M.photo[a0 + i] != M.photo[a1 + i]) return false;
-    return true;
-}
-
-__global__ void k_pat_count(const DMap *__restrict__ J, const int *__restrict__ featPre, int K,
-                            int totF, int totU, int *__restrict__ cnt)
-{
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g > totF + totU) return;
-    if (g == totF + totU) { cnt[g] = 0; return; }
-    if (g >= totF) { cnt[g] = 1; return; }
-    int k = seg_find(featPre, K, g);
-    int f = g - featPre[k];
-    const DMap &M = J[k];
-    int kf = M.wPtr[f + 1] - M.wPtr[f];
-    cnt[g] = same_observers(M, f) ? 0 : kf * (kf + 1) / 2;
-}
-
-__global__ void k_pat_emit(const DMap *__restrict__ J, const int *__restrict__ featPre,
-                           const int *__restrict__ uPre, int K, int totF, int totU,
-                           const int *__restrict__ scan, u64 *__restrict__ keys)
-{
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= totF + totU) return;
-    int o = scan[g];
-    if (g >= totF) {
-        int u = g - totF;
-        int k = seg_find(uPre, K, u);
-        int b = u - uPre[k];
-        keys[o] = pair_key(k, J[k].Ui[b], J[k].Uj[b]);
-        return;
-    }
-    if (scan[g + 1] == o) return;
-    int k = seg_find(featPre, K, g);
-    int f = g - featPre[k];
-    const DMap &M = J[k];
-    int w0 = M.wPtr[f], w1 = M.wPtr[f + 1];
-    for (int a = w0; a < w1; a++)
-        for (int b = a; b < w1; b++) keys[o++] = pair_key(k, M.photo[a], M.photo[b]);
-}
-
 // Chunk-level exact dedupe (default path): one CTA per chunk of consecutive features builds the
 // chunk's local pose table (bitmap + popcount prefix) and a bitmap over the <= 496 local pose
 // pairs; a pair bit is set only if ONE feature is seen by both poses (the reference's smask rule,
@@ -244,8 +195,14 @@ __device__ __forceinline__ int find_slot(const u64 *__restrict__ keys, const int
 // a9: V^-1 by the cofactor formula Eigen's Matrix3d::inverse uses, symmetrised from the upper
 // triangle exactly as pba_inverseV does (LinearSFMImp.cpp:3035-3040)
 // ---------------------------------------------------------------------------------------------
+// Also writes, per feature, the two 3-vectors the Schur kernels need for the reduced right-hand side:
+//     d_side = V^-1 eF_f - xhat_f^side          (side = End / Cur half of the joint pose list)
+// so that E_p = eP_p - sum_f W_pf d_side(p): with eP holding only the U part of the reference's eP
+// (2747-2790) this equals eP_ref - W V^-1 eF (2246-2332) without the join ever accumulating
+// W xhat_f per pose.  xhat == nullptr (stand-alone solve operator, mono): d = V^-1 eF, eP as given.
 __global__ void k_vinv(const DMap *__restrict__ J, const int *__restrict__ featPre, int K, int totF,
-                       double *__restrict__ Vinv)
+                       const double *__restrict__ eF, const double *__restrict__ xhat,
+                       double *__restrict__ Vinv, double *__restrict__ dvec)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= totF) return;
@@ -268,6 +225,18 @@ __global__ void k_vinv(const DMap *__restrict__ J, const int *__restrict__ featP
     o[0] = i00; o[1] = i01; o[2] = i02;
     o[3] = i01; o[4] = i11; o[5] = i12;
     o[6] = i02; o[7] = i12; o[8] = i22;
+    double e0 = eF[3 * (size_t)g], e1 = eF[3 * (size_t)g + 1], e2 = eF[3 * (size_t)g + 2];
+    double v0 = i00 * e0 + i01 * e1 + i02 * e2;
+    double v1 = i01 * e0 + i11 * e1 + i12 * e2;
+    double v2 = i02 * e0 + i12 * e1 + i22 * e2;
+    double *d = dvec + 6 * (size_t)g;
+    if (xhat) {
+        const double *x = xhat + 6 * (size_t)g;
+        d[0] = v0 - x[0]; d[1] = v1 - x[1]; d[2] = v2 - x[2];
+        d[3] = v0 - x[3]; d[4] = v1 - x[4]; d[5] = v2 - x[5];
+    } else {
+        d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v0; d[4] = v1; d[5] = v2;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -295,8 +264,8 @@ __global__ void k_s_from_u(const DMap *__restrict__ J, const int *__restrict__ u
 __global__ void __launch_bounds__(128)
 k_schur(const DMap *__restrict__ J, const int *__restrict__ wPre, const int *__restrict__ featPre,
         const int *__restrict__ posePre, int K, int totW, const double *__restrict__ Vinv,
-        const double *__restrict__ eF, const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
-        double *__restrict__ S, double *__restrict__ E)
+        const double *__restrict__ dvec, const int *__restrict__ split, const u64 *__restrict__ keys,
+        const int *__restrict__ rowPtr, double *__restrict__ S, double *__restrict__ E)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = g < totW;
@@ -311,9 +280,9 @@ k_schur(const DMap *__restrict__ J, const int *__restrict__ wPre, const int *__r
         sm::load<18>(M.W + 18 * (size_t)a, W);
         sm::load<9>(Vinv + 9 * (size_t)(featPre[k] + f), Vi);
         sm::mmt<6, 3, 3>(W, Vi, WV);                       // WV[i][j] = sum_k W[i][k] Vinv[j][k] (2269-2270)
-        double ef[3];
-        sm::load<3>(eF + 3 * (size_t)(featPre[k] + f), ef);
-        sm::mm<6, 3, 1>(WV, ef, y);
+        double d[3];
+        sm::load<3>(dvec + 6 * (size_t)(featPre[k] + f) + ((split && pa >= split[k]) ? 3 : 0), d);
+        sm::mm<6, 3, 1>(W, d, y);
 #pragma unroll
         for (int q = 0; q < 6; q++) y[q] = -y[q];
     }
@@ -336,17 +305,18 @@ k_schur(const DMap *__restrict__ J, const int *__restrict__ wPre, const int *__r
 // Slow path for one W block (global atomics), used when a chunk sees too many distinct poses.
 __device__ __noinline__ void schur_block_slow(const DMap &M, int k, int a, const int *__restrict__ featPre,
                                  const int *__restrict__ posePre, const double *__restrict__ Vinv,
-                                 const double *__restrict__ eF, const u64 *__restrict__ keys,
+                                 const double *__restrict__ dvec, const int *__restrict__ split,
+                                 const u64 *__restrict__ keys,
                                  const int *__restrict__ rowPtr, double *__restrict__ S,
                                  double *__restrict__ E)
 {
     int f = M.feature[a], pa = M.photo[a];
-    double W[18], Vi[9], WV[18], ef[3], y[6];
+    double W[18], Vi[9], WV[18], d[3], y[6];
     sm::load<18>(M.W + 18 * (size_t)a, W);
     sm::load<9>(Vinv + 9 * (size_t)(featPre[k] + f), Vi);
     sm::mmt<6, 3, 3>(W, Vi, WV);
-    sm::load<3>(eF + 3 * (size_t)(featPre[k] + f), ef);
-    sm::mm<6, 3, 1>(WV, ef, y);
+    sm::load<3>(dvec + 6 * (size_t)(featPre[k] + f) + ((split && pa >= split[k]) ? 3 : 0), d);
+    sm::mm<6, 3, 1>(W, d, y);
     for (int q = 0; q < 6; q++) atomicAdd(E + 6 * (size_t)(posePre[k] + pa) + q, -y[q]);
     for (int b = M.wPtr[f]; b < M.wPtr[f + 1]; b++) {
         int pb = M.photo[b];
@@ -364,166 +334,6 @@ constexpr int SCH_FCHUNK = 128;        // features per chunk (pattern + Schur ke
 } // namespace
 #include "schur_pipe.cuh"
 namespace {
-
-// v2: one CTA per chunk of consecutive features of one join.  The distinct poses seen by the chunk
-// (<= SCH_CMAX: a handful of "hub" poses + the local observers) get a local index; thread t owns the
-// pose pair (i<=j) and keeps its 6x6 block of S in REGISTERS while the chunk's features stream
-// through shared memory (W and W V^-1 staged per feature, coalesced).  One flush of 36 atomics per
-// touched pair and chunk replaces 36 atomics per pair and FEATURE.
-constexpr int SCH_CMAX = 31;          // 31*32/2 = 496 pairs = 2 per thread of a 256-thread CTA
-constexpr int SCH_NB = 16;            // features staged per barrier
-constexpr int SCH_THREADS = 256;
-constexpr int SCH_LD = 19;            // padded block stride (doubles): conflict-free 64-bit LDS
-
-typedef FeatChunk SchurChunk;
-
-__global__ void __launch_bounds__(SCH_THREADS)
-k_schur_tiled(const DMap *__restrict__ J, const SchurChunk *__restrict__ chunks,
-              const int *__restrict__ featPre, const int *__restrict__ posePre,
-              const double *__restrict__ Vinv, const double *__restrict__ eF,
-              const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
-              double *__restrict__ S, double *__restrict__ E, int *__restrict__ dbgCount)
-{
-    extern __shared__ double smd[];
-    double *Wsm = smd;                                          // [NB][CMAX][LD]
-    double *WVsm = Wsm + SCH_NB * SCH_CMAX * SCH_LD;            // [NB][CMAX][LD]
-    double *efs = WVsm + SCH_NB * SCH_CMAX * SCH_LD;            // [NB][4]
-    unsigned *present = (unsigned *)(efs + SCH_NB * 4);         // [NB]
-    int *poses = (int *)(present + SCH_NB);                     // [CMAX]
-    int *nposes_s = poses + SCH_CMAX;                           // [1] (+pad)
-    unsigned *bitmap = (unsigned *)(nposes_s + 4);              // [words]
-    const SchurChunk ch = chunks[blockIdx.x];
-    const DMap &M = J[ch.k];
-    const int k = ch.k;
-    const int words = (M.m + 31) >> 5;
-    int *prefix = (int *)(bitmap + words);                      // [words]
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int w0 = M.wPtr[ch.f0], w1 = M.wPtr[ch.f1];
-
-    for (int i = tid; i < words; i += nt) bitmap[i] = 0u;
-    __syncthreads();
-    for (int j = w0 + tid; j < w1; j += nt) {
-        int p = M.photo[j];
-        atomicOr(&bitmap[p >> 5], 1u << (p & 31));
-    }
-    __syncthreads();
-    if (warp == 0) {
-        int run = 0;
-        for (int base = 0; base < words; base += 32) {
-            int c = (base + lane < words) ? __popc(bitmap[base + lane]) : 0;
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (base + lane < words) prefix[base + lane] = run + incl - c;
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) *nposes_s = run;
-    }
-    __syncthreads();
-    const int nposes = *nposes_s;
-    if (dbgCount && tid == 0) { atomicAdd(&dbgCount[0], 1); atomicAdd(&dbgCount[1], nposes > SCH_CMAX); atomicMax(&dbgCount[2], nposes); }
-    if (nposes == 0) return;
-    if (nposes > SCH_CMAX) {
-        for (int a = w0 + tid; a < w1; a += nt)
-            schur_block_slow(M, k, a, featPre, posePre, Vinv, eF, keys, rowPtr, S, E);
-        return;
-    }
-    for (int i = tid; i < words; i += nt) {
-        unsigned b = bitmap[i];
-        int r = prefix[i];
-        while (b) { int bit = __ffs(b) - 1; poses[r++] = i * 32 + bit; b &= b - 1; }
-    }
-    // Every thread owns two "pair slots" (2 x 256 = 512 >= 496).  With few distinct poses (lower
-    // tree levels) the npairs pose pairs are replicated `rep` times and replica r takes the
-    // features fb = r, r+rep, ... of each batch, so the CTA stays busy; replicas flush separately.
-    const int npairs = nposes * (nposes + 1) / 2;
-    const int rep = max(1, min(SCH_NB, (2 * SCH_THREADS) / npairs));
-    int pi[2], pj[2], pr0[2];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-        pi[u] = -1; pj[u] = -1; pr0[u] = 0;
-        int q = tid + u * SCH_THREADS;
-        int r = q / npairs, t = q - r * npairs;
-        if (r < rep) {
-            int i = 0;
-            while (t >= nposes - i) { t -= nposes - i; i++; }
-            pi[u] = i; pj[u] = i + t; pr0[u] = r;
-        }
-    }
-    double acc[2][36], eacc[2][6];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-#pragma unroll
-        for (int q = 0; q < 36; q++) acc[u][q] = 0.0;
-#pragma unroll
-        for (int q = 0; q < 6; q++) eacc[u][q] = 0.0;
-    }
-    bool touched[2] = {false, false};
-
-    for (int fb0 = ch.f0; fb0 < ch.f1; fb0 += SCH_NB) {
-        const int nbf = min(SCH_NB, ch.f1 - fb0);
-        __syncthreads();                       // previous batch fully consumed (and poses[] visible)
-        if (tid < SCH_NB) present[tid] = 0u;
-        __syncthreads();
-        const int b0 = M.wPtr[fb0], b1 = M.wPtr[fb0 + nbf];
-        for (int e = tid; e < (b1 - b0) * 18; e += nt) {
-            int blk = b0 + e / 18, el = e % 18;
-            int f = M.feature[blk], fb = f - fb0, p = M.photo[blk];
-            int slot = prefix[p >> 5] + __popc(bitmap[p >> 5] & ((1u << (p & 31)) - 1u));
-            const double *Wb = M.W + 18 * (size_t)blk;
-            Wsm[(fb * SCH_CMAX + slot) * SCH_LD + el] = Wb[el];
-            const double *Wr = Wb + 3 * (el / 3);
-            const double *Vi = Vinv + 9 * (size_t)(featPre[k] + f) + 3 * (el % 3);
-            WVsm[(fb * SCH_CMAX + slot) * SCH_LD + el] = Wr[0] * Vi[0] + Wr[1] * Vi[1] + Wr[2] * Vi[2];
-            if (el == 0) atomicOr(&present[fb], 1u << slot);
-        }
-        for (int e = tid; e < nbf * 3; e += nt)
-            efs[(e / 3) * 4 + (e % 3)] = eF[3 * (size_t)(featPre[k] + fb0 + e / 3) + (e % 3)];
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            if (pi[u] < 0) continue;
-            for (int fb = pr0[u]; fb < nbf; fb += rep) {
-                unsigned pr = present[fb];
-                if (((pr >> pi[u]) & (pr >> pj[u]) & 1u) == 0u) continue;
-                touched[u] = true;
-                const double *wv = WVsm + (fb * SCH_CMAX + pi[u]) * SCH_LD;
-                const double *w = Wsm + (fb * SCH_CMAX + pj[u]) * SCH_LD;
-                double b[18];
-#pragma unroll
-                for (int q = 0; q < 18; q++) b[q] = w[q];
-#pragma unroll
-                for (int r = 0; r < 6; r++) {
-                    double a0 = wv[3 * r], a1 = wv[3 * r + 1], a2 = wv[3 * r + 2];
-#pragma unroll
-                    for (int c = 0; c < 6; c++)
-                        acc[u][6 * r + c] += a0 * b[3 * c] + a1 * b[3 * c + 1] + a2 * b[3 * c + 2];
-                    if (pi[u] == pj[u]) {
-                        const double *ef = efs + fb * 4;
-                        eacc[u][r] += a0 * ef[0] + a1 * ef[1] + a2 * ef[2];
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-        if (!touched[u]) continue;
-        int gi = poses[pi[u]], gj = poses[pj[u]];
-        int slot = find_slot(keys, rowPtr, posePre[k] + gi, pair_key(k, gi, gj));
-        double *sp = S + 36 * (size_t)slot;
-#pragma unroll
-        for (int q = 0; q < 36; q++) atomicAdd(sp + q, -acc[u][q]);
-        if (pi[u] == pj[u]) {
-            double *e = E + 6 * (size_t)(posePre[k] + gi);
-#pragma unroll
-            for (int q = 0; q < 6; q++) atomicAdd(e + q, -eacc[u][q]);
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // a17 (mono): gauge rows.  The reference deletes the six rows/columns of the zero pose and the
@@ -766,7 +576,7 @@ void exclusive_scan(Context &ctx, const int *in, int *out, int n)
 } // namespace
 
 void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const double *eF,
-                        SolveDebug *dbg, const MonoGauge *gauge)
+                        SolveDebug *dbg, const MonoGauge *gauge, const SolveExtra *ex)
 {
     const int K = J.K;
     cudaStream_t s = ctx.stream;
@@ -792,17 +602,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     DevBuf<int> chunkInfo((size_t)CHUNK_INFO_INTS * std::max(nChunks, 1), s), blkInfo((size_t)std::max(J.totW, 1), s);
     int pat_cmax_used = PAT_CMAX;
     DevBuf<u64> rawKeys, sortedKeys, keys;
-    static const bool pat_v1 = getenv("LSFM_PATTERN_V1") != nullptr;
-    if (pat_v1) {
-        int nItems = J.totFeat + J.totU;
-        DevBuf<int> pcnt(nItems + 1, s), pscan(nItems + 1, s);
-        k_pat_count<<<ceil_div(nItems + 1, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, K, J.totFeat, J.totU, pcnt.p); nl++;
-        exclusive_scan(ctx, pcnt.p, pscan.p, nItems + 1); nl += 2;
-        CUDA_CHECK(cudaMemcpyAsync(&nRaw, pscan.p + nItems, sizeof(int), cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaStreamSynchronize(s));
-        rawKeys.alloc(nRaw, s); sortedKeys.alloc(nRaw, s); keys.alloc(nRaw, s);
-        k_pat_emit<<<ceil_div(nItems, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, J.dUPre.p, K, J.totFeat, J.totU, pscan.p, rawKeys.p); nl++;
-    } else {
+    {
         DevBuf<int> pcnt(nChunks + 1, s), pscan(nChunks + 1, s);
         pcnt.zero();
         // test hook: LSFM_FORCE_OVERFLOW=1 sends every chunk with > 4 poses down the overflow paths
@@ -863,12 +663,19 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     ctx.end(8.0 * nRaw, 0.0, nl);
     nl = 0;
 
+    // The pattern is on its way to the host symbolic phase; work the caller deferred until now
+    // (the join's value copy) is queued here so that it runs while the host analyses the pattern.
+    if (ex && ex->after_pattern) ex->after_pattern();
+
     // ---- a9-a10: V^-1, S, E ----
     ctx.begin("solve.schur_prep");
     DevBuf<double> Vinv(9 * (size_t)J.totFeat, s), S(36 * (size_t)nuis, s), E(6 * (size_t)J.totPose, s);
+    DevBuf<double> dvec(6 * (size_t)std::max(J.totFeat, 1), s);
+    const double *xhat = ex ? ex->xhat : nullptr;
+    const int *split = ex ? ex->split : nullptr;
     S.zero();
     CUDA_CHECK(cudaMemcpyAsync(E.p, eP, sizeof(double) * 6 * (size_t)J.totPose, cudaMemcpyDeviceToDevice, s));
-    if (J.totFeat > 0) { k_vinv<<<ceil_div(J.totFeat, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, K, J.totFeat, Vinv.p); nl++; }
+    if (J.totFeat > 0) { k_vinv<<<ceil_div(J.totFeat, TB), TB, 0, s>>>(J.d.p, J.dFeatPre.p, K, J.totFeat, eF, xhat, Vinv.p, dvec.p); nl++; }
     if (J.totU > 0) {
         k_s_from_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, J.dPosePre.p, K, J.totU, keys.p, rowPtr.p, S.p); nl++;
     }
@@ -879,14 +686,14 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         static const bool use_v1 = getenv("LSFM_SCHUR_V1") != nullptr;
         if (use_v1) {
             k_schur<<<ceil_div(J.totW, 128), 128, 0, s>>>(J.d.p, J.dWPre.p, J.dFeatPre.p, J.dPosePre.p, K, J.totW,
-                                                         Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p); nl++;
-        } else if (getenv("LSFM_SCHUR_V2") == nullptr && !pat_v1) {   // (the old pattern path leaves no chunkInfo)
+                                                         Vinv.p, dvec.p, split, keys.p, rowPtr.p, S.p, E.p); nl++;
+        } else {
             // pipelined kernel; instantiation chosen from the measured max #distinct poses per chunk
             auto launch = [&](auto kern, size_t shb, int threads) {
                 if (shb > 48 * 1024)
                     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
                 kern<<<nChunks, threads, shb, s>>>(J.d.p, dChunks.p, chunkInfo.p, blkInfo.p, pat_cmax_used, J.dWPre.p,
-                                                  J.dFeatPre.p, J.dPosePre.p, Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p);
+                                                  J.dFeatPre.p, J.dPosePre.p, Vinv.p, dvec.p, split, keys.p, rowPtr.p, S.p, E.p);
             };
             static const bool force_ovf2 = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
             if (maxNposes <= 8 || force_ovf2)
@@ -896,20 +703,6 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             else
                 launch(schur_pipe::k_schur_pipe<31, 248, 32, 512, 1>, schur_pipe::Layout<31, 248, 32>::bytes(), 512);
             nl++;
-        } else {
-            DevBuf<int> err_dbg(4, s);
-            err_dbg.zero();
-            size_t shb = sizeof(double) * (2 * SCH_NB * SCH_CMAX * SCH_LD + SCH_NB * 4) +
-                         sizeof(int) * (SCH_NB + SCH_CMAX + 4 + 2 * (size_t)maxWords) + 16;
-            if (shb > 48 * 1024)
-                CUDA_CHECK(cudaFuncSetAttribute(k_schur_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
-            k_schur_tiled<<<(int)chunks.size(), SCH_THREADS, shb, s>>>(J.d.p, dChunks.p, J.dFeatPre.p, J.dPosePre.p,
-                                                                       Vinv.p, eF, keys.p, rowPtr.p, S.p, E.p,
-                                                                       getenv("LSFM_DEBUG") ? err_dbg.p : nullptr); nl++;
-            if (getenv("LSFM_DEBUG")) {
-                std::vector<int> h = err_dbg.to_host();
-                fprintf(stderr, "[schur] K=%d chunks=%d slow=%d max distinct poses=%d\n", K, h[0], h[1], h[2]);
-            }
         }
     }
     KERNEL_CHECK();
