@@ -419,15 +419,21 @@ __global__ void k_front_rhs(const int *__restrict__ poseSn, const int *__restric
 
 // one CTA per front of the level: extend-add the children, factor the leading ncols block columns,
 // leave the Schur complement (+ updated rhs row) in place for the parent.
+// The factorisation is blocked: a panel of up to `pcMax` columns (all rows below, rhs row included)
+// is staged in shared memory, factored there (6x6 diagonal blocks by one warp, row solves and the
+// in-panel updates by the whole CTA), applied ONCE to everything right of it in global memory
+// (left-looking rank-pc update, panel read from shared memory) and written back.
 __global__ void __launch_bounds__(256)
 k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
                const int *__restrict__ childIdx, const int *__restrict__ relIdx,
-               double *__restrict__ fronts, int *__restrict__ errflag)
+               double *__restrict__ fronts, int *__restrict__ errflag, int pcMax)
 {
+    extern __shared__ double P[];                 // [pc][ldp] column-major panel
     const SnodeDesc d = sn[levelSn[blockIdx.x]];
     double *F = fronts + d.frontOff;
     const int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1, nc = 6 * d.ncols;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
 
     for (int ci = 0; ci < d.nchild; ci++) {
         const SnodeDesc c = sn[childIdx[d.childOff + ci]];
@@ -445,48 +451,75 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
         __syncthreads();
     }
 
-    for (int c0 = 0; c0 < nc; c0 += 6) {
-        if (tid == 0) {
-            // 6x6 Cholesky of the diagonal block, in place (lower)
-            for (int j = 0; j < 6; j++) {
-                double djj = F[(size_t)(c0 + j) * ld + c0 + j];
-                for (int p = 0; p < j; p++) { double l = F[(size_t)(c0 + p) * ld + c0 + j]; djj -= l * l; }
-                if (!(djj > 0.0)) { atomicOr(errflag, 1); djj = 1.0; }
-                djj = sqrt(djj);
-                F[(size_t)(c0 + j) * ld + c0 + j] = djj;
-                for (int i = j + 1; i < 6; i++) {
-                    double v = F[(size_t)(c0 + j) * ld + c0 + i];
-                    for (int p = 0; p < j; p++)
-                        v -= F[(size_t)(c0 + p) * ld + c0 + i] * F[(size_t)(c0 + p) * ld + c0 + j];
-                    F[(size_t)(c0 + j) * ld + c0 + i] = v / djj;
+    for (int p0 = 0; p0 < nc; p0 += pcMax) {
+        const int pc = min(pcMax, nc - p0);
+        const int rows = fs + 1 - p0;             // front rows p0..fs (rhs row last)
+        const int ldp = rows;
+        for (int t = tid; t < pc * rows; t += nt) {
+            int q = t / rows, rr = t - q * rows;
+            P[q * ldp + rr] = (rr >= q) ? F[(size_t)(p0 + q) * ld + p0 + rr] : 0.0;
+        }
+        __syncthreads();
+        for (int b0 = 0; b0 < pc; b0 += 6) {
+            if (warp == 0) {
+                // 6x6 Cholesky of the diagonal block: lane i owns row i
+                for (int j = 0; j < 6; j++) {
+                    double v = 0.0;
+                    if (lane < 6 && lane >= j) {
+                        v = P[(b0 + j) * ldp + b0 + lane];
+                        for (int q = 0; q < j; q++) v -= P[(b0 + q) * ldp + b0 + lane] * P[(b0 + q) * ldp + b0 + j];
+                    }
+                    double djj = __shfl_sync(0xffffffffu, v, j);
+                    if (!(djj > 0.0)) { if (lane == 0) atomicOr(errflag, 1); djj = 1.0; }
+                    djj = sqrt(djj);
+                    if (lane < 6 && lane >= j) P[(b0 + j) * ldp + b0 + lane] = (lane == j) ? djj : v / djj;
+                    __syncwarp();
                 }
             }
-        }
-        __syncthreads();
-        // panel: rows below the diagonal block (including the rhs row fs)
-        for (int r = c0 + 6 + tid; r <= fs; r += nt) {
-            double x[6];
+            __syncthreads();
+            // rows below the diagonal block
+            for (int rr = b0 + 6 + tid; rr < rows; rr += nt) {
+                double x[6];
 #pragma unroll
-            for (int q = 0; q < 6; q++) {
-                double v = F[(size_t)(c0 + q) * ld + r];
+                for (int q = 0; q < 6; q++) {
+                    double v = P[(b0 + q) * ldp + rr];
 #pragma unroll
-                for (int p = 0; p < q; p++) v -= x[p] * F[(size_t)(c0 + p) * ld + c0 + q];
-                x[q] = v / F[(size_t)(c0 + q) * ld + c0 + q];
+                    for (int p = 0; p < q; p++) v -= x[p] * P[(b0 + p) * ldp + b0 + q];
+                    x[q] = v / P[(b0 + q) * ldp + b0 + q];
+                }
+#pragma unroll
+                for (int q = 0; q < 6; q++) P[(b0 + q) * ldp + rr] = x[q];
             }
+            __syncthreads();
+            // remaining panel columns
+            const int rem = pc - b0 - 6;
+            if (rem > 0) {
+                for (int c = b0 + 6 + warp; c < pc; c += nw) {
+                    double lc[6];
 #pragma unroll
-            for (int q = 0; q < 6; q++) F[(size_t)(c0 + q) * ld + r] = x[q];
+                    for (int q = 0; q < 6; q++) lc[q] = P[(b0 + q) * ldp + c];
+                    for (int rr = c + lane; rr < rows; rr += 32) {
+                        double v = P[c * ldp + rr];
+#pragma unroll
+                        for (int q = 0; q < 6; q++) v -= P[(b0 + q) * ldp + rr] * lc[q];
+                        P[c * ldp + rr] = v;
+                    }
+                }
+                __syncthreads();
+            }
         }
-        __syncthreads();
-        // trailing update (lower triangle + rhs row)
-        const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-        for (int c = c0 + 6 + warp; c < fs; c += nw) {
-            double lc[6];
-#pragma unroll
-            for (int q = 0; q < 6; q++) lc[q] = F[(size_t)(c0 + q) * ld + c];
+        // write the factored panel back
+        for (int t = tid; t < pc * rows; t += nt) {
+            int q = t / rows, rr = t - q * rows;
+            if (rr >= q) F[(size_t)(p0 + q) * ld + p0 + rr] = P[q * ldp + rr];
+        }
+        // rank-pc update of everything right of the panel (lower triangle + rhs row)
+        for (int c = p0 + pc + warp; c < fs; c += nw) {
+            const int cc = c - p0;
             for (int r = c + lane; r <= fs; r += 32) {
+                const int rr = r - p0;
                 double v = F[(size_t)c * ld + r];
-#pragma unroll
-                for (int q = 0; q < 6; q++) v -= F[(size_t)(c0 + q) * ld + r] * lc[q];
+                for (int q = 0; q < pc; q++) v -= P[q * ldp + rr] * P[q * ldp + cc];
                 F[(size_t)c * ld + r] = v;
             }
         }
@@ -494,7 +527,10 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
     }
 }
 
-// top-down: x_J = L11^-T (y_J - L21^T x_struct); xperm holds the solution in elimination order
+// top-down: x_J = L11^-T (y_J - L21^T x_struct); xperm holds the solution in elimination order.
+// L11 is solved in column blocks of <= BS_PC staged in shared memory (the per-column chain of a
+// triangular solve is latency-bound: shared memory instead of L2 for every step).
+constexpr int BS_PC = 48;
 __global__ void __launch_bounds__(128)
 k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
                   const int *__restrict__ structIdx, const double *__restrict__ fronts,
@@ -506,6 +542,7 @@ k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__
     extern __shared__ double sh[];
     double *xs = sh;            // us entries: solution at the struct rows
     double *t = sh + us;        // nc entries
+    double *T = t + nc;         // [BS_PC][BS_PC] triangle of the current column block (column-major)
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     double *xj = xperm + 6 * (size_t)d.poseOff;
     for (int i = tid; i < us; i += nt) xs[i] = xj[6 * structIdx[d.structOff + i / 6] + (i % 6)];
@@ -517,16 +554,32 @@ k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__
         if (lane == 0) t[c] = F[(size_t)c * ld + fs] - acc;
     }
     __syncthreads();
-    if (warp == 0) {
-        for (int c = nc - 1; c >= 0; c--) {
-            double acc = 0.0;
-            for (int r = c + 1 + lane; r < nc; r += 32) acc += F[(size_t)c * ld + r] * t[r];
-            acc = sm::warp_sum(acc);
-            if (lane == 0) t[c] = (t[c] - acc) / F[(size_t)c * ld + c];
-            __syncwarp();
+    for (int c1 = nc; c1 > 0; c1 -= BS_PC) {
+        const int c0 = max(0, c1 - BS_PC), pb = c1 - c0;
+        // contributions of the already solved columns [c1, nc)
+        if (c1 < nc)
+            for (int c = c0 + warp; c < c1; c += nw) {
+                double acc = 0.0;
+                for (int r = c1 + lane; r < nc; r += 32) acc += F[(size_t)c * ld + r] * t[r];
+                acc = sm::warp_sum(acc);
+                if (lane == 0) t[c] -= acc;
+            }
+        for (int e = tid; e < pb * pb; e += nt) {
+            int c = e / pb, r = e - c * pb;
+            T[c * BS_PC + r] = (r >= c) ? F[(size_t)(c0 + c) * ld + c0 + r] : 0.0;
         }
+        __syncthreads();
+        if (warp == 0) {
+            for (int c = pb - 1; c >= 0; c--) {
+                double acc = 0.0;
+                for (int r = c + 1 + lane; r < pb; r += 32) acc += T[c * BS_PC + r] * t[c0 + r];
+                acc = sm::warp_sum(acc);
+                if (lane == 0) t[c0 + c] = (t[c0 + c] - acc) / T[c * BS_PC + c];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int c = tid; c < nc; c += nt) xj[6 * (size_t)d.first + c] = t[c];
 }
 
@@ -754,12 +807,19 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     if (nuis > 0) { k_front_assemble<<<ceil_div(36ll * nuis, TB), TB, 0, s>>>(dSlot.p, nuis, dSn.p, S.p, fronts.p); nl++; }
     k_front_rhs<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(dPoseSn.p, dPoseLcol.p, J.totPose, dSn.p, E.p, fronts.p); nl++;
     int nLevels = (int)sym.levelPtr.size() - 1;
+    // panel width: 48 columns (8 pose blocks) unless the tallest front of the batch needs a narrower one
+    const size_t frows = 6 * (size_t)sym.maxFdim + 2;
+    int pcMax = (int)std::min<size_t>(48, ((size_t)200 * 1024 / (8 * frows)) / 6 * 6);
+    if (pcMax < 6) throw LsfmError(LSFM_ERR_ARG, "front too tall for the shared-memory panel");
+    const size_t shf = sizeof(double) * (size_t)pcMax * frows;
+    if (shf > 48 * 1024)
+        CUDA_CHECK(cudaFuncSetAttribute(k_front_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shf));
     for (int l = 0; l < nLevels; l++) {
         int cnt = sym.levelPtr[l + 1] - sym.levelPtr[l];
         if (cnt == 0) continue;
-        k_front_factor<<<cnt, 256, 0, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p); nl++;
+        k_front_factor<<<cnt, 256, shf, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p, pcMax); nl++;
     }
-    size_t shb = sizeof(double) * 6 * (size_t)(sym.maxFdim + 1);
+    size_t shb = sizeof(double) * (6 * (size_t)(sym.maxFdim + 1) + BS_PC * BS_PC);
     if (shb > 48 * 1024)
         CUDA_CHECK(cudaFuncSetAttribute(k_front_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
     for (int l = nLevels - 1; l >= 0; l--) {
