@@ -429,6 +429,7 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
                double *__restrict__ fronts, int *__restrict__ errflag, int pcMax)
 {
     extern __shared__ double P[];                 // [pc][ldp] column-major panel
+    __shared__ double Li[36];                     // inverse of the current diagonal block's factor
     const SnodeDesc d = sn[levelSn[blockIdx.x]];
     double *F = fronts + d.frontOff;
     const int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1, nc = 6 * d.ncols;
@@ -461,31 +462,63 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
         }
         __syncthreads();
         for (int b0 = 0; b0 < pc; b0 += 6) {
-            if (warp == 0) {
-                // 6x6 Cholesky of the diagonal block: lane i owns row i
+            if (tid == 0) {
+                // 6x6 Cholesky of the diagonal block and the inverse of its factor, in registers
+                double a[6][6], li[6][6];
+#pragma unroll
+                for (int j = 0; j < 6; j++)
+#pragma unroll
+                    for (int i = j; i < 6; i++) a[i][j] = P[(b0 + j) * ldp + b0 + i];
+                bool bad = false;
+#pragma unroll
                 for (int j = 0; j < 6; j++) {
-                    double v = 0.0;
-                    if (lane < 6 && lane >= j) {
-                        v = P[(b0 + j) * ldp + b0 + lane];
-                        for (int q = 0; q < j; q++) v -= P[(b0 + q) * ldp + b0 + lane] * P[(b0 + q) * ldp + b0 + j];
+                    double sdiag = a[j][j];
+#pragma unroll
+                    for (int q = 0; q < j; q++) sdiag = fma(-a[j][q], a[j][q], sdiag);
+                    if (!(sdiag > 0.0)) { bad = true; sdiag = 1.0; }
+                    double djj = sqrt(sdiag);
+                    double inv = 1.0 / djj;
+                    a[j][j] = djj;
+                    li[j][j] = inv;
+#pragma unroll
+                    for (int i = j + 1; i < 6; i++) {
+                        double v = a[i][j];
+#pragma unroll
+                        for (int q = 0; q < j; q++) v = fma(-a[i][q], a[j][q], v);
+                        a[i][j] = v * inv;
                     }
-                    double djj = __shfl_sync(0xffffffffu, v, j);
-                    if (!(djj > 0.0)) { if (lane == 0) atomicOr(errflag, 1); djj = 1.0; }
-                    djj = sqrt(djj);
-                    if (lane < 6 && lane >= j) P[(b0 + j) * ldp + b0 + lane] = (lane == j) ? djj : v / djj;
-                    __syncwarp();
                 }
+                // li = L^-1 (lower): li[i][j] = -li[i][i] * sum_{q=j}^{i-1} L[i][q] li[q][j]
+#pragma unroll
+                for (int j = 0; j < 6; j++)
+#pragma unroll
+                    for (int i = j + 1; i < 6; i++) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int q = j; q < i; q++) v = fma(a[i][q], li[q][j], v);
+                        li[i][j] = -li[i][i] * v;
+                    }
+                if (bad) atomicOr(errflag, 1);
+#pragma unroll
+                for (int j = 0; j < 6; j++)
+#pragma unroll
+                    for (int i = j; i < 6; i++) {
+                        P[(b0 + j) * ldp + b0 + i] = a[i][j];
+                        Li[6 * i + j] = li[i][j];
+                    }
             }
             __syncthreads();
-            // rows below the diagonal block
+            // rows below the diagonal block: X = A L^-T, no dependent chain per row
             for (int rr = b0 + 6 + tid; rr < rows; rr += nt) {
-                double x[6];
+                double av[6], x[6];
+#pragma unroll
+                for (int q = 0; q < 6; q++) av[q] = P[(b0 + q) * ldp + rr];
 #pragma unroll
                 for (int q = 0; q < 6; q++) {
-                    double v = P[(b0 + q) * ldp + rr];
+                    double v = 0.0;
 #pragma unroll
-                    for (int p = 0; p < q; p++) v -= x[p] * P[(b0 + p) * ldp + b0 + q];
-                    x[q] = v / P[(b0 + q) * ldp + b0 + q];
+                    for (int p = 0; p <= q; p++) v = fma(av[p], Li[6 * q + p], v);
+                    x[q] = v;
                 }
 #pragma unroll
                 for (int q = 0; q < 6; q++) P[(b0 + q) * ldp + rr] = x[q];
@@ -518,9 +551,12 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
             const int cc = c - p0;
             for (int r = c + lane; r <= fs; r += 32) {
                 const int rr = r - p0;
-                double v = F[(size_t)c * ld + r];
-                for (int q = 0; q < pc; q++) v -= P[q * ldp + rr] * P[q * ldp + cc];
-                F[(size_t)c * ld + r] = v;
+                double v0 = F[(size_t)c * ld + r], v1 = 0.0;
+                for (int q = 0; q < pc; q += 2) {
+                    v0 = fma(-P[q * ldp + rr], P[q * ldp + cc], v0);
+                    v1 = fma(-P[(q + 1) * ldp + rr], P[(q + 1) * ldp + cc], v1);
+                }
+                F[(size_t)c * ld + r] = v0 + v1;
             }
         }
         __syncthreads();
@@ -531,6 +567,7 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
 // L11 is solved in column blocks of <= BS_PC staged in shared memory (the per-column chain of a
 // triangular solve is latency-bound: shared memory instead of L2 for every step).
 constexpr int BS_PC = 48;
+constexpr int BS_TS = BS_PC + 1;      // padded stride: a lane walks a ROW of the column-major triangle
 __global__ void __launch_bounds__(128)
 k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
                   const int *__restrict__ structIdx, const double *__restrict__ fronts,
@@ -566,16 +603,33 @@ k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__
             }
         for (int e = tid; e < pb * pb; e += nt) {
             int c = e / pb, r = e - c * pb;
-            T[c * BS_PC + r] = (r >= c) ? F[(size_t)(c0 + c) * ld + c0 + r] : 0.0;
+            T[c * BS_TS + r] = (r >= c) ? F[(size_t)(c0 + c) * ld + c0 + r] : 0.0;
         }
         __syncthreads();
         if (warp == 0) {
-            for (int c = pb - 1; c >= 0; c--) {
-                double acc = 0.0;
-                for (int r = c + 1 + lane; r < pb; r += 32) acc += T[c * BS_PC + r] * t[c0 + r];
-                acc = sm::warp_sum(acc);
-                if (lane == 0) t[c0 + c] = (t[c0 + c] - acc) / T[c * BS_PC + c];
-                __syncwarp();
+            // column-oriented back substitution: lane owns columns lane, lane+32; once x_r is known
+            // every lane removes it from its own right-hand sides (no reduction on the chain)
+            double tv[2], idg[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                int c = lane + 32 * u;
+                tv[u] = c < pb ? t[c0 + c] : 0.0;
+                idg[u] = c < pb ? 1.0 / T[c * BS_TS + c] : 0.0;
+            }
+            for (int r = pb - 1; r >= 0; r--) {
+                double mine = (r >= 32) ? tv[1] * idg[1] : tv[0] * idg[0];
+                double xr = __shfl_sync(0xffffffffu, mine, r & 31);
+                if (lane == (r & 31)) { if (r >= 32) tv[1] = xr; else tv[0] = xr; }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    int c = lane + 32 * u;
+                    if (c < r) tv[u] = fma(-T[c * BS_TS + r], xr, tv[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                int c = lane + 32 * u;
+                if (c < pb) t[c0 + c] = tv[u];
             }
         }
         __syncthreads();
@@ -819,7 +873,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         if (cnt == 0) continue;
         k_front_factor<<<cnt, 256, shf, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p, pcMax); nl++;
     }
-    size_t shb = sizeof(double) * (6 * (size_t)(sym.maxFdim + 1) + BS_PC * BS_PC);
+    size_t shb = sizeof(double) * (6 * (size_t)(sym.maxFdim + 1) + BS_PC * BS_TS);
     if (shb > 48 * 1024)
         CUDA_CHECK(cudaFuncSetAttribute(k_front_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
     for (int l = nLevels - 1; l >= 0; l--) {
