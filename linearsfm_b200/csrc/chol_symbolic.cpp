@@ -176,18 +176,18 @@ void analyse_join(int m, const u64 *keys, int nk, JoinSym &J)
 } // namespace
 
 void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &posePre,
-                    const std::vector<u64> &keys, const std::vector<int> &sOff,
+                    const u64 *keys, size_t nkeys, const std::vector<int> &sOff,
                     BatchSymbolic &out, int nthreads)
 {
     std::vector<JoinSym> js(K);
     nthreads = std::max(1, std::min(nthreads, K));
-    long long work = (long long)keys.size();
+    long long work = (long long)nkeys;
     if (work < 20000) nthreads = 1;
     std::vector<std::string> errs(nthreads);
     auto worker = [&](int tid) {
         try {
             for (int k = tid; k < K; k += nthreads)
-                analyse_join(m[k], keys.data() + sOff[k], sOff[k + 1] - sOff[k], js[k]);
+                analyse_join(m[k], keys + sOff[k], sOff[k + 1] - sOff[k], js[k]);
         } catch (const std::exception &e) { errs[tid] = e.what(); }
     };
     if (nthreads == 1) worker(0);
@@ -203,7 +203,7 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
     out.poseSn.assign(totPose, -1);
     out.poseLcol.assign(totPose, 0);
     out.perm.assign(totPose, 0);
-    out.slot.resize(keys.size());
+    out.slot.resize(nkeys);
     std::vector<int> snBase(K + 1, 0);
     for (int k = 0; k < K; k++) snBase[k + 1] = snBase[k] + (int)js[k].structs.size();
     int nsTot = snBase[K];

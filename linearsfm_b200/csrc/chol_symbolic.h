@@ -42,5 +42,5 @@ struct BatchSymbolic {
 // keys: sorted unique (join<<44 | row<<22 | col) with row<=col; sOff[K+1] offsets per join;
 // m[k] poses per join; posePre[K+1].
 void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &posePre,
-                    const std::vector<unsigned long long> &keys, const std::vector<int> &sOff,
+                    const unsigned long long *keys, size_t nkeys, const std::vector<int> &sOff,
                     BatchSymbolic &out, int nthreads);

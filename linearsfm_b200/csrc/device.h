@@ -164,6 +164,22 @@ struct Context {
     bool want_objective = false;
     int num_sms = 148;
 
+    // persistent pinned host scratch for the per-level device->host hand-over (pattern keys, row
+    // pointers): no per-level allocation / page faults, true asynchronous copies
+    struct Pinned {
+        char *p = nullptr;
+        size_t cap = 0;
+        char *need(size_t bytes)
+        {
+            if (bytes > cap) {
+                if (p) cudaFreeHost(p);
+                cap = bytes + bytes / 2 + 65536;
+                CUDA_CHECK(cudaMallocHost((void **)&p, cap));
+            }
+            return p;
+        }
+    } pinDown;
+
     // sticky device-side error flag (bit 0: non-positive pivot in the Cholesky); read by check_errors()
     int *d_err = nullptr;
     int *error_flag()

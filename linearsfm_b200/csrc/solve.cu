@@ -742,10 +742,13 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         }
     }
     {
+        // keys are (join << 44 | row << 22 | col): only 44 + bits(K) bits can be set
+        int endBit = 44;
+        while (endBit < 64 && ((long long)(K - 1) >> (endBit - 44)) != 0) endBit++;
         size_t tb = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, tb, rawKeys.p, sortedKeys.p, nRaw, 0, 64, s);
+        cub::DeviceRadixSort::SortKeys(nullptr, tb, rawKeys.p, sortedKeys.p, nRaw, 0, endBit, s);
         DevBuf<char> tmp(tb, s);
-        cub::DeviceRadixSort::SortKeys(tmp.p, tb, rawKeys.p, sortedKeys.p, nRaw, 0, 64, s); nl += 8;
+        cub::DeviceRadixSort::SortKeys(tmp.p, tb, rawKeys.p, sortedKeys.p, nRaw, 0, endBit, s); nl += (endBit + 7) / 8;
     }
     DevBuf<int> dNuis(1, s);
     {
@@ -759,13 +762,15 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     int nuis = 0;
     DevBuf<int> rowPtr(J.totPose + 1, s);
     k_rowptr<<<ceil_div(J.totPose + 1, TB), TB, 0, s>>>(keys.p, dNuis.p, J.dPosePre.p, K, J.totPose, rowPtr.p); nl++;
-    std::vector<u64> hKeys(nRaw);
-    std::vector<int> hRowPtr(J.totPose + 1);
-    CUDA_CHECK(cudaMemcpyAsync(&nuis, dNuis.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (nRaw) CUDA_CHECK(cudaMemcpyAsync(hKeys.data(), keys.p, sizeof(u64) * nRaw, cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaMemcpyAsync(hRowPtr.data(), rowPtr.p, sizeof(int) * (J.totPose + 1), cudaMemcpyDeviceToHost, s));
+    char *pin = ctx.pinDown.need(sizeof(u64) * ((size_t)nRaw + 1) + sizeof(int) * ((size_t)J.totPose + 2));
+    u64 *hKeys = (u64 *)pin;
+    int *hRowPtr = (int *)(pin + sizeof(u64) * ((size_t)nRaw + 1));
+    int *hNuis = hRowPtr + J.totPose + 1;
+    CUDA_CHECK(cudaMemcpyAsync(hNuis, dNuis.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (nRaw) CUDA_CHECK(cudaMemcpyAsync(hKeys, keys.p, sizeof(u64) * nRaw, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(hRowPtr, rowPtr.p, sizeof(int) * (J.totPose + 1), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
-    hKeys.resize(nuis);
+    nuis = *hNuis;
     KERNEL_CHECK();
     ctx.end(8.0 * nRaw, 0.0, nl);
     nl = 0;
@@ -831,7 +836,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     static const bool dbg_time = getenv("LSFM_DEBUG") != nullptr;
     auto tsym0 = std::chrono::steady_clock::now();
     try {
-        build_symbolic(K, mvec, J.posePre, hKeys, sOff, sym, (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+        build_symbolic(K, mvec, J.posePre, hKeys, (size_t)nuis, sOff, sym, (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
     } catch (const std::exception &e) { throw LsfmError(LSFM_ERR_ARG, std::string("symbolic: ") + e.what()); }
     if (dbg_time) {
         double hms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tsym0).count();
@@ -896,7 +901,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
 
     if (dbg) {
         int m0 = J.h[0].m, n0 = sOff[1];
-        dbg->rowptr.assign(hRowPtr.begin(), hRowPtr.begin() + m0 + 1);
+        dbg->rowptr.assign(hRowPtr, hRowPtr + m0 + 1);
         dbg->colidx.resize(n0);
         for (int i = 0; i < n0; i++) dbg->colidx[i] = (int)(hKeys[i] & ((1ull << 22) - 1));
         dbg->S.resize(36 * (size_t)n0);
