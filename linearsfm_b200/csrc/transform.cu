@@ -866,6 +866,8 @@ k_tf_posefin(DMap *__restrict__ out, const int *__restrict__ posePre, int K, int
     }
 }
 
+#include "transform_chunk.cuh"
+
 } // namespace
 
 void OpMaps::build(const std::vector<DMap> &maps, cudaStream_t s)
@@ -1025,9 +1027,36 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
     }
     if (A.totFeat > 0) {
         static const bool tf_v1 = getenv("LSFM_TF_V1") != nullptr;
+        static const bool tf_v3 = getenv("LSFM_TF_V3") != nullptr;
         if (tf_v1) {
             k_wvcong<<<ceil_div(A.totFeat, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dFeatPre.p, A.dPosePre.p, K,
                                                              A.totFeat, tc.p, pj.p, fScan.p); nl++;
+        } else if (!tf_v3) {
+            // default: one pass over W, CTA per chunk of consecutive features (transform_chunk.cuh)
+            std::vector<tfc::Chunk> chunks;
+            int maxWords = 1;
+            for (int k = 0; k < K; k++) {
+                maxWords = std::max(maxWords, (A.h[k].m + 31) / 32);
+                for (int f0 = 0; f0 < A.h[k].n; f0 += tfc::TC_FCH)
+                    chunks.push_back({k, f0, std::min(A.h[k].n, f0 + tfc::TC_FCH)});
+            }
+            const int nChunks = (int)chunks.size();
+            DevBuf<tfc::Chunk> dChunks(nChunks, s);
+            dChunks.upload(chunks);
+            DevBuf<double> poseAcc(36 * (size_t)A.totPose, s);
+            poseAcc.zero();
+            static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;   // test hook: slow path
+            const int cmaxUse = force_ovf ? 4 : tfc::TC_CMAX;
+            const size_t shb = tfc::Layout::bytes(maxWords);
+            static size_t shb_set = 0;
+            if (shb > shb_set) {
+                CUDA_CHECK(cudaFuncSetAttribute(tfc::k_tf_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
+                shb_set = shb;
+            }
+            tfc::k_tf_chunk<<<nChunks, tfc::TC_THREADS, shb, s>>>(A.d.p, B.d.p, dChunks.p, A.dFeatPre.p, A.dPosePre.p,
+                                                                tc.p, pj.p, fScan.p, poseAcc.p, cmaxUse); nl++;
+            k_tf_posefin<<<ceil_div(A.totPose, 128), 128, 0, s>>>(B.d.p, A.dPosePre.p, K, A.totPose, tc.p, pj.p,
+                                                                 poseAcc.p); nl++;
         } else {
             static const bool tf_v2 = getenv("LSFM_TF_V2") != nullptr;
             DevBuf<double> TfBuf(9 * (size_t)A.totFeat, s);

@@ -1,0 +1,381 @@
+// k_tf_chunk: the W/V part of the frame transform as ONE pass over W (included by transform.cu).
+//
+//   LinearSFMImp.cpp:1300-1915 -- for a map re-expressed in the frame of its pose `pos`:
+//     per feature f : X' = R (X - t), V' = Q^T V Q, new block W'(pos,f) = [-V'; T_f^T V Q] + sum_p wadd_pf,
+//                     U'(pos,pos) += C_f^T V C_f
+//     per block (p,f): a1 = D_p^T W Q  (kept, unless p == pos: folded into W'(pos,f)),
+//                     wadd = C_p^T W Q (p != pos)  or  D_pos^T W Q (p == pos)
+//     per pose p    : SW_p = sum_f W_pf, SWT_p = sum_f W_pf T_f  (k_tf_posefin applies the pose
+//                     Jacobians once per pose: U'(p,pos), U'(pos,pos))
+//
+// One CTA (128 threads) per chunk of TC_FCH consecutive features of one map.  Prologue: local pose
+// table of the chunk (bitmap + popcount prefix), per-feature prep (thread per feature: X', V', d_f,
+// the V part of W'(pos,f) -> shared accumulator, C_f^T V C_f -> CTA sum).  Then the chunk's W blocks
+// are walked in batches of 128, ONE THREAD PER BLOCK with the whole 6x3 block in registers:
+//     A   nine 16-byte loads of the block (-> shared tile); T_f from d_f; W T_f -> shared tile; X = W Q;
+//         a1 -> its output slot directly (nine 16-byte stores); wadd -> shared tile;
+//         the block joins the batch list of its local pose
+//     B   thread per (local pose, element): SW / SWT partial sums in REGISTERS for the whole chunk
+//         (from the W and W T_f tiles);
+//         thread per (feature, element): the feature's wadd rows of this batch -> W'(pos,f)
+// Two barriers per batch; W is read once from HBM and written once.  At the end the pose sums are
+// flushed with one atomic per (local pose, element).
+// Chunks with more than 31 distinct poses take a slow path (thread per block, global atomics).
+#pragma once
+
+namespace tfc {
+
+constexpr int TC_FCH = 128;       // features per chunk
+constexpr int TC_THREADS = 128;
+constexpr int TC_BATCH = 128;     // W blocks per batch (one per thread)
+constexpr int TC_CMAX = 31;       // distinct poses per chunk on the fast path
+constexpr int TC_LD = 19;         // padded tile row (doubles): conflict-free 64-bit shared accesses
+constexpr int TC_ACC = (TC_CMAX * 36 + TC_THREADS - 1) / TC_THREADS;   // pose-sum accumulators per thread
+
+struct Chunk { int k, f0, f1; };
+
+struct Layout {
+    static constexpr int WA = 0;                                           // [BATCH][LD] double: wadd rows
+    static constexpr int WT = WA + TC_BATCH * TC_LD * 8;                   // [BATCH][LD] double: W T_f
+    static constexpr int Wr = WT + TC_BATCH * TC_LD * 8;                   // [BATCH][LD] double: the W blocks themselves
+    static constexpr int dF = Wr + TC_BATCH * TC_LD * 8;                   // [FCH][3] double: X'_f - t'
+    static constexpr int Cst = dF + TC_FCH * 3 * 8;                        // Q, QA, QB, QG (36 doubles)
+    static constexpr int wptr = Cst + 36 * 8;                              // [FCH+4] int
+    static constexpr int optr = wptr + (TC_FCH + 4) * 4;                   // [FCH+4] int
+    static constexpr int pidPos = optr + (TC_FCH + 4) * 4;                 // [FCH] int
+    static constexpr int lcnt = pidPos + TC_FCH * 4;                       // [2][32] int: blocks per local pose in the batch
+    static constexpr int poses = lcnt + 2 * 32 * 4;                        // [32] int
+    static constexpr int misc = poses + 32 * 4;                            // [4] int
+    static constexpr int lst = misc + 16;                                  // [32][BATCH] uchar: the batch's blocks per local pose
+    static constexpr int bitmap = lst + 32 * TC_BATCH;                     // [words] unsigned + [words] int
+    static size_t bytes(int words) { return (size_t)bitmap + 8 * (size_t)words + 16; }
+};
+
+// bottom half of J^T X for the block-triangular pose Jacobian [[a,b],[0,c]]: b^T Xtop + c^T Xbot
+__device__ __forceinline__ void jt_bottom(const double *__restrict__ b, const double *__restrict__ c,
+                                          bool has_b, const double *X, double *out)
+{
+    double cc[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) cc[i] = c[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) s = fma(cc[3 * k + i], X[9 + 3 * k + j], s);
+            out[3 * i + j] = s;
+        }
+    if (has_b) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) cc[i] = b[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double s = out[3 * i + j];
+#pragma unroll
+                for (int k = 0; k < 3; k++) s = fma(cc[3 * k + i], X[3 * k + j], s);
+                out[3 * i + j] = s;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 3)
+k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__restrict__ chunks,
+           const int *__restrict__ featPre, const int *__restrict__ posePre,
+           const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj, const int *__restrict__ fScan,
+           double *__restrict__ poseAcc, int cmaxUse)
+{
+    typedef Layout L;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double *WAt = (double *)(smraw + L::WA);
+    double *WTt = (double *)(smraw + L::WT);
+    double *Wrt = (double *)(smraw + L::Wr);
+    double *dFs = (double *)(smraw + L::dF);
+    double *Cst = (double *)(smraw + L::Cst);
+    int *wptr = (int *)(smraw + L::wptr);
+    int *optr = (int *)(smraw + L::optr);
+    int *pidPos = (int *)(smraw + L::pidPos);
+    int *lcnt = (int *)(smraw + L::lcnt);
+    int *poses = (int *)(smraw + L::poses);
+    int *misc = (int *)(smraw + L::misc);
+    unsigned char *lst = smraw + L::lst;
+    unsigned *bitmap = (unsigned *)(smraw + L::bitmap);
+
+    const Chunk ch = chunks[blockIdx.x];
+    const int k = ch.k;
+    const DMap &M = in[k];
+    const DMap &O = out[k];
+    const TfConst &c = tc[k];
+    const int pid = c.posID;
+    const int words = (M.m + 31) >> 5;
+    int *prefix = (int *)(bitmap + words);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nfeat = ch.f1 - ch.f0;
+    const int gf0 = featPre[k] + ch.f0;
+    const PoseJac *pjk = pj + posePre[k];
+
+    // ---------------- prologue ----------------
+    {
+        const int fbase = fScan[featPre[k]];
+        for (int i = tid; i <= nfeat; i += TC_THREADS) {
+            wptr[i] = M.wPtr[ch.f0 + i];
+            optr[i] = fScan[gf0 + i] - fbase;
+        }
+    }
+    for (int i = tid; i < nfeat; i += TC_THREADS) pidPos[i] = 0x7fffffff;
+    for (int i = tid; i < words; i += TC_THREADS) bitmap[i] = 0u;
+    if (tid < 64) lcnt[tid] = 0;
+    if (tid < 9) {
+        Cst[tid] = c.Q[tid]; Cst[9 + tid] = c.QA[tid]; Cst[18 + tid] = c.QB[tid]; Cst[27 + tid] = c.QG[tid];
+    }
+    __syncthreads();
+    const int w0 = wptr[0], w1 = wptr[nfeat];
+    for (int j = w0 + tid; j < w1; j += TC_THREADS) {
+        int p = M.photo[j];
+        atomicOr(&bitmap[p >> 5], 1u << (p & 31));
+        if (p == pid) {                         // position of the pos block inside its feature
+            int lo = 0, hi = nfeat;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= j) lo = mid; else hi = mid; }
+            pidPos[lo] = j - wptr[lo];
+        }
+    }
+    if (tid < nfeat) O.wPtr[ch.f0 + tid] = optr[tid];
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < words; base += 32) {
+            int cc = (base + lane < words) ? __popc(bitmap[base + lane]) : 0;
+            int incl = cc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (base + lane < words) prefix[base + lane] = run + incl - cc;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) misc[0] = run;
+    }
+    __syncthreads();
+    const int nposes = misc[0];
+    const bool fast = nposes <= cmaxUse;
+    if (fast)
+        for (int i = tid; i < words; i += TC_THREADS) {
+            unsigned b = bitmap[i];
+            int r = prefix[i];
+            while (b) { int bit = __ffs(b) - 1; poses[r++] = i * 32 + bit; b &= b - 1; }
+        }
+    double Q[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Q[i] = Cst[i];
+    // per-feature prep: X', V', d_f, the V part of W'(pos,f) and of U'(pos,pos)
+    {
+        double S21[21];
+#pragma unroll
+        for (int i = 0; i < 21; i++) S21[i] = 0.0;
+        if (tid < nfeat) {
+            const int f = ch.f0 + tid;
+            const double *x = M.featVal + 3 * (size_t)f;
+            double d0[3] = {x[0] - c.t[0], x[1] - c.t[1], x[2] - c.t[2]};
+            double xn[3];
+            geom::mat3_vec(c.R, d0, xn);
+            double *y = O.featVal + 3 * (size_t)f;
+            y[0] = xn[0]; y[1] = xn[1]; y[2] = xn[2];
+            O.featNo[f] = M.featNo[f];
+            double d[3] = {xn[0] - c.tn[0], xn[1] - c.tn[1], xn[2] - c.tn[2]};
+            dFs[3 * tid] = d[0]; dFs[3 * tid + 1] = d[1]; dFs[3 * tid + 2] = d[2];
+            double Tf[9], v[3];
+            geom::mat3_vec(Cst + 9, d, v);  Tf[0] = v[0]; Tf[3] = v[1]; Tf[6] = v[2];
+            geom::mat3_vec(Cst + 18, d, v); Tf[1] = v[0]; Tf[4] = v[1]; Tf[7] = v[2];
+            geom::mat3_vec(Cst + 27, d, v); Tf[2] = v[0]; Tf[5] = v[1]; Tf[8] = v[2];
+            double V[9], VQ[9], VT[9], Vn[9], M1[9], M2[9];
+            sm::load<9>(M.V + 9 * (size_t)f, V);
+            sm::mm<3, 3, 3>(V, Q, VQ);
+            sm::mm<3, 3, 3>(V, Tf, VT);
+            sm::mtm<3, 3, 3>(Q, VQ, Vn);
+            sm::mtm<3, 3, 3>(Tf, VQ, M1);
+            sm::mtm<3, 3, 3>(Tf, VT, M2);
+            sm::store<9>(O.V + 9 * (size_t)f, Vn);
+            const int o0 = optr[tid];
+            O.photo[o0] = pid;
+            O.feature[o0] = f;
+            // the (posID,f) block starts as C_f^T V D_f = [-V'; M1]; the batches add the W terms
+            // (read-modify-write by threads of this CTA only, ordered by the CTA barriers)
+            double *wp = O.W + 18 * (size_t)o0;
+#pragma unroll
+            for (int i = 0; i < 9; i++) { wp[i] = -Vn[i]; wp[9 + i] = M1[i]; }
+            // upper triangle of C_f^T V C_f = [[V', -M1^T],[-M1, M2]]
+            int q = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int cc = r; cc < 6; cc++) {
+                    double s;
+                    if (r < 3 && cc < 3) s = Vn[3 * r + cc];
+                    else if (r < 3) s = -M1[3 * (cc - 3) + r];
+                    else s = M2[3 * (r - 3) + (cc - 3)];
+                    S21[q++] = s;
+                }
+        }
+        // CTA sum of the 21 values (scratch: the WA/WT tiles, 21 x 128 doubles)
+        double *scr = WAt;
+#pragma unroll
+        for (int i = 0; i < 21; i++) scr[i * TC_FCH + tid] = S21[i];
+        __syncthreads();
+        {
+            const int i = tid >> 2, part = tid & 3;           // 32 groups of 4 lanes, 21 in use
+            double s = 0.0;
+            if (i < 21)
+                for (int t = 0; t < 32; t++) s += scr[i * TC_FCH + part * 32 + t];
+            s += __shfl_down_sync(0xffffffffu, s, 2, 4);
+            s += __shfl_down_sync(0xffffffffu, s, 1, 4);
+            if (part == 0 && i < 21) {
+                int r = 0, rem = i;
+                while (rem >= 6 - r) { rem -= 6 - r; r++; }
+                int cc = r + rem;
+                double *u = O.U + 36 * (size_t)pid;
+                atomicAdd(u + 6 * r + cc, s);
+                if (cc != r) atomicAdd(u + 6 * cc + r, s);
+            }
+        }
+        __syncthreads();
+    }
+
+    double acc[TC_ACC];
+#pragma unroll
+    for (int u = 0; u < TC_ACC; u++) acc[u] = 0.0;
+    const int nitems = fast ? nposes * 36 : 0;
+    const double *Wg = M.W;
+
+    // ---------------- batches: one thread per W block ----------------
+    int bt = 0;
+    for (int jb = w0; jb < w1; jb += TC_BATCH, bt++) {
+        const int j = jb + tid;
+        int *lc = lcnt + (bt & 1) * 32;
+        if (j < w1) {
+            const int p = M.photo[j];
+            int fb;
+            {
+                int lo = 0, hi = nfeat;             // feature fb with wptr[fb] <= j < wptr[fb+1]
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= j) lo = mid; else hi = mid; }
+                fb = lo;
+            }
+            const bool isPos = (p == pid);
+            double W[18];
+            {
+                const double2 *src = reinterpret_cast<const double2 *>(Wg + 18 * (size_t)j);
+#pragma unroll
+                for (int i = 0; i < 9; i++) { double2 v = src[i]; W[2 * i] = v.x; W[2 * i + 1] = v.y; }
+            }
+            const PoseJac &J = pjk[p];
+            {
+                // T_f = [QA d | QB d | QG d];  W T_f -> tile (or straight to the pose sums on the slow path)
+                const double d0 = dFs[3 * fb], d1 = dFs[3 * fb + 1], d2 = dFs[3 * fb + 2];
+                double Tf[9];
+#pragma unroll
+                for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+                        Tf[3 * r + cc] = fma(Cst[9 + 9 * cc + 3 * r + 2], d2,
+                                             fma(Cst[9 + 9 * cc + 3 * r + 1], d1, Cst[9 + 9 * cc + 3 * r] * d0));
+                double WT[18];
+                sm::mm<6, 3, 3>(W, Tf, WT);
+                if (fast) {
+#pragma unroll
+                    for (int i = 0; i < 18; i++) { WTt[tid * TC_LD + i] = WT[i]; Wrt[tid * TC_LD + i] = W[i]; }
+                } else {
+                    double *pa = poseAcc + 36 * (size_t)(posePre[k] + p);
+#pragma unroll
+                    for (int i = 0; i < 18; i++) { atomicAdd(pa + i, W[i]); atomicAdd(pa + 18 + i, WT[i]); }
+                }
+            }
+            double X[18];
+            sm::mm<6, 3, 3>(W, Q, X);                                   // W Q
+            double P[9], B1[9];
+            sm::mtm<3, 3, 3>(Q, X, P);                                  // Q^T Xtop
+            if (!isPos) {
+                jt_bottom(J.b1, J.c1, false, X, B1);                    // a1 = D_p^T W Q = [P; c1^T Xbot]
+                const int jrel = j - wptr[fb];
+                const int o = optr[fb] + 1 + jrel - ((pidPos[fb] < jrel) ? 1 : 0);
+                double2 *dst = reinterpret_cast<double2 *>(O.W + 18 * (size_t)o);
+                dst[0] = make_double2(P[0], P[1]); dst[1] = make_double2(P[2], P[3]);
+                dst[2] = make_double2(P[4], P[5]); dst[3] = make_double2(P[6], P[7]);
+                dst[4] = make_double2(P[8], B1[0]); dst[5] = make_double2(B1[1], B1[2]);
+                dst[6] = make_double2(B1[3], B1[4]); dst[7] = make_double2(B1[5], B1[6]);
+                dst[8] = make_double2(B1[7], B1[8]);
+                O.photo[o] = p;
+                O.feature[o] = ch.f0 + fb;
+            }
+            // wadd = [-P; Bm^T Xtop + Cm^T Xbot]: C_p^T W Q, or D_pos^T W Q for the pos block
+            jt_bottom(isPos ? J.b1 : J.f2, isPos ? J.c1 : J.g2, true, X, B1);
+#pragma unroll
+            for (int i = 0; i < 9; i++) { WAt[tid * TC_LD + i] = -P[i]; WAt[tid * TC_LD + 9 + i] = B1[i]; }
+            if (fast) {
+                const int slot = prefix[p >> 5] + __popc(bitmap[p >> 5] & ((1u << (p & 31)) - 1u));
+                lst[slot * TC_BATCH + atomicAdd(&lc[slot], 1)] = (unsigned char)tid;
+            }
+        }
+        __syncthreads();
+        if (tid < 32) lcnt[((bt & 1) ^ 1) * 32 + tid] = 0;          // the next batch's counters
+        // pose sums (thread owns (local pose, element) pairs for the whole chunk)
+#pragma unroll
+        for (int u = 0; u < TC_ACC; u++) {
+            const int it = tid + u * TC_THREADS;
+            if (it < nitems) {
+                const int slot = it / 36, el = it - 36 * slot;
+                const unsigned *ls4 = reinterpret_cast<const unsigned *>(lst + slot * TC_BATCH);
+                const int nl = lc[slot];
+                const double *src = (el < 18) ? (Wrt + el) : (WTt + (el - 18));
+                double s0 = acc[u], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int i = 0;
+                for (; i + 4 <= nl; i += 4) {             // four independent shared loads in flight
+                    const unsigned b4 = ls4[i >> 2];
+                    s0 += src[TC_LD * (int)(b4 & 255u)];
+                    s1 += src[TC_LD * (int)((b4 >> 8) & 255u)];
+                    s2 += src[TC_LD * (int)((b4 >> 16) & 255u)];
+                    s3 += src[TC_LD * (int)(b4 >> 24)];
+                }
+                if (i < nl) {
+                    const unsigned b4 = ls4[i >> 2];
+                    s0 += src[TC_LD * (int)(b4 & 255u)];
+                    if (i + 1 < nl) s1 += src[TC_LD * (int)((b4 >> 8) & 255u)];
+                    if (i + 2 < nl) s2 += src[TC_LD * (int)((b4 >> 16) & 255u)];
+                }
+                const double s = (s0 + s1) + (s2 + s3);
+                acc[u] = s;
+            }
+        }
+        // W'(pos,f) += the feature's wadd rows of this batch
+        {
+            const int jl = min(jb + TC_BATCH, w1) - 1;
+            int lo = 0, hi = nfeat;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= jb) lo = mid; else hi = mid; }
+            const int fLo = lo;
+            lo = fLo; hi = nfeat;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= jl) lo = mid; else hi = mid; }
+            const int nfb = lo - fLo + 1;
+            for (int e = tid; e < nfb * 18; e += TC_THREADS) {
+                const int fl = e / 18, el = e - 18 * fl;
+                const int fx = fLo + fl;
+                const int j0 = max(wptr[fx], jb) - jb, j1 = min(wptr[fx + 1], jl + 1) - jb;
+                double s = 0.0;
+                for (int b = j0; b < j1; b++) s += WAt[b * TC_LD + el];
+                O.W[18 * (size_t)optr[fx] + el] += s;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < TC_ACC; u++) {
+        const int it = tid + u * TC_THREADS;
+        if (it < nitems) {
+            const int slot = it / 36, el = it - 36 * slot;
+            atomicAdd(poseAcc + 36 * (size_t)(posePre[k] + poses[slot]) + el, acc[u]);
+        }
+    }
+}
+
+} // namespace tfc

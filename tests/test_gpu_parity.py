@@ -74,6 +74,18 @@ def test_tree_88(gpu, oracle):
     assert state_rel_err(got, ref) <= 1e-6
 
 
+@pytest.mark.parametrize("env", [{"LSFM_FORCE_OVERFLOW": "1"}, {"LSFM_TF_V3": "1"}])
+def test_tree_slow_paths(gpu, oracle, env):
+    # chunks that see "too many" distinct poses (forced: > 4) take the thread-per-block paths of the
+    # Transform / pattern / Schur kernels; LSFM_TF_V3 selects the previous multi-kernel Transform.
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_tree.py"), "37", "30"],
+                       env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_solve_operator_and_pattern(gpu, oracle, scene16):
     # the narrowest pure-array operator (LinearSFMImp.h:209) + integer parity of the S pattern
     e = oracle.transform_stereo(scene16[0], scene16[1].Ref)
