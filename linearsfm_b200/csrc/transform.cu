@@ -19,6 +19,7 @@
 #include "small_mat.cuh"
 #include <cub/cub.cuh>
 #include <climits>
+#include <type_traits>
 
 namespace {
 

@@ -29,17 +29,26 @@ constexpr int TC_FCH = 128;       // features per chunk
 constexpr int TC_THREADS = 128;
 constexpr int TC_BATCH = 128;     // W blocks per batch (one per thread)
 constexpr int TC_CMAX = 31;       // distinct poses per chunk on the fast path
-constexpr int TC_LD = 19;         // padded tile row (doubles): conflict-free 64-bit shared accesses
+constexpr int TC_LD = 18;         // dense tile rows: written / read per block as nine 16-byte accesses (conflict-free)
 constexpr int TC_ACC = (TC_CMAX * 36 + TC_THREADS - 1) / TC_THREADS;   // pose-sum accumulators per thread
 
 struct Chunk { int k, f0, f1; };
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 struct Layout {
     static constexpr int WA = 0;                                           // [BATCH][LD] double: wadd rows
     static constexpr int WT = WA + TC_BATCH * TC_LD * 8;                   // [BATCH][LD] double: W T_f
     static constexpr int Wr = WT + TC_BATCH * TC_LD * 8;                   // [BATCH][LD] double: the W blocks themselves
     static constexpr int dF = Wr + TC_BATCH * TC_LD * 8;                   // [FCH][3] double: X'_f - t'
-    static constexpr int Cst = dF + TC_FCH * 3 * 8;                        // Q, QA, QB, QG (36 doubles)
+    static constexpr int Jt = dF + TC_FCH * 3 * 8;                         // [CMAX][27] double: c1, Bm, Cm per local pose
+    static constexpr int Cst = Jt + TC_CMAX * 27 * 8;                      // Q, QA, QB, QG (36 doubles)
     static constexpr int wptr = Cst + 36 * 8;                              // [FCH+4] int
     static constexpr int optr = wptr + (TC_FCH + 4) * 4;                   // [FCH+4] int
     static constexpr int pidPos = optr + (TC_FCH + 4) * 4;                 // [FCH] int
@@ -94,6 +103,7 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     double *WTt = (double *)(smraw + L::WT);
     double *Wrt = (double *)(smraw + L::Wr);
     double *dFs = (double *)(smraw + L::dF);
+    double *Jt = (double *)(smraw + L::Jt);
     double *Cst = (double *)(smraw + L::Cst);
     int *wptr = (int *)(smraw + L::wptr);
     int *optr = (int *)(smraw + L::optr);
@@ -225,6 +235,14 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
 #pragma unroll
         for (int i = 0; i < 21; i++) scr[i * TC_FCH + tid] = S21[i];
         __syncthreads();
+        if (fast)                                   // Jacobian blocks of the chunk's poses -> shared
+            for (int i = tid; i < nposes * 27; i += TC_THREADS) {
+                const int slot = i / 27, e = i - 27 * slot;
+                const int p = poses[slot];
+                const PoseJac &J = pjk[p];
+                const bool isPos = (p == pid);
+                Jt[i] = e < 9 ? J.c1[e] : e < 18 ? (isPos ? J.b1[e - 9] : J.f2[e - 9]) : (isPos ? J.c1[e - 18] : J.g2[e - 18]);
+            }
         {
             const int i = tid >> 2, part = tid & 3;           // 32 groups of 4 lanes, 21 in use
             double s = 0.0;
@@ -251,72 +269,109 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     const double *Wg = M.W;
 
     // ---------------- batches: one thread per W block ----------------
+    // phase A for one block; FAST: chunk-local pose slots (lists, Jacobians from shared memory, W
+    // through the warp's private part of the Wr tile), else global Jacobians / atomics
+    auto phase_a = [&](auto fast_tag, const int j, int *lc) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        const int p = M.photo[j];
+        int fb;
+        {
+            int lo = 0, hi = nfeat;             // feature fb with wptr[fb] <= j < wptr[fb+1]
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= j) lo = mid; else hi = mid; }
+            fb = lo;
+        }
+        const bool isPos = (p == pid);
+        int slot = 0;
+        if (FAST) slot = prefix[p >> 5] + __popc(bitmap[p >> 5] & ((1u << (p & 31)) - 1u));
+        double W[18];
+        {
+            const double2 *src = FAST ? reinterpret_cast<const double2 *>(Wrt + 18 * tid)
+                                      : reinterpret_cast<const double2 *>(Wg + 18 * (size_t)j);
+#pragma unroll
+            for (int i = 0; i < 9; i++) { double2 v = src[i]; W[2 * i] = v.x; W[2 * i + 1] = v.y; }
+        }
+        {
+            // T_f = [QA d | QB d | QG d];  W T_f -> tile (or straight to the pose sums on the slow path)
+            const double d0 = dFs[3 * fb], d1 = dFs[3 * fb + 1], d2 = dFs[3 * fb + 2];
+            double Tf[9];
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    Tf[3 * r + cc] = fma(Cst[9 + 9 * cc + 3 * r + 2], d2,
+                                         fma(Cst[9 + 9 * cc + 3 * r + 1], d1, Cst[9 + 9 * cc + 3 * r] * d0));
+            double WT[18];
+            sm::mm<6, 3, 3>(W, Tf, WT);
+            if (FAST) {
+                double2 *row = reinterpret_cast<double2 *>(WTt + 18 * tid);
+#pragma unroll
+                for (int i = 0; i < 9; i++) row[i] = make_double2(WT[2 * i], WT[2 * i + 1]);
+            } else {
+                double *pa = poseAcc + 36 * (size_t)(posePre[k] + p);
+#pragma unroll
+                for (int i = 0; i < 18; i++) { atomicAdd(pa + i, W[i]); atomicAdd(pa + 18 + i, WT[i]); }
+            }
+        }
+        double X[18];
+        sm::mm<6, 3, 3>(W, Q, X);                                   // W Q
+        double P[9], B1[9];
+        sm::mtm<3, 3, 3>(Q, X, P);                                  // Q^T Xtop
+        const PoseJac &J = pjk[p];
+        const double *jc1 = FAST ? Jt + 27 * slot : J.c1;
+        const double *jB = FAST ? Jt + 27 * slot + 9 : (isPos ? J.b1 : J.f2);
+        const double *jC = FAST ? Jt + 27 * slot + 18 : (isPos ? J.c1 : J.g2);
+        if (!isPos) {
+            jt_bottom(jc1, jc1, false, X, B1);                      // a1 = D_p^T W Q = [P; c1^T Xbot]
+            const int jrel = j - wptr[fb];
+            const int o = optr[fb] + 1 + jrel - ((pidPos[fb] < jrel) ? 1 : 0);
+            double2 *dst = reinterpret_cast<double2 *>(O.W + 18 * (size_t)o);
+            dst[0] = make_double2(P[0], P[1]); dst[1] = make_double2(P[2], P[3]);
+            dst[2] = make_double2(P[4], P[5]); dst[3] = make_double2(P[6], P[7]);
+            dst[4] = make_double2(P[8], B1[0]); dst[5] = make_double2(B1[1], B1[2]);
+            dst[6] = make_double2(B1[3], B1[4]); dst[7] = make_double2(B1[5], B1[6]);
+            dst[8] = make_double2(B1[7], B1[8]);
+            O.photo[o] = p;
+            O.feature[o] = ch.f0 + fb;
+        }
+        // wadd = [-P; Bm^T Xtop + Cm^T Xbot]: C_p^T W Q, or D_pos^T W Q for the pos block
+        jt_bottom(jB, jC, true, X, B1);
+        {
+            double2 *row = reinterpret_cast<double2 *>(WAt + 18 * tid);
+            row[0] = make_double2(-P[0], -P[1]); row[1] = make_double2(-P[2], -P[3]);
+            row[2] = make_double2(-P[4], -P[5]); row[3] = make_double2(-P[6], -P[7]);
+            row[4] = make_double2(-P[8], B1[0]); row[5] = make_double2(B1[1], B1[2]);
+            row[6] = make_double2(B1[3], B1[4]); row[7] = make_double2(B1[5], B1[6]);
+            row[8] = make_double2(B1[7], B1[8]);
+        }
+        if (FAST) lst[slot * TC_BATCH + atomicAdd(&lc[slot], 1)] = (unsigned char)tid;
+    };
+
     int bt = 0;
     for (int jb = w0; jb < w1; jb += TC_BATCH, bt++) {
         const int j = jb + tid;
         int *lc = lcnt + (bt & 1) * 32;
-        if (j < w1) {
-            const int p = M.photo[j];
-            int fb;
-            {
-                int lo = 0, hi = nfeat;             // feature fb with wptr[fb] <= j < wptr[fb+1]
-                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= j) lo = mid; else hi = mid; }
-                fb = lo;
+        if (fast) {
+            // the warp's 32 blocks = one contiguous 4.6 KB span: coalesced 16-byte async copies into
+            // the warp's private part of the Wr tile; the next batch is pulled into L2 meanwhile
+            const int jw = jb + 32 * warp;
+            const int nv = min(32, w1 - jw);
+            if (nv > 0) {
+                const double *srcw = Wg + 18 * (size_t)jw;
+                double *dstw = Wrt + 18 * 32 * warp;
+                for (int q = lane; q < nv * 9; q += 32) cp_async16(dstw + 2 * q, srcw + 2 * q);
             }
-            const bool isPos = (p == pid);
-            double W[18];
-            {
-                const double2 *src = reinterpret_cast<const double2 *>(Wg + 18 * (size_t)j);
-#pragma unroll
-                for (int i = 0; i < 9; i++) { double2 v = src[i]; W[2 * i] = v.x; W[2 * i + 1] = v.y; }
+            cp_async_commit();
+            if (j + TC_BATCH < w1) {
+                const char *nx = reinterpret_cast<const char *>(Wg + 18 * (size_t)(j + TC_BATCH));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128));
+                if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(M.photo + j + TC_BATCH));
             }
-            const PoseJac &J = pjk[p];
-            {
-                // T_f = [QA d | QB d | QG d];  W T_f -> tile (or straight to the pose sums on the slow path)
-                const double d0 = dFs[3 * fb], d1 = dFs[3 * fb + 1], d2 = dFs[3 * fb + 2];
-                double Tf[9];
-#pragma unroll
-                for (int cc = 0; cc < 3; cc++)
-#pragma unroll
-                    for (int r = 0; r < 3; r++)
-                        Tf[3 * r + cc] = fma(Cst[9 + 9 * cc + 3 * r + 2], d2,
-                                             fma(Cst[9 + 9 * cc + 3 * r + 1], d1, Cst[9 + 9 * cc + 3 * r] * d0));
-                double WT[18];
-                sm::mm<6, 3, 3>(W, Tf, WT);
-                if (fast) {
-#pragma unroll
-                    for (int i = 0; i < 18; i++) { WTt[tid * TC_LD + i] = WT[i]; Wrt[tid * TC_LD + i] = W[i]; }
-                } else {
-                    double *pa = poseAcc + 36 * (size_t)(posePre[k] + p);
-#pragma unroll
-                    for (int i = 0; i < 18; i++) { atomicAdd(pa + i, W[i]); atomicAdd(pa + 18 + i, WT[i]); }
-                }
-            }
-            double X[18];
-            sm::mm<6, 3, 3>(W, Q, X);                                   // W Q
-            double P[9], B1[9];
-            sm::mtm<3, 3, 3>(Q, X, P);                                  // Q^T Xtop
-            if (!isPos) {
-                jt_bottom(J.b1, J.c1, false, X, B1);                    // a1 = D_p^T W Q = [P; c1^T Xbot]
-                const int jrel = j - wptr[fb];
-                const int o = optr[fb] + 1 + jrel - ((pidPos[fb] < jrel) ? 1 : 0);
-                double2 *dst = reinterpret_cast<double2 *>(O.W + 18 * (size_t)o);
-                dst[0] = make_double2(P[0], P[1]); dst[1] = make_double2(P[2], P[3]);
-                dst[2] = make_double2(P[4], P[5]); dst[3] = make_double2(P[6], P[7]);
-                dst[4] = make_double2(P[8], B1[0]); dst[5] = make_double2(B1[1], B1[2]);
-                dst[6] = make_double2(B1[3], B1[4]); dst[7] = make_double2(B1[5], B1[6]);
-                dst[8] = make_double2(B1[7], B1[8]);
-                O.photo[o] = p;
-                O.feature[o] = ch.f0 + fb;
-            }
-            // wadd = [-P; Bm^T Xtop + Cm^T Xbot]: C_p^T W Q, or D_pos^T W Q for the pos block
-            jt_bottom(isPos ? J.b1 : J.f2, isPos ? J.c1 : J.g2, true, X, B1);
-#pragma unroll
-            for (int i = 0; i < 9; i++) { WAt[tid * TC_LD + i] = -P[i]; WAt[tid * TC_LD + 9 + i] = B1[i]; }
-            if (fast) {
-                const int slot = prefix[p >> 5] + __popc(bitmap[p >> 5] & ((1u << (p & 31)) - 1u));
-                lst[slot * TC_BATCH + atomicAdd(&lc[slot], 1)] = (unsigned char)tid;
-            }
+            cp_async_wait_all();
+            __syncwarp();
+            if (j < w1) phase_a(std::true_type(), j, lc);
+        } else if (j < w1) {
+            phase_a(std::false_type(), j, lc);
         }
         __syncthreads();
         if (tid < 32) lcnt[((bt & 1) ^ 1) * 32 + tid] = 0;          // the next batch's counters
