@@ -259,12 +259,37 @@ def main():
                       "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
                       "GFps": round(v["flops"] / max(v["ms"], 1e-9) / 1e6, 2)} for k, v in st.items()}
         peak, how = load_peaks()
-        top = max(st.items(), key=lambda kv: kv[1]["ms"])
+        # stages that are ONE kernel launched once per tree level (CUDA events on the library's
+        # stream around that launch): the roofline object is the one with the most time
+        single = {"transform.wv": "tfc::k_tf_chunk", "solve.schur": "schur_pipe::k_schur_pipe",
+                  "join.values": "k_join_w", "solve.backsub": "k_backsub"}
+        cand = {k: v for k, v in st.items() if k in single and v["launches"] > 0}
+        top = max(cand.items(), key=lambda kv: kv[1]["ms"])
         ach = top[1]["bytes"] / max(top[1]["ms"], 1e-9) / 1e6
-        roof = {"kernel": top[0], "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None, "peak_source": how,
+        traffic = None
+        traffic_note = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):     # dram bytes per launch from the committed ncu --set full capture
+            try:
+                tj = json.load(open(tpath)).get(single[top[0]], {})
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_note = {k: tj[k] for k in ("launch", "time_ms", "algorithmic_bytes_that_launch") if k in tj}
+            except Exception:
+                traffic = None
+        # share of the GPU time of a step: the host-only stage (symbolic analysis, overlapped with
+        # the Schur kernel when the stage timers are off) is left out, like in an ncu launch list
+        total_ms = max(sum(v["ms"] for k, v in st.items() if k != "solve.symbolic"), 1e-9)
+        roof = {"kernel": single[top[0]], "stage": top[0], "bound": "hbm", "achieved": round(ach, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic, "traffic_launch": traffic_note,
+                "peak_source": how,
                 "launches": top[1]["launches"], "ms_total": round(top[1]["ms"], 3),
-                "share_of_step": round(top[1]["ms"] / max(sum(v["ms"] for v in st.values()), 1e-9), 3)}
+                "avg_launch_ms": round(top[1]["ms"] / top[1]["launches"], 4),
+                "algorithmic_bytes_per_launch": round(top[1]["bytes"] / top[1]["launches"]),
+                "share_of_step": round(top[1]["ms"] / total_ms, 3),
+                "other_kernels": {single[k]: {"GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
+                                              "frac": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6 / peak, 4),
+                                              "ms_total": round(v["ms"], 3), "share_of_step": round(v["ms"] / total_ms, 3)}
+                                  for k, v in cand.items() if k != top[0]}}
         api.stats_reset(stage_timing=False)
 
     cpu = None

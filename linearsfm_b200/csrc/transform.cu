@@ -1054,8 +1054,22 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
                 CUDA_CHECK(cudaFuncSetAttribute(tfc::k_tf_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
                 shb_set = shb;
             }
+            // stage timer of its own: this one kernel carries the W/V bytes of the transform
+            //   in : W 144 + photo 4 per block; V 72 + X 24 + id 4 + wPtr 4 per feature
+            //   out: W 144 + photo/feature 8 per block; V 72 + X 24 + id 4 + wPtr 4 per feature
+            ctx.end(0.0, 0.0, nl);
+            nl = 0;
+            ctx.begin("transform.wv");
             tfc::k_tf_chunk<<<nChunks, tfc::TC_THREADS, shb, s>>>(A.d.p, B.d.p, dChunks.p, A.dFeatPre.p, A.dPosePre.p,
-                                                                tc.p, pj.p, fScan.p, poseAcc.p, cmaxUse); nl++;
+                                                                tc.p, pj.p, fScan.p, poseAcc.p, cmaxUse);
+            {
+                double wvBytes = 0.0;
+                for (int k = 0; k < K; k++)
+                    wvBytes += 148.0 * A.h[k].nW + 152.0 * out[k].d.nW + 2.0 * 104.0 * A.h[k].n;
+                bytes -= wvBytes;
+                ctx.end(wvBytes, 0.0, 1);
+            }
+            ctx.begin("transform");
             k_tf_posefin<<<ceil_div(A.totPose, 128), 128, 0, s>>>(B.d.p, A.dPosePre.p, K, A.totPose, tc.p, pj.p,
                                                                  poseAcc.p); nl++;
         } else {
