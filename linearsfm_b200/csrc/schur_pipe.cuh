@@ -12,8 +12,8 @@
 //     raw stage   : cp.async (LDGSTS) of the batch's contiguous W blocks / block infos / V^-1 / eF
 //                   into a DOUBLE-BUFFERED raw area -- issued one batch ahead, so HBM latency
 //                   overlaps the arithmetic of the previous batch;
-//     re-layout   : one thread per (block, row): raw -> [feature][local pose] padded tiles (stride 19
-//                   doubles: conflict-free 64-bit LDS), computing the row of W V^-1 on the way;
+//     re-layout   : one thread per (block, row): the row of W V^-1 -> a dense tile (W itself stays in
+//                   the raw buffer; both operands are read with 16-byte shared loads);
 //     pair update : thread (i,j) adds W V^-1|_i * W^T|_j for every feature that sees both poses.
 // One flush of 36 FP64 atomics per touched pair and chunk.  Three instantiations trade registers /
 // shared memory for resident CTAs: (CMAX 8, 64 thr) x4-5 per SM for the lower tree levels,
@@ -22,7 +22,7 @@
 
 namespace schur_pipe {
 
-constexpr int LD = 19;
+constexpr int LD = 18;           // dense 144-byte rows: operands are read as nine 16-byte loads
 // lower-triangle entries of a diagonal pair's accumulator block that carry its share of E
 __device__ constexpr int EIDX[6] = {6, 12, 13, 18, 19, 20};
 
@@ -54,8 +54,7 @@ struct Layout {
     static constexpr int rawVi = rawW + 2 * MAXBLK * 18 * 8;         // [2][NBMAX*9+1] double (+1: 16B pad)
     static constexpr int rawEf = rawVi + 2 * (NBMAX * 9 + 1) * 8;    // [2][NBMAX*6] double (d vectors)
     static constexpr int rawPh = rawEf + 2 * (NBMAX * 6) * 8;        // [2][MAXBLK] int (block infos)
-    static constexpr int Wsm = rawPh + 2 * MAXBLK * 4;               // [MAXBLK][LD] double
-    static constexpr int WVsm = Wsm + MAXBLK * LD * 8;               // [MAXBLK][LD] double
+    static constexpr int WVsm = (rawPh + 2 * MAXBLK * 4 + 15) / 16 * 16;   // [MAXBLK][LD] double: W V^-1 (W itself is read from the raw buffer)
     static constexpr int present = WVsm + MAXBLK * LD * 8;           // [2][NBMAX] unsigned (by raw buffer)
     static constexpr int poses = present + 2 * NBMAX * 4;            // [CMAX+1] int
     static constexpr int wptr = poses + (CMAX + 1 + 3) / 4 * 16;     // [SCH_FCHUNK+1] int
@@ -81,7 +80,6 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     double *rawVi = (double *)(smraw + L::rawVi);
     double *rawEf = (double *)(smraw + L::rawEf);
     int *rawPh = (int *)(smraw + L::rawPh);
-    double *Wsm = (double *)(smraw + L::Wsm);
     double *WVsm = (double *)(smraw + L::WVsm);
     unsigned *present = (unsigned *)(smraw + L::present);
     int *poses = (int *)(smraw + L::poses);
@@ -193,9 +191,7 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
             const double *wr = rW + 18 * blk + 3 * r;
             const double *vi = rV + 9 * fb;
             double w0_ = wr[0], w1_ = wr[1], w2_ = wr[2];
-            double *dw = Wsm + blk * LD + 3 * r;
             double *dv = WVsm + blk * LD + 3 * r;
-            dw[0] = w0_; dw[1] = w1_; dw[2] = w2_;
             dv[0] = w0_ * vi[0] + w1_ * vi[1] + w2_ * vi[2];
             dv[1] = w0_ * vi[3] + w1_ * vi[4] + w2_ * vi[5];
             dv[2] = w0_ * vi[6] + w1_ * vi[7] + w2_ * vi[8];
@@ -213,29 +209,41 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
                 unsigned pr = present[buf * NBMAX + fb];
                 if (((pr >> pi[u]) & (pr >> pj[u]) & 1u) == 0u) continue;
                 touched[u] = true;
-                const double *wv = WVsm + (int)blkOf[fb * 32 + pi[u]] * LD;
-                const double *w = Wsm + (int)blkOf[fb * 32 + pj[u]] * LD;
+                const double2 *wv2 = reinterpret_cast<const double2 *>(WVsm + (int)blkOf[fb * 32 + pi[u]] * LD);
+                const double2 *w2 = reinterpret_cast<const double2 *>(rW + (int)blkOf[fb * 32 + pj[u]] * 18);
                 double b[18];
 #pragma unroll
-                for (int q = 0; q < 18; q++) b[q] = w[q];
+                for (int q = 0; q < 9; q++) { double2 v = w2[q]; b[2 * q] = v.x; b[2 * q + 1] = v.y; }
                 if (pi[u] == pj[u]) {
                     const double *ef = rE + 6 * fb + sideOff[u];
                     const double e0 = ef[0], e1 = ef[1], e2 = ef[2];
 #pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        double a0 = wv[3 * r], a1 = wv[3 * r + 1], a2 = wv[3 * r + 2];
+                    for (int rp = 0; rp < 3; rp++) {            // two rows of W V^-1 per three 16-byte loads
+                        const double2 x0 = wv2[3 * rp], x1 = wv2[3 * rp + 1], x2 = wv2[3 * rp + 2];
+                        const double av[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
 #pragma unroll
-                        for (int c = r; c < 6; c++)
-                            acc[u][6 * r + c] = fma(a2, b[3 * c + 2], fma(a1, b[3 * c + 1], fma(a0, b[3 * c], acc[u][6 * r + c])));
-                        acc[u][EIDX[r]] = fma(b[3 * r + 2], e2, fma(b[3 * r + 1], e1, fma(b[3 * r], e0, acc[u][EIDX[r]])));
+                        for (int h = 0; h < 2; h++) {
+                            const int r = 2 * rp + h;
+                            const double a0 = av[3 * h], a1 = av[3 * h + 1], a2 = av[3 * h + 2];
+#pragma unroll
+                            for (int c = r; c < 6; c++)
+                                acc[u][6 * r + c] = fma(a2, b[3 * c + 2], fma(a1, b[3 * c + 1], fma(a0, b[3 * c], acc[u][6 * r + c])));
+                            acc[u][EIDX[r]] = fma(b[3 * r + 2], e2, fma(b[3 * r + 1], e1, fma(b[3 * r], e0, acc[u][EIDX[r]])));
+                        }
                     }
                 } else {
 #pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        double a0 = wv[3 * r], a1 = wv[3 * r + 1], a2 = wv[3 * r + 2];
+                    for (int rp = 0; rp < 3; rp++) {
+                        const double2 x0 = wv2[3 * rp], x1 = wv2[3 * rp + 1], x2 = wv2[3 * rp + 2];
+                        const double av[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
 #pragma unroll
-                        for (int c = 0; c < 6; c++)     // three chained FMAs (not mul/fma/fma + add)
-                            acc[u][6 * r + c] = fma(a2, b[3 * c + 2], fma(a1, b[3 * c + 1], fma(a0, b[3 * c], acc[u][6 * r + c])));
+                        for (int h = 0; h < 2; h++) {
+                            const int r = 2 * rp + h;
+                            const double a0 = av[3 * h], a1 = av[3 * h + 1], a2 = av[3 * h + 2];
+#pragma unroll
+                            for (int c = 0; c < 6; c++)     // three chained FMAs (not mul/fma/fma + add)
+                                acc[u][6 * r + c] = fma(a2, b[3 * c + 2], fma(a1, b[3 * c + 1], fma(a0, b[3 * c], acc[u][6 * r + c])));
+                        }
                     }
                 }
             }
