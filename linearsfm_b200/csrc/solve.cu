@@ -37,9 +37,19 @@ struct FeatChunk { int k, f0, f1; };
 //   [0..30] local pose table (ascending pose index), [31] #distinct poses, [32..47] pair bitmap
 constexpr int CHUNK_INFO_INTS = 48;
 
+// set bit (lo,hi) of join k's upper-triangular pose-pair bitmap (row lo, W words per row); the plain
+// read first keeps the hub pairs (set by every chunk of a map) from turning into atomic traffic
+__device__ __forceinline__ void bm_set(unsigned *__restrict__ bm, int off, int W, int a, int b)
+{
+    int lo = a < b ? a : b, hi = a < b ? b : a;
+    unsigned *w = bm + off + lo * W + (hi >> 5);
+    unsigned bit = 1u << (hi & 31);
+    if ((*(volatile unsigned *)w & bit) == 0u) atomicOr(w, bit);
+}
+
 __global__ void __launch_bounds__(PAT_THREADS)
-k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, int mode,
-            int *__restrict__ cnt, const int *__restrict__ scan, u64 *__restrict__ keys,
+k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
+            unsigned *__restrict__ bm, const int *__restrict__ bmOff,
             int *__restrict__ maxNposes, int pat_cmax, int *__restrict__ chunkInfo,
             int *__restrict__ blkInfo, const int *__restrict__ wPre)
 {
@@ -51,32 +61,13 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, in
     int *prefix = (int *)(bitmap + words);           // [words]
     unsigned *pairBits = (unsigned *)(prefix + words);   // [16]
     int *poses = (int *)(pairBits + 16);             // [PAT_CMAX + 1]
-    int *misc = poses + PAT_CMAX + 1;                // [0] nposes, [1] raw count
-    int *featOff = misc + 2;                         // [PAT_THREADS + 1] (overflow path only)
+    int *misc = poses + PAT_CMAX + 1;                // [0] nposes
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     int *ci = chunkInfo + CHUNK_INFO_INTS * (size_t)blockIdx.x;
-    if (mode == 1 && ci[31] <= pat_cmax) {
-        // pass 1: emit the chunk's distinct pairs from what pass 0 left behind (no second look at W)
-        const int nposes = ci[31];
-        if (tid < PAT_CMAX) poses[tid] = ci[tid];
-        if (tid < 16) pairBits[tid] = (unsigned)ci[32 + tid];
-        __syncthreads();
-        const int o0 = scan[blockIdx.x];
-        const int npairs = nposes * (nposes + 1) / 2;
-        for (int t = tid; t < npairs; t += nt) {
-            if (!((pairBits[t >> 5] >> (t & 31)) & 1u)) continue;
-            int rank = __popc(pairBits[t >> 5] & ((1u << (t & 31)) - 1u));
-            for (int q = 0; q < (t >> 5); q++) rank += __popc(pairBits[q]);
-            int r = t, i = 0;
-            while (r >= nposes - i) { r -= nposes - i; i++; }
-            keys[o0 + rank] = pair_key(ch.k, poses[i], poses[i + r]);
-        }
-        return;
-    }
+    const int boff = bmOff[ch.k];
     const int w0 = M.wPtr[ch.f0], w1 = M.wPtr[ch.f1];
     for (int i = tid; i < words; i += nt) bitmap[i] = 0u;
     if (tid < 16) pairBits[tid] = 0u;
-    if (tid == 0) misc[1] = 0;
     __syncthreads();
     for (int j = w0 + tid; j < w1; j += nt) {
         int p = M.photo[j];
@@ -100,8 +91,8 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, in
     }
     __syncthreads();
     const int nposes = misc[0];
-    if (mode == 0 && tid == 0) { atomicMax(maxNposes, nposes); ci[31] = nposes; }
-    if (nposes <= pat_cmax) {      // mode 0 only (mode 1 took the early exit above)
+    if (tid == 0) { atomicMax(maxNposes, nposes); ci[31] = nposes; }
+    if (nposes <= pat_cmax) {
         int *bi = blkInfo + wPre[ch.k];
         for (int f = ch.f0 + tid; f < ch.f1; f += nt) {
             int a0 = M.wPtr[f], a1 = M.wPtr[f + 1];
@@ -121,66 +112,87 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, in
         for (int i = tid; i < words; i += nt) {
             unsigned b = bitmap[i];
             int r = prefix[i];
-            while (b) { int bit = __ffs(b) - 1; ci[r++] = i * 32 + bit; b &= b - 1; }
+            while (b) { int bit = __ffs(b) - 1; poses[r] = i * 32 + bit; ci[r] = i * 32 + bit; r++; b &= b - 1; }
         }
         __syncthreads();
-        if (tid < 16) ci[32 + tid] = (int)pairBits[tid];
-        if (tid == 0) {
-            int c = 0;
-            for (int q = 0; q < 16; q++) c += __popc(pairBits[q]);
-            cnt[blockIdx.x] = c;
+        // the chunk's distinct pairs -> the join's pose-pair bitmap (exact dedupe across chunks)
+        const int npairs = nposes * (nposes + 1) / 2;
+        for (int t = tid; t < npairs; t += nt) {
+            if (!((pairBits[t >> 5] >> (t & 31)) & 1u)) continue;
+            int r = t, i = 0;
+            while (r >= nposes - i) { r -= nposes - i; i++; }
+            bm_set(bm, boff, words, poses[i], poses[i + r]);
         }
         return;
     }
-    // overflow: too many distinct poses in this chunk -> raw per-feature pairs
-    int myf = ch.f0 + tid;
-    int kf = (myf < ch.f1) ? M.wPtr[myf + 1] - M.wPtr[myf] : 0;
-    int mine = kf * (kf + 1) / 2;
-    if (mode == 0) {
-        atomicAdd(&misc[1], mine);
-        __syncthreads();
-        if (tid == 0) cnt[blockIdx.x] = misc[1];
-        return;
-    }
-    featOff[tid] = mine;
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int q = 0; q < nt; q++) { int c = featOff[q]; featOff[q] = run; run += c; }
-    }
-    __syncthreads();
-    if (myf < ch.f1) {
-        int o = scan[blockIdx.x] + featOff[tid];
-        int a0 = M.wPtr[myf], a1 = M.wPtr[myf + 1];
+    // overflow: too many distinct poses in this chunk -> per-feature pairs straight to the bitmap
+    for (int f = ch.f0 + tid; f < ch.f1; f += nt) {
+        int a0 = M.wPtr[f], a1 = M.wPtr[f + 1];
         for (int a = a0; a < a1; a++)
-            for (int b = a; b < a1; b++) keys[o++] = pair_key(ch.k, M.photo[a], M.photo[b]);
+            for (int b = a; b < a1; b++) bm_set(bm, boff, words, M.photo[a], M.photo[b]);
     }
 }
 
 __global__ void k_pat_u(const DMap *__restrict__ J, const int *__restrict__ uPre, int K, int totU,
-                        u64 *__restrict__ keys)
+                        unsigned *__restrict__ bm, const int *__restrict__ bmOff)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= totU) return;
     int k = seg_find(uPre, K, g);
     int b = g - uPre[k];
-    keys[g] = pair_key(k, J[k].Ui[b], J[k].Uj[b]);
+    bm_set(bm, bmOff[k], (J[k].m + 31) >> 5, J[k].Ui[b], J[k].Uj[b]);
 }
 
-// rowPtr[global pose] = first slot of that block row (keys are sorted by join,row,col)
-__global__ void k_rowptr(const u64 *__restrict__ keys, const int *__restrict__ nPtr,
-                         const int *__restrict__ posePre, int K, int totP, int *__restrict__ rowPtr)
+// one warp per block row (global pose g): number of pattern blocks in the row
+__global__ void k_bm_rowcount(const unsigned *__restrict__ bm, const int *__restrict__ bmOff,
+                              const DMap *__restrict__ J, const int *__restrict__ posePre, int K, int totP,
+                              int *__restrict__ rowCnt)
 {
-    const int n = *nPtr;
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (g > totP) return;
-    if (g == totP) { rowPtr[g] = n; return; }
-    int k = seg_find(posePre, K, g);
-    int p = g - posePre[k];
-    u64 key = ((u64)(unsigned)k << 44) | ((u64)(unsigned)p << 22);
-    int lo = 0, hi = n;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
-    rowPtr[g] = lo;
+    if (g == totP) { if (lane == 0) rowCnt[g] = 0; return; }
+    const int k = seg_find(posePre, K, g);
+    const int r = g - posePre[k];
+    const int W = (J[k].m + 31) >> 5;
+    const unsigned *row = bm + bmOff[k] + (size_t)r * W;
+    int c = 0;
+    for (int w = (r >> 5) + lane; w < W; w += 32) c += __popc(row[w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) rowCnt[g] = c;
+}
+
+// one warp per block row: the row's keys (join << 44 | row << 22 | col) in ascending column order
+// at rowPtr[g]; rows are consecutive, so the key list is sorted by (join, row, col)
+__global__ void k_bm_emit(const unsigned *__restrict__ bm, const int *__restrict__ bmOff,
+                          const DMap *__restrict__ J, const int *__restrict__ posePre, int K, int totP,
+                          const int *__restrict__ rowPtr, u64 *__restrict__ keys, int cap)
+{
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= totP) return;
+    const int k = seg_find(posePre, K, g);
+    const int r = g - posePre[k];
+    const int W = (J[k].m + 31) >> 5;
+    const unsigned *row = bm + bmOff[k] + (size_t)r * W;
+    int base = rowPtr[g];
+    for (int w0 = (r >> 5); w0 < W; w0 += 32) {
+        const int w = w0 + lane;
+        unsigned bits = (w < W) ? row[w] : 0u;
+        int c = __popc(bits), incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int o = base + incl - c;
+        while (bits) {
+            int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (o < cap) keys[o] = pair_key(k, r, w * 32 + bit);
+            o++;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
 }
 
 __device__ __forceinline__ int find_slot(const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
@@ -341,13 +353,14 @@ namespace {
 // zeros afterwards (7010-7026).  Here the rows/columns stay in the block system but are replaced by
 // identity rows with a zero right-hand side -- same solution, block structure intact.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_pat_diag(const int *__restrict__ posePre, int K, int totP, u64 *__restrict__ keys)
+__global__ void k_pat_diag(const DMap *__restrict__ J, const int *__restrict__ posePre, int K, int totP,
+                           unsigned *__restrict__ bm, const int *__restrict__ bmOff)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= totP) return;
     int k = seg_find(posePre, K, g);
     int p = g - posePre[k];
-    keys[g] = pair_key(k, p, p);
+    bm_set(bm, bmOff[k], (J[k].m + 31) >> 5, p, p);
 }
 
 __global__ void k_mono_gauge(const u64 *__restrict__ keys, int nuis, const int *__restrict__ refPose,
@@ -703,76 +716,74 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     const int nChunks = (int)chunks.size();
     DevBuf<FeatChunk> dChunks(nChunks, s);
     dChunks.upload(chunks);
-    int nRaw = 0;
     int maxNposes = 1 << 30;             // max distinct poses of any chunk (measured by k_pat_chunk)
     DevBuf<int> dMaxNp(1, s);
     DevBuf<int> chunkInfo((size_t)CHUNK_INFO_INTS * std::max(nChunks, 1), s), blkInfo((size_t)std::max(J.totW, 1), s);
-    int pat_cmax_used = PAT_CMAX;
-    DevBuf<u64> rawKeys, sortedKeys, keys;
-    {
-        DevBuf<int> pcnt(nChunks + 1, s), pscan(nChunks + 1, s);
-        pcnt.zero();
-        // test hook: LSFM_FORCE_OVERFLOW=1 sends every chunk with > 4 poses down the overflow paths
-        static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
-        const int pat_cmax = force_ovf ? 4 : PAT_CMAX;
-        pat_cmax_used = pat_cmax;
-        size_t shb = sizeof(int) * (2 * (size_t)maxWords + 16 + PAT_CMAX + 1 + 2 + PAT_THREADS + 1);
+    // test hook: LSFM_FORCE_OVERFLOW=1 sends every chunk with > 4 poses down the overflow paths
+    static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
+    const int pat_cmax_used = force_ovf ? 4 : PAT_CMAX;
+    // Pose-pair bitmap per join (upper triangle, (m+31)/32 words per row): every chunk ORs its
+    // distinct pairs in, the U blocks (and the mono gauge diagonal) follow; row popcounts + one scan
+    // give the block-CRS row pointers and the keys come out already sorted -- no key sort, no
+    // intermediate count on the host.
+    std::vector<int> bmOff(K + 1, 0);
+    long long capBlocks = 0;
+    for (int k = 0; k < K; k++) {
+        long long mk = J.h[k].m;
+        long long wordsK = mk * ((mk + 31) / 32);
+        if (bmOff[k] + wordsK > 0x7fffffffLL) throw LsfmError(LSFM_ERR_ARG, "pattern bitmap too large");
+        bmOff[k + 1] = bmOff[k] + (int)wordsK;
+        capBlocks += mk * (mk + 1) / 2;
+    }
+    DevBuf<int> dBmOff(K + 1, s);
+    dBmOff.upload(bmOff);
+    DevBuf<unsigned> bm((size_t)std::max(bmOff[K], 1), s);
+    bm.zero();
+    if (nChunks > 0) {
+        size_t shb = sizeof(int) * (2 * (size_t)maxWords + 16 + PAT_CMAX + 1 + 4);
         if (shb > 48 * 1024)
             CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
-        int nChunkKeys = 0;
-        if (nChunks > 0) {
-            dMaxNp.zero();
-            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 0, pcnt.p, nullptr, nullptr, dMaxNp.p, pat_cmax,
-                                                          chunkInfo.p, blkInfo.p, J.dWPre.p); nl++;
-            exclusive_scan(ctx, pcnt.p, pscan.p, nChunks + 1); nl += 2;
-            CUDA_CHECK(cudaMemcpyAsync(&nChunkKeys, pscan.p + nChunks, sizeof(int), cudaMemcpyDeviceToHost, s));
-            CUDA_CHECK(cudaMemcpyAsync(&maxNposes, dMaxNp.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-            CUDA_CHECK(cudaStreamSynchronize(s));
-        }
-        nRaw = nChunkKeys + J.totU + (gauge ? J.totPose : 0);
-        rawKeys.alloc(nRaw, s); sortedKeys.alloc(nRaw, s); keys.alloc(nRaw, s);
-        if (gauge) {   // mono: the zero pose has no block at all after the join; keep every diagonal
-            k_pat_diag<<<ceil_div(J.totPose, TB), TB, 0, s>>>(J.dPosePre.p, K, J.totPose,
-                                                            rawKeys.p + J.totU + nChunkKeys); nl++;
-        }
-        if (J.totU > 0) { k_pat_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, K, J.totU, rawKeys.p); nl++; }
-        if (nChunks > 0) {
-            k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, 1, nullptr, pscan.p, rawKeys.p + J.totU, nullptr, pat_cmax,
-                                                          chunkInfo.p, blkInfo.p, J.dWPre.p); nl++;
-        }
+        dMaxNp.zero();
+        k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, bm.p, dBmOff.p, dMaxNp.p, pat_cmax_used,
+                                                      chunkInfo.p, blkInfo.p, J.dWPre.p); nl++;
     }
-    {
-        // keys are (join << 44 | row << 22 | col): only 44 + bits(K) bits can be set
-        int endBit = 44;
-        while (endBit < 64 && ((long long)(K - 1) >> (endBit - 44)) != 0) endBit++;
-        size_t tb = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, tb, rawKeys.p, sortedKeys.p, nRaw, 0, endBit, s);
-        DevBuf<char> tmp(tb, s);
-        cub::DeviceRadixSort::SortKeys(tmp.p, tb, rawKeys.p, sortedKeys.p, nRaw, 0, endBit, s); nl += (endBit + 7) / 8;
+    if (gauge) {   // mono: the zero pose has no block at all after the join; keep every diagonal
+        k_pat_diag<<<ceil_div(J.totPose, TB), TB, 0, s>>>(J.d.p, J.dPosePre.p, K, J.totPose, bm.p, dBmOff.p); nl++;
     }
-    DevBuf<int> dNuis(1, s);
-    {
-        size_t tb = 0;
-        cub::DeviceSelect::Unique(nullptr, tb, sortedKeys.p, keys.p, dNuis.p, nRaw, s);
-        DevBuf<char> tmp(tb, s);
-        cub::DeviceSelect::Unique(tmp.p, tb, sortedKeys.p, keys.p, dNuis.p, nRaw, s); nl += 2;
-    }
-    // one synchronisation for everything the host needs: #blocks, keys (upper bound nRaw copied),
-    // row pointers
+    if (J.totU > 0) { k_pat_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, K, J.totU, bm.p, dBmOff.p); nl++; }
+    DevBuf<int> rowCnt(J.totPose + 1, s), rowPtr(J.totPose + 1, s);
+    k_bm_rowcount<<<ceil_div((J.totPose + 1) * 32, TB), TB, 0, s>>>(bm.p, dBmOff.p, J.d.p, J.dPosePre.p, K, J.totPose, rowCnt.p); nl++;
+    exclusive_scan(ctx, rowCnt.p, rowPtr.p, J.totPose + 1); nl += 2;
+    // the number of blocks is not known on the host yet: keys are produced / copied up to a bound
+    // (exact for small joins, generous for large ones); the rare overshoot takes a second copy
+    const int keyCap = (int)std::min<long long>(capBlocks, 64LL * J.totPose + 4096);
+    DevBuf<u64> keys((size_t)std::max(keyCap, 1), s);
+    k_bm_emit<<<ceil_div(J.totPose * 32, TB), TB, 0, s>>>(bm.p, dBmOff.p, J.d.p, J.dPosePre.p, K, J.totPose, rowPtr.p, keys.p, keyCap); nl++;
+    // one synchronisation for everything the host needs: keys, row pointers (#blocks = last entry)
     int nuis = 0;
-    DevBuf<int> rowPtr(J.totPose + 1, s);
-    k_rowptr<<<ceil_div(J.totPose + 1, TB), TB, 0, s>>>(keys.p, dNuis.p, J.dPosePre.p, K, J.totPose, rowPtr.p); nl++;
-    char *pin = ctx.pinDown.need(sizeof(u64) * ((size_t)nRaw + 1) + sizeof(int) * ((size_t)J.totPose + 2));
+    char *pin = ctx.pinDown.need(sizeof(u64) * ((size_t)keyCap + 1) + sizeof(int) * ((size_t)J.totPose + 4));
     u64 *hKeys = (u64 *)pin;
-    int *hRowPtr = (int *)(pin + sizeof(u64) * ((size_t)nRaw + 1));
-    int *hNuis = hRowPtr + J.totPose + 1;
-    CUDA_CHECK(cudaMemcpyAsync(hNuis, dNuis.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (nRaw) CUDA_CHECK(cudaMemcpyAsync(hKeys, keys.p, sizeof(u64) * nRaw, cudaMemcpyDeviceToHost, s));
+    int *hRowPtr = (int *)(pin + sizeof(u64) * ((size_t)keyCap + 1));
+    int *hMaxNp = hRowPtr + J.totPose + 1;
+    *hMaxNp = 0;
+    if (nChunks > 0) CUDA_CHECK(cudaMemcpyAsync(hMaxNp, dMaxNp.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (keyCap) CUDA_CHECK(cudaMemcpyAsync(hKeys, keys.p, sizeof(u64) * keyCap, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(hRowPtr, rowPtr.p, sizeof(int) * (J.totPose + 1), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
-    nuis = *hNuis;
+    nuis = hRowPtr[J.totPose];
+    if (nChunks > 0) maxNposes = *hMaxNp;
+    if (nuis > keyCap) {                  // bound overshot: emit and fetch again with the exact size
+        keys.alloc((size_t)nuis, s);
+        k_bm_emit<<<ceil_div(J.totPose * 32, TB), TB, 0, s>>>(bm.p, dBmOff.p, J.d.p, J.dPosePre.p, K, J.totPose, rowPtr.p, keys.p, nuis); nl++;
+        pin = ctx.pinDown.need(sizeof(u64) * ((size_t)nuis + 1) + sizeof(int) * ((size_t)J.totPose + 4));
+        hKeys = (u64 *)pin;
+        hRowPtr = (int *)(pin + sizeof(u64) * ((size_t)nuis + 1));
+        CUDA_CHECK(cudaMemcpyAsync(hKeys, keys.p, sizeof(u64) * nuis, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(hRowPtr, rowPtr.p, sizeof(int) * (J.totPose + 1), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
     KERNEL_CHECK();
-    ctx.end(8.0 * nRaw, 0.0, nl);
+    ctx.end(8.0 * nuis + 4.0 * bmOff[K], 0.0, nl);
     nl = 0;
 
     // The pattern is on its way to the host symbolic phase; work the caller deferred until now
