@@ -6,6 +6,7 @@
 // (stno -> poseNo/featNo, FBlock/feature -> CSR wPtr) happen during packing.
 #include "mapio.h"
 #include <cstring>
+#include <atomic>
 #include <thread>
 #include <algorithm>
 
@@ -70,56 +71,84 @@ std::vector<MapHandle> upload_maps(Context &ctx, const lsfm_map *maps, int K, bo
     char *base = A.base;
     auto H = [&](const void *devp) { return stage + ((const char *)devp - base); };
 
+    // Packing and the host-to-device copy are pipelined: the maps are cut into groups of ~8 MB
+    // (contiguous in the arena); worker threads pack groups in order, the calling thread issues one
+    // asynchronous copy per group as soon as it is packed, so the PCIe transfer of group g overlaps
+    // the packing of the groups behind it.
     int nthreads = std::min<int>(std::max(1u, std::thread::hardware_concurrency()), 16);
     if (A.used < (1u << 22)) nthreads = 1;
-    std::vector<std::string> errs(nthreads);
-    auto work = [&](int tid) {
-        try {
-            for (int k = tid; k < K; k += nthreads) {
-                const lsfm_map &M = maps[k];
-                const DMap &d = out[k].d;
-                int *poseNo = (int *)H(d.poseNo);
-                double *poseVal = (double *)H(d.poseVal);
-                for (int p = 0; p < M.m; p++) poseNo[p] = M.stno[6 * p];
-                if (M.m) memcpy(poseVal, M.stVal, sizeof(double) * 6 * (size_t)M.m);
-                int *featNo = (int *)H(d.featNo);
-                for (int f = 0; f < M.n; f++) featNo[f] = M.stno[6 * M.m + 3 * f];
-                if (M.n) memcpy(H(d.featVal), M.stVal + 6 * (size_t)M.m, sizeof(double) * 3 * (size_t)M.n);
-                if (M.nU) {
-                    memcpy(H(d.U), M.U, sizeof(double) * 36 * (size_t)M.nU);
-                    memcpy(H(d.Ui), M.Ui, sizeof(int) * M.nU);
-                    memcpy(H(d.Uj), M.Uj, sizeof(int) * M.nU);
-                }
-                if (M.nW) {
-                    memcpy(H(d.W), M.W, sizeof(double) * 18 * (size_t)M.nW);
-                    memcpy(H(d.photo), M.photo, sizeof(int) * M.nW);
-                    memcpy(H(d.feature), M.feature, sizeof(int) * M.nW);
-                }
-                if (M.n) memcpy(H(d.V), M.V, sizeof(double) * 9 * (size_t)M.n);
-                int *wPtr = (int *)H(d.wPtr);
-                int j = 0;
-                for (int f = 0; f < M.n; f++) {
-                    wPtr[f] = j;
-                    while (j < M.nW && M.feature[j] == f) j++;
-                    if (validate && M.FBlock) {
-                        int fb = (j > wPtr[f]) ? wPtr[f] : -1;
-                        if (M.FBlock[f] != fb)
-                            throw LsfmError(LSFM_ERR_FORMAT, "local map " + std::to_string(k) +
-                                                                 ": FBlock inconsistent with feature[]");
-                    }
-                }
-                wPtr[M.n] = M.nW;
+    auto map_begin = [&](int k) { return (size_t)((const char *)out[k].d.poseNo - base); };
+    std::vector<int> gstart{0};
+    for (int k = 1; k < K; k++)
+        if (map_begin(k) - map_begin(gstart.back()) >= (size_t)(8u << 20)) gstart.push_back(k);
+    const int G = (int)gstart.size();
+    gstart.push_back(K);
+    auto pack_map = [&](int k) {
+        const lsfm_map &M = maps[k];
+        const DMap &d = out[k].d;
+        int *poseNo = (int *)H(d.poseNo);
+        double *poseVal = (double *)H(d.poseVal);
+        for (int p = 0; p < M.m; p++) poseNo[p] = M.stno[6 * p];
+        if (M.m) memcpy(poseVal, M.stVal, sizeof(double) * 6 * (size_t)M.m);
+        int *featNo = (int *)H(d.featNo);
+        for (int f = 0; f < M.n; f++) featNo[f] = M.stno[6 * M.m + 3 * f];
+        if (M.n) memcpy(H(d.featVal), M.stVal + 6 * (size_t)M.m, sizeof(double) * 3 * (size_t)M.n);
+        if (M.nU) {
+            memcpy(H(d.U), M.U, sizeof(double) * 36 * (size_t)M.nU);
+            memcpy(H(d.Ui), M.Ui, sizeof(int) * M.nU);
+            memcpy(H(d.Uj), M.Uj, sizeof(int) * M.nU);
+        }
+        if (M.nW) {
+            memcpy(H(d.W), M.W, sizeof(double) * 18 * (size_t)M.nW);
+            memcpy(H(d.photo), M.photo, sizeof(int) * M.nW);
+            memcpy(H(d.feature), M.feature, sizeof(int) * M.nW);
+        }
+        if (M.n) memcpy(H(d.V), M.V, sizeof(double) * 9 * (size_t)M.n);
+        int *wPtr = (int *)H(d.wPtr);
+        int j = 0;
+        for (int f = 0; f < M.n; f++) {
+            wPtr[f] = j;
+            while (j < M.nW && M.feature[j] == f) j++;
+            if (validate && M.FBlock) {
+                int fb = (j > wPtr[f]) ? wPtr[f] : -1;
+                if (M.FBlock[f] != fb)
+                    throw LsfmError(LSFM_ERR_FORMAT, "local map " + std::to_string(k) +
+                                                         ": FBlock inconsistent with feature[]");
             }
-        } catch (const std::exception &e) { errs[tid] = e.what(); }
+        }
+        wPtr[M.n] = M.nW;
     };
-    if (nthreads == 1) work(0);
-    else {
+    std::vector<std::string> errs(nthreads);
+    if (nthreads == 1) {
+        try { for (int k = 0; k < K; k++) pack_map(k); } catch (const std::exception &e) { errs[0] = e.what(); }
+        if (errs[0].empty()) CUDA_CHECK(cudaMemcpyAsync(A.base, stage, A.used, cudaMemcpyHostToDevice, ctx.stream));
+    } else {
+        std::atomic<int> next(0);
+        std::vector<std::atomic<int>> done(G);
+        for (auto &d : done) d.store(0);
+        auto work = [&](int tid) {
+            for (;;) {
+                int g = next.fetch_add(1);
+                if (g >= G) break;
+                try {
+                    for (int k = gstart[g]; k < gstart[g + 1]; k++) pack_map(k);
+                } catch (const std::exception &e) { errs[tid] = e.what(); }
+                done[g].store(1, std::memory_order_release);
+            }
+        };
         std::vector<std::thread> th;
         for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
+        bool failed = false;
+        for (int g = 0; g < G; g++) {
+            while (!done[g].load(std::memory_order_acquire)) std::this_thread::yield();
+            for (auto &e : errs) if (!e.empty()) failed = true;
+            if (failed) continue;
+            size_t b0 = map_begin(gstart[g]), b1 = (g + 1 < G) ? map_begin(gstart[g + 1]) : A.used;
+            CUDA_CHECK(cudaMemcpyAsync(A.base + b0, stage + b0, b1 - b0, cudaMemcpyHostToDevice, ctx.stream));
+        }
         for (auto &t : th) t.join();
     }
     for (auto &e : errs) if (!e.empty()) throw LsfmError(LSFM_ERR_FORMAT, e);
-    CUDA_CHECK(cudaMemcpyAsync(A.base, stage, A.used, cudaMemcpyHostToDevice, ctx.stream));
     // the staging buffer is reused by the next upload: make sure this copy has been consumed
     CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
     return out;

@@ -825,8 +825,9 @@ k_tf_posefin(DMap *__restrict__ out, const int *__restrict__ posePre, int K, int
              const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj,
              const double *__restrict__ poseAcc)
 {
-    int gp = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gp >= totPose) return;
+    int gp0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = gp0 < totPose;             // no early return: the warp stays converged
+    const int gp = live ? gp0 : totPose - 1;
     int k = seg_find(posePre, K, gp);
     int p = gp - posePre[k];
     const TfConst &c = tc[k];
@@ -842,29 +843,37 @@ k_tf_posefin(DMap *__restrict__ out, const int *__restrict__ posePre, int K, int
     jt_mul<3>(Q, isPos ? -1.0 : 1.0, J.b1, J.c1, isPos, SWQ, a1);
     jt_mul<3>(Q, isPos ? -1.0 : 1.0, J.b1, J.c1, isPos, SWT, a3);
     double *u = out[k].U + 36 * (size_t)p;
+    // every pose of a map adds into the map's (pos,pos) block: reduced across the warp first
+    // (lanes of one warp mostly belong to one map), otherwise the root map's 3499 poses serialise
+    // on 36 addresses
+    double G2[36];
 #pragma unroll
-    for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int q = 0; q < 6; q++) {
-            double xrq = (q < 3) ? -a1[3 * r + q] : a3[3 * r + q - 3];
-            if (p < pid) atomicAdd(u + 6 * r + q, xrq);
-            else if (p > pid) atomicAdd(u + 6 * q + r, xrq);
-            else { atomicAdd(u + 6 * r + q, xrq); atomicAdd(u + 6 * q + r, xrq); }
-        }
-    if (!isPos) {
-        double a2[18], a4[18];
-        jt_mul<3>(Q, -1.0, J.f2, J.g2, true, SWQ, a2);
-        jt_mul<3>(Q, -1.0, J.f2, J.g2, true, SWT, a4);
-        double *up = out[k].U + 36 * (size_t)pid;
+    for (int q = 0; q < 36; q++) G2[q] = 0.0;
+    if (live) {
 #pragma unroll
         for (int r = 0; r < 6; r++)
 #pragma unroll
             for (int q = 0; q < 6; q++) {
-                double grq = (q < 3) ? -a2[3 * r + q] : a4[3 * r + q - 3];
-                atomicAdd(up + 6 * r + q, grq);
-                atomicAdd(up + 6 * q + r, grq);
+                double xrq = (q < 3) ? -a1[3 * r + q] : a3[3 * r + q - 3];
+                if (p < pid) atomicAdd(u + 6 * r + q, xrq);
+                else if (p > pid) atomicAdd(u + 6 * q + r, xrq);
+                else { G2[6 * r + q] += xrq; G2[6 * q + r] += xrq; }
             }
+        if (!isPos) {
+            double a2[18], a4[18];
+            jt_mul<3>(Q, -1.0, J.f2, J.g2, true, SWQ, a2);
+            jt_mul<3>(Q, -1.0, J.f2, J.g2, true, SWT, a4);
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int q = 0; q < 6; q++) {
+                    double grq = (q < 3) ? -a2[3 * r + q] : a4[3 * r + q - 3];
+                    G2[6 * r + q] += grq;
+                    G2[6 * q + r] += grq;
+                }
+        }
     }
+    sm::warp_agg_atomic_add<36>(out[k].U + 36 * (size_t)pid, G2, live);
 }
 
 #include "transform_chunk.cuh"
