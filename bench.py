@@ -313,7 +313,7 @@ def main():
             "config": {"workload": f"synthetic NC3500-shape stereo scene, {nmaps} local maps, {FEATS} new landmarks/frame",
                        "l2": "inputs larger than L2 (leaf maps ~0.4 GB, upper levels > 1 GB)",
                        "parallelism": f"tree-level sharding x{world}" if world > 1 else "single GPU"},
-            "device_ms_per_step": dev_ms / args.steps,
+            "device_ms_per_step": (dev_ms / args.steps) if world == 1 else None,
             "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes)},
             "gpu_launches": int(launches),
