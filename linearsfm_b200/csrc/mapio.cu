@@ -28,14 +28,25 @@ struct Pinned {
     ~Pinned() { if (p) cudaFreeHost(p); }
 };
 Pinned g_stage_up, g_stage_down;
+cudaEvent_t g_up_done = nullptr;      // last upload's copies out of g_stage_up
+bool g_up_pending = false;
 
-void validate_map(const lsfm_map &M, int idx)
+// sizes only (needed before anything is allocated)
+void validate_shape(const lsfm_map &M, int idx)
 {
     auto bad = [&](const std::string &why) {
         throw LsfmError(LSFM_ERR_FORMAT, "local map " + std::to_string(idx) + ": " + why);
     };
     if (M.m < 0 || M.n < 0 || M.nU < 0 || M.nW < 0) bad("negative size");
     if (M.r != 6 * M.m + 3 * M.n) bad("r != 6m+3n");
+}
+
+// contents; runs on the packing threads
+void validate_map(const lsfm_map &M, int idx)
+{
+    auto bad = [&](const std::string &why) {
+        throw LsfmError(LSFM_ERR_FORMAT, "local map " + std::to_string(idx) + ": " + why);
+    };
     for (int p = 0; p < M.m; p++)
         if (M.stno[6 * p] > 0) bad("pose row with positive stno");
     for (int f = 0; f < M.n; f++)
@@ -56,7 +67,7 @@ std::vector<MapHandle> upload_maps(Context &ctx, const lsfm_map *maps, int K, bo
 {
     std::vector<DMap> shapes(K);
     for (int k = 0; k < K; k++) {
-        if (validate) validate_map(maps[k], k);
+        if (validate) validate_shape(maps[k], k);
         DMap &d = shapes[k];
         memset(&d, 0, sizeof(d));
         d.Ref = maps[k].Ref; d.FRef = maps[k].FRef; d.m = maps[k].m; d.n = maps[k].n;
@@ -67,6 +78,7 @@ std::vector<MapHandle> upload_maps(Context &ctx, const lsfm_map *maps, int K, bo
     std::vector<MapHandle> out = alloc_maps(ctx, shapes);
     if (K == 0) return out;
     Arena &A = *out[0].arena;
+    if (g_up_pending) { CUDA_CHECK(cudaEventSynchronize(g_up_done)); g_up_pending = false; }
     char *stage = g_stage_up.get(A.used);
     char *base = A.base;
     auto H = [&](const void *devp) { return stage + ((const char *)devp - base); };
@@ -85,6 +97,7 @@ std::vector<MapHandle> upload_maps(Context &ctx, const lsfm_map *maps, int K, bo
     gstart.push_back(K);
     auto pack_map = [&](int k) {
         const lsfm_map &M = maps[k];
+        if (validate) validate_map(M, k);
         const DMap &d = out[k].d;
         int *poseNo = (int *)H(d.poseNo);
         double *poseVal = (double *)H(d.poseVal);
@@ -149,8 +162,11 @@ std::vector<MapHandle> upload_maps(Context &ctx, const lsfm_map *maps, int K, bo
         for (auto &t : th) t.join();
     }
     for (auto &e : errs) if (!e.empty()) throw LsfmError(LSFM_ERR_FORMAT, e);
-    // the staging buffer is reused by the next upload: make sure this copy has been consumed
-    CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    // the staging buffer is reused by the next upload: that one waits for this copy (the caller's
+    // own buffers have been read completely by now, and the stream orders the copy before any kernel)
+    if (!g_up_done) CUDA_CHECK(cudaEventCreateWithFlags(&g_up_done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(g_up_done, ctx.stream));
+    g_up_pending = true;
     return out;
 }
 
