@@ -449,18 +449,37 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
     const int tid = threadIdx.x, nt = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
 
+    // extend-add of the children's update matrices (lower triangle + rhs row).  A warp walks one
+    // child column at a time, four 32-row pieces per pass: all loads of a pass (child values and
+    // the parent entries they land on) are issued before the first add, so the L2 latency of this
+    // scattered read-modify-write is paid once per pass instead of once per entry.
     for (int ci = 0; ci < d.nchild; ci++) {
         const SnodeDesc c = sn[childIdx[d.childOff + ci]];
         const double *Fc = fronts + c.frontOff;
         const int ncc = 6 * c.ncols, us = 6 * c.nstruct, ldc = 6 * (c.ncols + c.nstruct) + 1;
         const int *rel = relIdx + c.structOff;
         const int rows = us + 1;
-        for (int t = tid; t < rows * us; t += nt) {
-            int cc = t / rows, r = t - cc * rows;
-            if (r < cc) continue;
-            int pr = (r == us) ? fs : 6 * rel[r / 6] + (r % 6);
-            int pc = 6 * rel[cc / 6] + (cc % 6);
-            F[(size_t)pc * ld + pr] += Fc[(size_t)(ncc + cc) * ldc + ncc + r];
+        for (int cc = warp; cc < us; cc += nw) {
+            const int pcx = 6 * rel[cc / 6] + (cc % 6);
+            const double *src = Fc + (size_t)(ncc + cc) * ldc + ncc;
+            double *dstc = F + (size_t)pcx * ld;
+            for (int r0 = cc + lane; r0 < rows; r0 += 128) {
+                double cv[4], pv[4];
+                int pr[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int r = r0 + 32 * j;
+                    pr[j] = -1;
+                    if (r < rows) {
+                        pr[j] = (r == us) ? fs : 6 * rel[r / 6] + (r % 6);
+                        cv[j] = src[r];
+                        pv[j] = dstc[pr[j]];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (pr[j] >= 0) dstc[pr[j]] = pv[j] + cv[j];
+            }
         }
         __syncthreads();
     }
@@ -559,17 +578,30 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
             int q = t / rows, rr = t - q * rows;
             if (rr >= q) F[(size_t)(p0 + q) * ld + p0 + rr] = P[q * ldp + rr];
         }
-        // rank-pc update of everything right of the panel (lower triangle + rhs row)
+        // rank-pc update of everything right of the panel (lower triangle + rhs row): a warp per
+        // column, four 32-row pieces at a time (their global loads are issued together; the panel
+        // entry of the column is read once per q for all four pieces)
         for (int c = p0 + pc + warp; c < fs; c += nw) {
             const int cc = c - p0;
-            for (int r = c + lane; r <= fs; r += 32) {
-                const int rr = r - p0;
-                double v0 = F[(size_t)c * ld + r], v1 = 0.0;
-                for (int q = 0; q < pc; q += 2) {
-                    v0 = fma(-P[q * ldp + rr], P[q * ldp + cc], v0);
-                    v1 = fma(-P[(q + 1) * ldp + rr], P[(q + 1) * ldp + cc], v1);
+            double *Fcol = F + (size_t)c * ld;
+            for (int r0 = c + lane; r0 <= fs; r0 += 128) {
+                double v[4];
+                int rr[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int r = r0 + 32 * j;
+                    const bool ok = r <= fs;
+                    rr[j] = ok ? r - p0 : cc;        // idle pieces read a valid panel entry, result dropped
+                    v[j] = ok ? Fcol[r] : 0.0;
                 }
-                F[(size_t)c * ld + r] = v0 + v1;
+                for (int q = 0; q < pc; q++) {
+                    const double a = -P[q * ldp + cc];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = fma(P[q * ldp + rr[j]], a, v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (r0 + 32 * j <= fs) Fcol[r0 + 32 * j] = v[j];
             }
         }
         __syncthreads();
