@@ -5,6 +5,7 @@
 #include <memory>
 #include <vector>
 #include <map>
+#include <chrono>
 #include <string>
 
 // Caching device allocator.  Every allocation / free of the library happens in program order on ONE
@@ -200,6 +201,15 @@ struct Context {
             CUDA_CHECK(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
             throw LsfmError(LSFM_ERR_NOT_SPD, "reduced camera system is not positive definite");
         }
+    }
+
+    // host time between a size read-back (stream drained) and the next launch = GPU idle; LSFM_DEBUG
+    double idle_ms[4] = {0, 0, 0, 0};
+    std::chrono::steady_clock::time_point idle_t0;
+    void idle_begin() { idle_t0 = std::chrono::steady_clock::now(); }
+    void idle_end(int site)
+    {
+        idle_ms[site] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - idle_t0).count();
     }
 
     // event pool for stage timing

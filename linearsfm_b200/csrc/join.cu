@@ -419,6 +419,7 @@ std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHand
     std::vector<int> nOnly(K);
     dOnly.download(nOnly.data(), K);
     CUDA_CHECK(cudaStreamSynchronize(s));
+    ctx.idle_begin();
     KERNEL_CHECK();
     ctx.end(8.0 * (E.totFeat + C.totFeat), 0.0, nl);
     nl = 0;
@@ -444,6 +445,7 @@ std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHand
     for (int k = 0; k < K; k++) bytes += map_bytes(J.h[k]);
 
     DevBuf<int> jointOfCur(C.totFeat + 1, s), curOfJoint(J.totFeat + 1, s);
+    ctx.idle_end(1);
     CUDA_CHECK(cudaMemsetAsync(curOfJoint.p, 0xff, (J.totFeat + 1) * sizeof(int), s));
     if (C.totFeat > 0) {
         k_joint_index<<<ceil_div(C.totFeat, TB), TB, 0, s>>>(E.d.p, C.dFeatPre.p, J.dFeatPre.p, K, C.totFeat,

@@ -104,6 +104,11 @@ std::vector<MapHandle> solve_tree_stereo(Context &ctx, std::vector<MapHandle> le
         level = std::move(next);
         L++;
     }
+    if (getenv("LSFM_DEBUG")) {
+        fprintf(stderr, "host work between a size read-back and the next launch (GPU idle): transform %.3f ms, join %.3f ms, pattern %.3f ms\n",
+                ctx.idle_ms[0], ctx.idle_ms[1], ctx.idle_ms[2]);
+        ctx.idle_ms[0] = ctx.idle_ms[1] = ctx.idle_ms[2] = 0.0;
+    }
     return level;
 }
 

@@ -578,30 +578,40 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
             int q = t / rows, rr = t - q * rows;
             if (rr >= q) F[(size_t)(p0 + q) * ld + p0 + rr] = P[q * ldp + rr];
         }
-        // rank-pc update of everything right of the panel (lower triangle + rhs row): a warp per
-        // column, four 32-row pieces at a time (their global loads are issued together; the panel
-        // entry of the column is read once per q for all four pieces)
-        for (int c = p0 + pc + warp; c < fs; c += nw) {
-            const int cc = c - p0;
-            double *Fcol = F + (size_t)c * ld;
+        // rank-pc update of everything right of the panel (lower triangle + rhs row): a warp takes
+        // two columns and four 32-row pieces at a time -- eight independent FMA chains per lane, the
+        // global loads of a pass issued together, six shared loads per eight FMAs
+        for (int c = p0 + pc + 2 * warp; c < fs; c += 2 * nw) {
+            const bool has2 = (c + 1 < fs);
+            const int cc0 = c - p0, cc1 = has2 ? cc0 + 1 : cc0;
+            double *F0 = F + (size_t)c * ld;
+            double *F1 = F + (size_t)(c + 1) * ld;
             for (int r0 = c + lane; r0 <= fs; r0 += 128) {
-                double v[4];
+                double v0[4], v1[4];
                 int rr[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int r = r0 + 32 * j;
-                    const bool ok = r <= fs;
-                    rr[j] = ok ? r - p0 : cc;        // idle pieces read a valid panel entry, result dropped
-                    v[j] = ok ? Fcol[r] : 0.0;
+                    const bool ok0 = r <= fs, ok1 = has2 && ok0 && r > c;
+                    rr[j] = ok0 ? r - p0 : cc0;      // idle pieces read a valid panel entry, result dropped
+                    v0[j] = ok0 ? F0[r] : 0.0;
+                    v1[j] = ok1 ? F1[r] : 0.0;
                 }
                 for (int q = 0; q < pc; q++) {
-                    const double a = -P[q * ldp + cc];
+                    const double a0 = -P[q * ldp + cc0], a1 = -P[q * ldp + cc1];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) v[j] = fma(P[q * ldp + rr[j]], a, v[j]);
+                    for (int j = 0; j < 4; j++) {
+                        const double x = P[q * ldp + rr[j]];
+                        v0[j] = fma(x, a0, v0[j]);
+                        v1[j] = fma(x, a1, v1[j]);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (r0 + 32 * j <= fs) Fcol[r0 + 32 * j] = v[j];
+                for (int j = 0; j < 4; j++) {
+                    const int r = r0 + 32 * j;
+                    if (r <= fs) F0[r] = v0[j];
+                    if (has2 && r <= fs && r > c) F1[r] = v1[j];
+                }
             }
         }
         __syncthreads();
@@ -613,7 +623,7 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
 // triangular solve is latency-bound: shared memory instead of L2 for every step).
 constexpr int BS_PC = 48;
 constexpr int BS_TS = BS_PC + 1;      // padded stride: a lane walks a ROW of the column-major triangle
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
                   const int *__restrict__ structIdx, const double *__restrict__ fronts,
                   double *__restrict__ xperm)
@@ -629,22 +639,39 @@ k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__
     double *xj = xperm + 6 * (size_t)d.poseOff;
     for (int i = tid; i < us; i += nt) xs[i] = xj[6 * structIdx[d.structOff + i / 6] + (i % 6)];
     __syncthreads();
-    for (int c = warp; c < nc; c += nw) {
-        double acc = 0.0;
-        for (int r = lane; r < us; r += 32) acc += F[(size_t)c * ld + nc + r] * xs[r];
-        acc = sm::warp_sum(acc);
-        if (lane == 0) t[c] = F[(size_t)c * ld + fs] - acc;
+    // four columns per warp and pass: their loads are independent, the L2 latency is paid once
+    for (int cb = 4 * warp; cb < nc; cb += 4 * nw) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r = lane; r < us; r += 32) {
+            const double x = xs[r];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (cb + j < nc) acc[j] = fma(F[(size_t)(cb + j) * ld + nc + r], x, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double a = sm::warp_sum(acc[j]);
+            if (lane == 0 && cb + j < nc) t[cb + j] = F[(size_t)(cb + j) * ld + fs] - a;
+        }
     }
     __syncthreads();
     for (int c1 = nc; c1 > 0; c1 -= BS_PC) {
         const int c0 = max(0, c1 - BS_PC), pb = c1 - c0;
         // contributions of the already solved columns [c1, nc)
         if (c1 < nc)
-            for (int c = c0 + warp; c < c1; c += nw) {
-                double acc = 0.0;
-                for (int r = c1 + lane; r < nc; r += 32) acc += F[(size_t)c * ld + r] * t[r];
-                acc = sm::warp_sum(acc);
-                if (lane == 0) t[c] -= acc;
+            for (int cb = c0 + 4 * warp; cb < c1; cb += 4 * nw) {
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int r = c1 + lane; r < nc; r += 32) {
+                    const double x = t[r];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (cb + j < c1) acc[j] = fma(F[(size_t)(cb + j) * ld + r], x, acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    double a = sm::warp_sum(acc[j]);
+                    if (lane == 0 && cb + j < c1) t[cb + j] -= a;
+                }
             }
         for (int e = tid; e < pb * pb; e += nt) {
             int c = e / pb, r = e - c * pb;
@@ -788,7 +815,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     exclusive_scan(ctx, rowCnt.p, rowPtr.p, J.totPose + 1); nl += 2;
     // the number of blocks is not known on the host yet: keys are produced / copied up to a bound
     // (exact for small joins, generous for large ones); the rare overshoot takes a second copy
-    const int keyCap = (int)std::min<long long>(capBlocks, 64LL * J.totPose + 4096);
+    int keyCap = (int)std::min<long long>(capBlocks, 64LL * J.totPose + 4096);
+    if (force_ovf) keyCap = std::min(keyCap, 16);     // test hook: exercise the second-copy path
     DevBuf<u64> keys((size_t)std::max(keyCap, 1), s);
     k_bm_emit<<<ceil_div(J.totPose * 32, TB), TB, 0, s>>>(bm.p, dBmOff.p, J.d.p, J.dPosePre.p, K, J.totPose, rowPtr.p, keys.p, keyCap); nl++;
     // one synchronisation for everything the host needs: keys, row pointers (#blocks = last entry)
@@ -802,6 +830,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     if (keyCap) CUDA_CHECK(cudaMemcpyAsync(hKeys, keys.p, sizeof(u64) * keyCap, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(hRowPtr, rowPtr.p, sizeof(int) * (J.totPose + 1), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
+    ctx.idle_begin();
     nuis = hRowPtr[J.totPose];
     if (nChunks > 0) maxNposes = *hMaxNp;
     if (nuis > keyCap) {                  // bound overshot: emit and fetch again with the exact size
@@ -820,6 +849,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
 
     // The pattern is on its way to the host symbolic phase; work the caller deferred until now
     // (the join's value copy) is queued here so that it runs while the host analyses the pattern.
+    ctx.idle_end(2);
     if (ex && ex->after_pattern) ex->after_pattern();
 
     // ---- a9-a10: V^-1, S, E ----
@@ -927,7 +957,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     for (int l = nLevels - 1; l >= 0; l--) {
         int cnt = sym.levelPtr[l + 1] - sym.levelPtr[l];
         if (cnt == 0) continue;
-        k_front_backsolve<<<cnt, 128, shb, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dStruct.p, fronts.p, xperm.p); nl++;
+        k_front_backsolve<<<cnt, 256, shb, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dStruct.p, fronts.p, xperm.p); nl++;
     }
     k_unpermute<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(J.d.p, J.dPosePre.p, K, J.totPose, dPerm.p, xperm.p); nl++;
     // the not-SPD flag is sticky in the context and checked once per API call (no sync here)

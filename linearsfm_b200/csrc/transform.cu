@@ -1007,6 +1007,7 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
     dPos.download(hPos.data(), K);
     dSizes.download(hSizes.data(), 2 * (size_t)K);
     CUDA_CHECK(cudaStreamSynchronize(s));
+    ctx.idle_begin();
     KERNEL_CHECK();
 
     std::vector<DMap> shapes(K);
@@ -1028,6 +1029,7 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
     B.build(out, s);
     DevBuf<TfConst> tc(K, s);
     DevBuf<PoseJac> pj(A.totPose, s);
+    ctx.idle_end(0);
     k_tf_const<<<ceil_div(K, 64), 64, 0, s>>>(A.d.p, B.d.p, A.dPosePre.p, K, dPos.p, dSizes.p + K, tc.p, pj.p); nl++;
     k_tf_pose<<<ceil_div(A.totPose, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dPosePre.p, K, A.totPose, tc.p, pj.p); nl++;
     k_tf_uinit<<<ceil_div(A.totPose, TB), TB, 0, s>>>(B.d.p, A.dPosePre.p, K, A.totPose, dPos.p); nl++;
