@@ -459,12 +459,16 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
         const int ncc = 6 * c.ncols, us = 6 * c.nstruct, ldc = 6 * (c.ncols + c.nstruct) + 1;
         const int *rel = relIdx + c.structOff;
         const int rows = us + 1;
-        for (int cc = warp; cc < us; cc += nw) {
-            const int pcx = 6 * rel[cc / 6] + (cc % 6);
-            const double *src = Fc + (size_t)(ncc + cc) * ldc + ncc;
-            double *dstc = F + (size_t)pcx * ld;
+        for (int cc = 2 * warp; cc < us; cc += 2 * nw) {
+            const bool has2 = (cc + 1 < us);
+            const int pcx0 = 6 * rel[cc / 6] + (cc % 6);
+            const int pcx1 = has2 ? 6 * rel[(cc + 1) / 6] + ((cc + 1) % 6) : pcx0;
+            const double *src0 = Fc + (size_t)(ncc + cc) * ldc + ncc;
+            const double *src1 = src0 + ldc;
+            double *dst0 = F + (size_t)pcx0 * ld;
+            double *dst1 = F + (size_t)pcx1 * ld;
             for (int r0 = cc + lane; r0 < rows; r0 += 128) {
-                double cv[4], pv[4];
+                double cv0[4], pv0[4], cv1[4], pv1[4];
                 int pr[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -472,13 +476,17 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
                     pr[j] = -1;
                     if (r < rows) {
                         pr[j] = (r == us) ? fs : 6 * rel[r / 6] + (r % 6);
-                        cv[j] = src[r];
-                        pv[j] = dstc[pr[j]];
+                        cv0[j] = src0[r];
+                        pv0[j] = dst0[pr[j]];
+                        if (has2 && r > cc) { cv1[j] = src1[r]; pv1[j] = dst1[pr[j]]; }
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    if (pr[j] >= 0) dstc[pr[j]] = pv[j] + cv[j];
+                    if (pr[j] >= 0) {
+                        dst0[pr[j]] = pv0[j] + cv0[j];
+                        if (has2 && r0 + 32 * j > cc) dst1[pr[j]] = pv1[j] + cv1[j];
+                    }
             }
         }
         __syncthreads();
