@@ -30,8 +30,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's own banner / debug output goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line: file descriptor 1 is pointed at stderr for everything else
+# (NCCL's version banner, the reference's printf progress lines, library chatter); the JSON line
+# goes to a private duplicate of the original stdout
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 FULL_MAPS = 3499
 FEATS = 128
@@ -145,7 +148,7 @@ def run_reference(args, rank):
                          "sample": f"first {ns} of {nmaps} local maps, measured {t:.3f} s/solve, scaled x{nmaps / ns:.3f} (linear in maps)"},
         "e2e": {"value": scaled, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def main():
@@ -326,7 +329,7 @@ def main():
             line["stages"] = stages
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
