@@ -9,8 +9,10 @@
 //     four families per block (D^T I D, C^T I D, D^T I C, C^T I C);
 //   * feature Jacobians (D_f = Q, C_f = [-Q | dQ (X'-t')]) are recomputed on the fly, pose
 //     Jacobians are kept as four 3x3 blocks per pose (structural zeros skipped);
-//   * one thread per feature streams that feature's W blocks; sums into shared targets
-//     (U'(p,pos), U'(pos,pos)) are warp-aggregated FP64 atomics;
+//   * the W/V part is one pass over W (k_tf_chunk, transform_chunk.cuh: CTA per 128 features, one
+//     thread per W block, per-feature and per-pose sums formed in shared memory / registers);
+//     the per-pose sums are applied to U'(p,pos) and U'(pos,pos) once per pose (k_tf_posefin);
+//     sums into one shared target are reduced across the warp before the FP64 atomics;
 //   * output block lists keep the reference's exact order (Appendix C.1 of SURVEY.md): slots
 //     [0,m) = pairs with posID, then surviving U blocks in input order; per feature the new
 //     (posID,f) block first, then its surviving W blocks in input order.
@@ -290,164 +292,11 @@ __device__ __forceinline__ void jt_mul(const double *a, double sgn, const double
     if (has_b) sm::mtm_acc<3, 3, N>(b, X, out + 3 * N);
 }
 
-// one thread per feature (LinearSFMImp.cpp:1300-1915)
-__global__ void __launch_bounds__(128)
-k_wvcong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ featPre,
-         const int *__restrict__ posePre, int K, int totFeat, const TfConst *__restrict__ tc,
-         const PoseJac *__restrict__ pj, const int *__restrict__ fScan)
-{
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = g < totFeat;
-    int k = live ? seg_find(featPre, K, g) : 0;
-    int f = live ? g - featPre[k] : 0;
-    const DMap &M = in[k];
-    const DMap &O = out[k];
-    const TfConst &c = tc[k];
-    const int pid = c.posID;
-
-    double Q[9];
-    sm::load<9>(c.Q, Q);
-    double Tf[9];                    // columns QA d, QB d, QG d,  d = X' - t'
-    double Wpos[18];                 // new block (posID, f)
-    double G[36];                    // this feature's share of U'(pos,pos) (before symmetrising)
-    double Vn[9];
-    int kf = 0, w0 = 0, o0 = 0;
-    if (live) {
-        const double *x = M.featVal + 3 * (size_t)f;
-        double d0[3] = {x[0] - c.t[0], x[1] - c.t[1], x[2] - c.t[2]};
-        double xn[3];
-        geom::mat3_vec(c.R, d0, xn);
-        double *y = O.featVal + 3 * (size_t)f;
-        y[0] = xn[0]; y[1] = xn[1]; y[2] = xn[2];
-        O.featNo[f] = M.featNo[f];
-        double d[3] = {xn[0] - c.tn[0], xn[1] - c.tn[1], xn[2] - c.tn[2]};
-        double v[3];
-        geom::mat3_vec(c.QA, d, v); Tf[0] = v[0]; Tf[3] = v[1]; Tf[6] = v[2];
-        geom::mat3_vec(c.QB, d, v); Tf[1] = v[0]; Tf[4] = v[1]; Tf[7] = v[2];
-        geom::mat3_vec(c.QG, d, v); Tf[2] = v[0]; Tf[5] = v[1]; Tf[8] = v[2];
-
-        double V[9], VQ[9], VT[9], M1[9], M2[9];
-        sm::load<9>(M.V + 9 * (size_t)f, V);
-        sm::mm<3, 3, 3>(V, Q, VQ);
-        sm::mm<3, 3, 3>(V, Tf, VT);
-        sm::mtm<3, 3, 3>(Q, VQ, Vn);          // V' = Q^T V Q
-        sm::mtm<3, 3, 3>(Tf, VQ, M1);         // T^T V Q
-        sm::mtm<3, 3, 3>(Tf, VT, M2);         // T^T V T
-        sm::store<9>(O.V + 9 * (size_t)f, Vn);
-        // W'(pos,f) = C_f^T V D_f = [-V'; M1]
-#pragma unroll
-        for (int i = 0; i < 9; i++) { Wpos[i] = -Vn[i]; Wpos[9 + i] = M1[i]; }
-        // C_f^T V C_f = [[V', -M1^T],[-M1, M2]]  (already symmetric -> goes in full, halve later)
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                G[6 * r + q] = 0.5 * Vn[3 * r + q];
-                G[6 * r + 3 + q] = -0.5 * M1[3 * q + r];
-                G[6 * (r + 3) + q] = -0.5 * M1[3 * r + q];
-                G[6 * (r + 3) + 3 + q] = 0.5 * M2[3 * r + q];
-            }
-        w0 = M.wPtr[f];
-        kf = M.wPtr[f + 1] - w0;
-        o0 = fScan[g] - fScan[featPre[k]];
-        O.wPtr[f] = o0;
-        O.photo[o0] = pid;
-        O.feature[o0] = f;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 36; i++) G[i] = 0.0;
-    }
-
-    int kmax = __reduce_max_sync(0xffffffffu, kf);
-    int onext = o0 + 1;
-    for (int jj = 0; jj < kmax; jj++) {
-        bool act = jj < kf;
-        int p = 0;
-        double A3[36];
-        if (act) {
-            int j = w0 + jj;
-            p = M.photo[j];
-            double W[18], WQ[18], WT[18];
-            sm::load<18>(M.W + 18 * (size_t)j, W);
-            sm::mm<6, 3, 3>(W, Q, WQ);
-            sm::mm<6, 3, 3>(W, Tf, WT);
-            const PoseJac &J = pj[posePre[k] + p];
-            bool isPos = (p == pid);
-            double a1[18], a3[18];
-            // D_p^T [WQ | WT]
-            jt_mul<3>(Q, isPos ? -1.0 : 1.0, J.b1, J.c1, isPos, WQ, a1);
-            jt_mul<3>(Q, isPos ? -1.0 : 1.0, J.b1, J.c1, isPos, WT, a3);
-            if (isPos) {
-#pragma unroll
-                for (int i = 0; i < 18; i++) Wpos[i] += a1[i];
-            } else {
-                sm::store<18>(O.W + 18 * (size_t)onext, a1);
-                O.photo[onext] = p;
-                O.feature[onext] = f;
-                onext++;
-                // C_p^T [WQ | WT]  (zero for slot pos)
-                double a2[18], a4[18];
-                jt_mul<3>(Q, -1.0, J.f2, J.g2, true, WQ, a2);
-                jt_mul<3>(Q, -1.0, J.f2, J.g2, true, WT, a4);
-#pragma unroll
-                for (int i = 0; i < 18; i++) Wpos[i] += a2[i];
-                // C_p^T W C_f = [-a2 | a4]
-#pragma unroll
-                for (int r = 0; r < 6; r++)
-#pragma unroll
-                    for (int q = 0; q < 3; q++) {
-                        G[6 * r + q] -= a2[3 * r + q];
-                        G[6 * r + 3 + q] += a4[3 * r + q];
-                    }
-            }
-            // D_p^T W C_f = [-a1 | a3] -> U'(p,pos), slot p
-#pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    A3[6 * r + q] = -a1[3 * r + q];
-                    A3[6 * r + 3 + q] = a3[3 * r + q];
-                }
-            if (p > pid) {          // stored as (posID, p): transpose
-                double Tt[36];
-#pragma unroll
-                for (int r = 0; r < 6; r++)
-#pragma unroll
-                    for (int q = 0; q < 6; q++) Tt[6 * r + q] = A3[6 * q + r];
-#pragma unroll
-                for (int i = 0; i < 36; i++) A3[i] = Tt[i];
-            } else if (p == pid) {  // diagonal block gets X + X^T
-                double Tt[36];
-#pragma unroll
-                for (int r = 0; r < 6; r++)
-#pragma unroll
-                    for (int q = 0; q < 6; q++) Tt[6 * r + q] = A3[6 * r + q] + A3[6 * q + r];
-#pragma unroll
-                for (int i = 0; i < 36; i++) A3[i] = Tt[i];
-            }
-        }
-        sm::warp_agg_atomic_add<36>(O.U + 36 * (size_t)p, A3, act);
-    }
-    if (live) sm::store<18>(O.W + 18 * (size_t)o0, Wpos);
-    // U'(pos,pos) += G + G^T
-    double S[36];
-#pragma unroll
-    for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int q = 0; q < 6; q++) S[6 * r + q] = G[6 * r + q] + G[6 * q + r];
-    sm::warp_agg_atomic_add<36>(O.U + 36 * (size_t)pid, S, live);
-}
-
 // ---------------------------------------------------------------------------------------------
-// v2 of the W/V congruence: "lanes = blocks".
+// Cross-check variant of the W/V congruence (LSFM_TF_V3=1; the default is k_tf_chunk,
+// transform_chunk.cuh): separate kernels that read W twice.
 //   k_tf_featprep : one thread per feature  -> X', V', T_f scratch, the V part of W'(pos,f) and of
 //                   U'(pos,pos), output CSR/labels of the new (posID,f) block.
-//   k_tf_wblock   : one thread per OLD W block (a warp reads 32 consecutive 144-byte blocks = one
-//                   contiguous 4.6 KB span) -> D_p^T W D_f written to its slot; the per-feature sum
-//                   into W'(pos,f) by a warp-segmented shuffle reduction; the per-pose sums into
-//                   U'(p,pos) / U'(pos,pos) through a per-CTA shared-memory hash of 6x6 accumulators
-//                   that is flushed once per CTA (global FP64 atomics cost ~1e10/s, so they are
-//                   aggregated across the 1024 blocks a CTA walks).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_tf_featprep(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ featPre,
@@ -509,189 +358,8 @@ k_tf_featprep(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__
     sm::warp_agg_atomic_add<36>(O.U + 36 * (size_t)c.posID, S, live);
 }
 
-constexpr int TW_THREADS = 128;
-constexpr int TW_TILES = 8;            // a CTA walks TW_TILES x 128 consecutive W blocks
-constexpr int TW_HASH = 64;            // per-CTA pose hash (slots of 36 doubles)
-
-__device__ __forceinline__ int tw_hash_slot(int *keys, int key)
-{
-    unsigned h = ((unsigned)key * 2654435761u) >> 26;          // 6 bits
-    for (int probe = 0; probe < TW_HASH; probe++) {
-        int cur = keys[h];
-        if (cur == key) return (int)h;
-        if (cur == -1) {
-            int prev = atomicCAS(&keys[h], -1, key);
-            if (prev == -1 || prev == key) return (int)h;
-        }
-        h = (h + 1) & (TW_HASH - 1);
-    }
-    return -1;
-}
-
-__global__ void __launch_bounds__(TW_THREADS)
-k_tf_wblock(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ wPre,
-            const int *__restrict__ featPre, const int *__restrict__ posePre, int K, int totW,
-            const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj,
-            const double *__restrict__ TfBuf)
-{
-    __shared__ int hkeys[TW_HASH];
-    __shared__ double hvals[TW_HASH][36];
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < TW_HASH; i += TW_THREADS) hkeys[i] = -1;
-    for (int i = tid; i < TW_HASH * 36; i += TW_THREADS) (&hvals[0][0])[i] = 0.0;
-    __syncthreads();
-
-    const long long base = (long long)blockIdx.x * TW_THREADS * TW_TILES;
-    for (int tile = 0; tile < TW_TILES; tile++) {
-        long long gl = base + (long long)tile * TW_THREADS + tid;
-        if (base + (long long)tile * TW_THREADS >= totW) break;       // CTA-uniform
-        bool live = gl < totW;
-        int g = live ? (int)gl : 0;
-        int k = live ? seg_find(wPre, K, g) : 0;
-        int j = g - wPre[k];
-        const DMap &M = in[k];
-        const DMap &O = out[k];
-        const TfConst &c = tc[k];
-        const int pid = c.posID;
-        int f = 0, p = 0, gf = -1 - lane;          // dead lanes get unique negative keys
-        bool isPos = false;
-        double wadd[18];                            // this block's share of W'(pos,f)
-        double G[36];                               // share of U'(pos,pos) (before symmetrising)
-        double A3[36];                              // share of U'(p,pos), already oriented for slot p
-#pragma unroll
-        for (int i = 0; i < 18; i++) wadd[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < 36; i++) { G[i] = 0.0; A3[i] = 0.0; }
-        if (live) {
-            f = M.feature[j];
-            p = M.photo[j];
-            gf = featPre[k] + f;
-            isPos = (p == pid);
-            double Q[9], Tf[9], W[18], X[18], a1[18];
-            sm::load<9>(c.Q, Q);
-            sm::load<9>(TfBuf + 9 * (size_t)gf, Tf);
-            sm::load<18>(M.W + 18 * (size_t)j, W);
-            const PoseJac &J = pj[posePre[k] + p];
-            const double sgn = isPos ? -1.0 : 1.0;
-            sm::mm<6, 3, 3>(W, Q, X);                                   // W Q
-            jt_mul<3>(Q, sgn, J.b1, J.c1, isPos, X, a1);               // D_p^T W Q
-            if (isPos) {
-#pragma unroll
-                for (int i = 0; i < 18; i++) wadd[i] = a1[i];
-            } else {
-                // output slot: after the new (posID,f) block, skipping blocks folded into it
-                int w0 = M.wPtr[f], skip = 0;
-                for (int i = w0; i < j; i++) skip += (M.photo[i] == pid);
-                int o = O.wPtr[f] + 1 + (j - w0) - skip;
-                sm::store<18>(O.W + 18 * (size_t)o, a1);
-                O.photo[o] = p;
-                O.feature[o] = f;
-                jt_mul<3>(Q, -1.0, J.f2, J.g2, true, X, wadd);          // C_p^T W Q
-#pragma unroll
-                for (int r = 0; r < 6; r++)
-#pragma unroll
-                    for (int q = 0; q < 3; q++) G[6 * r + q] = -wadd[3 * r + q];
-            }
-            double a3[18];
-            sm::mm<6, 3, 3>(W, Tf, X);                                  // W T_f
-            jt_mul<3>(Q, sgn, J.b1, J.c1, isPos, X, a3);               // D_p^T W T_f
-            if (!isPos) {
-                double a4[18];
-                jt_mul<3>(Q, -1.0, J.f2, J.g2, true, X, a4);            // C_p^T W T_f
-#pragma unroll
-                for (int r = 0; r < 6; r++)
-#pragma unroll
-                    for (int q = 0; q < 3; q++) G[6 * r + 3 + q] = a4[3 * r + q];
-            }
-            // D_p^T W C_f = [-a1 | a3], oriented for slot p: as is (p<pid), transposed (p>pid), X+X^T (p==pid)
-#pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-                for (int q = 0; q < 6; q++) {
-                    double xrq = (q < 3) ? -a1[3 * r + q] : a3[3 * r + q - 3];
-                    if (p < pid) A3[6 * r + q] = xrq;
-                    else if (p > pid) A3[6 * q + r] = xrq;
-                    else { A3[6 * r + q] += xrq; A3[6 * q + r] += xrq; }
-                }
-        }
-        // ---- W'(pos,f) += sum over the feature's blocks: warp-segmented reduction by feature ----
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            int okey = __shfl_down_sync(0xffffffffu, gf, off);
-            bool take = (lane + off < 32) && (okey == gf);
-#pragma unroll
-            for (int i = 0; i < 18; i++) {
-                double ov = __shfl_down_sync(0xffffffffu, wadd[i], off);
-                if (take) wadd[i] += ov;
-            }
-        }
-        {
-            int pkey = __shfl_up_sync(0xffffffffu, gf, 1);
-            bool head = live && (lane == 0 || pkey != gf);
-            if (head) {
-                double *wp = O.W + 18 * (size_t)O.wPtr[f];
-#pragma unroll
-                for (int i = 0; i < 18; i++) atomicAdd(wp + i, wadd[i]);
-            }
-        }
-        // ---- U'(pos,pos) += G + G^T: warp sum when the whole warp is in one map ----
-        {
-            int k0 = __shfl_sync(0xffffffffu, live ? k : -1, 0);
-            bool uni = __all_sync(0xffffffffu, !live || k == k0) && k0 >= 0;
-            if (uni) {
-                int slot = -1;
-                if (lane == 0) slot = tw_hash_slot(hkeys, posePre[k0] + tc[k0].posID);
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-#pragma unroll
-                for (int r = 0; r < 6; r++)
-#pragma unroll
-                    for (int q = r; q < 6; q++) {
-                        double s = sm::warp_sum(G[6 * r + q] + G[6 * q + r]);
-                        if (lane == 0) {
-                            if (slot >= 0) {
-                                atomicAdd(&hvals[slot][6 * r + q], s);
-                                if (q != r) atomicAdd(&hvals[slot][6 * q + r], s);
-                            } else {
-                                double *u = out[k0].U + 36 * (size_t)tc[k0].posID;
-                                atomicAdd(u + 6 * r + q, s);
-                                if (q != r) atomicAdd(u + 6 * q + r, s);
-                            }
-                        }
-                    }
-            } else if (live) {
-                double *u = O.U + 36 * (size_t)pid;
-#pragma unroll
-                for (int r = 0; r < 6; r++)
-#pragma unroll
-                    for (int q = 0; q < 6; q++) atomicAdd(u + 6 * r + q, G[6 * r + q] + G[6 * q + r]);
-            }
-        }
-        // ---- U'(p,pos) += A3 through the CTA's pose hash ----
-        if (live) {
-            int slot = tw_hash_slot(hkeys, posePre[k] + p);
-            if (slot >= 0) {
-#pragma unroll
-                for (int i = 0; i < 36; i++) atomicAdd(&hvals[slot][i], A3[i]);
-            } else {
-                double *u = O.U + 36 * (size_t)p;
-#pragma unroll
-                for (int i = 0; i < 36; i++) atomicAdd(u + i, A3[i]);
-            }
-        }
-    }
-    __syncthreads();
-    // flush: one global atomic per accumulated value
-    for (int e = tid; e < TW_HASH * 36; e += TW_THREADS) {
-        int slot = e / 36, i = e - 36 * slot;
-        int key = hkeys[slot];
-        if (key < 0) continue;
-        int k = seg_find(posePre, K, key);
-        atomicAdd(out[k].U + 36 * (size_t)(key - posePre[k]) + i, hvals[slot][i]);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// v3 (default): the pose-major sums are taken out of the block-major kernel.
+// the pose-major sums are taken out of the block-major kernel.
 //   U'(p,pos) and the W part of U'(pos,pos) only need, per pose p,
 //       SW_p = sum_f W_pf          SWT_p = sum_f W_pf T_f            (two 6x3 sums)
 //   because D_p / C_p / Q factor out of the sums:
@@ -1038,12 +706,8 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
                                                      tc.p, pj.p, uScan.p); nl++;
     }
     if (A.totFeat > 0) {
-        static const bool tf_v1 = getenv("LSFM_TF_V1") != nullptr;
         static const bool tf_v3 = getenv("LSFM_TF_V3") != nullptr;
-        if (tf_v1) {
-            k_wvcong<<<ceil_div(A.totFeat, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dFeatPre.p, A.dPosePre.p, K,
-                                                             A.totFeat, tc.p, pj.p, fScan.p); nl++;
-        } else if (!tf_v3) {
+        if (!tf_v3) {
             // default: one pass over W, CTA per chunk of consecutive features (transform_chunk.cuh)
             std::vector<tfc::Chunk> chunks;
             int maxWords = 1;
@@ -1084,14 +748,10 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
             k_tf_posefin<<<ceil_div(A.totPose, 128), 128, 0, s>>>(B.d.p, A.dPosePre.p, K, A.totPose, tc.p, pj.p,
                                                                  poseAcc.p); nl++;
         } else {
-            static const bool tf_v2 = getenv("LSFM_TF_V2") != nullptr;
             DevBuf<double> TfBuf(9 * (size_t)A.totFeat, s);
             k_tf_featprep<<<ceil_div(A.totFeat, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dFeatPre.p, K, A.totFeat,
                                                                   tc.p, fScan.p, TfBuf.p); nl++;
-            if (A.totW > 0 && tf_v2) {
-                k_tf_wblock<<<ceil_div(A.totW, TW_THREADS * TW_TILES), TW_THREADS, 0, s>>>(
-                    A.d.p, B.d.p, A.dWPre.p, A.dFeatPre.p, A.dPosePre.p, K, A.totW, tc.p, pj.p, TfBuf.p); nl++;
-            } else if (A.totW > 0) {
+            if (A.totW > 0) {
                 const int totW = A.totW, totP = A.totPose;
                 DevBuf<int> sortKey(totW, s), sortVal(totW, s), sortedKey(totW, s), sortedVal(totW, s);
                 k_tf_wblock3<<<ceil_div(totW, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dWPre.p, A.dFeatPre.p,
