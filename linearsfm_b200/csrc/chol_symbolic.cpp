@@ -65,10 +65,11 @@ void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm
             uncovered += c;
         }
         uncovered /= 2;
-        std::vector<int> sep;
+        std::vector<int> sep, cand;              // only endpoints of cross edges can enter the cover
+        for (int v : L) if (cnt[v] > 0) cand.push_back(v);
         while (uncovered > 0) {
             int best = -1, bc = 0;
-            for (int v : L)
+            for (int v : cand)
                 if (cnt[v] > bc) { bc = cnt[v]; best = v; }     // ascending scan: ties keep the smallest index
             char other = side[best] == 1 ? 2 : 1;
             for (int p = ptr[best]; p < ptr[best + 1]; p++) {
@@ -134,7 +135,9 @@ void analyse_join(int m, const u64 *keys, int nk, JoinSym &J)
         int a = (int)((keys[i] >> 22) & M22), b = (int)(keys[i] & M22);
         if (a != b) { adj[fill[a]++] = b; adj[fill[b]++] = a; }
     }
-    for (int v = 0; v < m; v++) std::sort(adj.begin() + ptr[v], adj.begin() + ptr[v + 1]);
+    // the keys are sorted by (row, col) with row <= col: vertex v first receives its smaller
+    // neighbours (rows a < v, in ascending a), then the larger ones (row v, ascending col) -- every
+    // adjacency list is already ascending, no sort needed
     lsfm_nd_order(m, ptr.data(), adj.data(), J.perm, J.nodes);
     if ((int)J.perm.size() != m) throw std::runtime_error("ordering lost vertices");
     J.iperm.assign(m, 0);
