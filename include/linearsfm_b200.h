@@ -148,6 +148,30 @@ int lsfm_save_outputs(const lsfm_map *m, const char *state_path, const char *pos
  *   -path <dir> -num <N> -type {Monocular|Stereo} [-p <pose>] [-f <feature>] [-st <state>] [-help] */
 int lsfm_cli_main(int argc, char **argv);
 
+/* ---- local-map builder -----------------------------------------------------
+ * The step UPSTREAM of the reference: LinearSFM starts from finished localmap_*.txt files (DOC p.1,
+ * "initial reconstructions"), there is no reference interface to replace.  One local map = two
+ * consecutive stereo frames; conventions follow LinearSFMImp.cpp:132-143 (X_cam = R (X - t),
+ * R = Rx(gamma) Ry(beta) Rz(alpha)) and SURVEY Appendix A: map frame = first frame, state = pose of
+ * the second frame + landmarks, camera along +x (y left, z up), right camera at y = -baseline,
+ * measurement (uL, vL, uR) = (cx - f y/x, cy - f z/x, cx - f (y+b)/x).                           */
+typedef struct lsfm_stereo_pair {
+    int Ref;               /* pose id of the first frame (the map's frame; becomes lsfm_map.Ref)   */
+    int pose_id;           /* pose id of the second frame (state rows carry -pose_id)              */
+    int n;                 /* landmarks observed in both frames                                     */
+    const int *feat_id;    /* [n]  landmark ids (> 0)                                               */
+    const double *z0;      /* [3n] (uL, vL, uR) in the first frame                                  */
+    const double *z1;      /* [3n] (uL, vL, uR) in the second frame                                 */
+    const double *pose0;   /* [6]  initial guess of the second frame's pose in the first frame      */
+    const double *X0;      /* [3n] initial landmark positions, or NULL: triangulated from z0        */
+} lsfm_stereo_pair;
+typedef struct lsfm_stereo_cam { double f, baseline, cx, cy, sigma; } lsfm_stereo_cam;
+/* Gauss-Newton two-view bundle adjustment of every pair (one CTA per pair, one launch), stopping
+ * when max|d pose| < tol or after max_iters; out[k] is the local map (m = 1, nU = 1, nW = n) with
+ * the information blocks evaluated at the estimate.  iters_done[K] may be NULL.                   */
+int lsfm_build_localmaps_stereo(const lsfm_stereo_pair *pairs, int num, const lsfm_stereo_cam *cam,
+                                int max_iters, double tol, lsfm_map *out, int *iters_done);
+
 #ifdef __cplusplus
 }
 #endif

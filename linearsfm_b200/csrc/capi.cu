@@ -3,6 +3,7 @@
 #include "mapio.h"
 #include "scheduler.h"
 #include "chol_symbolic.h"
+#include "builder.h"
 #include <cstring>
 #include <sstream>
 #include <algorithm>
@@ -283,6 +284,15 @@ int lsfm_block_ordering(int m, const int *Ap, const int *Ai, int *perm)
     } catch (const std::exception &e) {
         return fail(LSFM_ERR_ARG, e.what());
     }
+}
+
+int lsfm_build_localmaps_stereo(const lsfm_stereo_pair *pairs, int num, const lsfm_stereo_cam *cam,
+                                int max_iters, double tol, lsfm_map *out, int *iters_done)
+{
+    return guarded([&] {
+        if (!pairs || !cam || !out || num < 0) throw LsfmError(LSFM_ERR_ARG, "builder: null argument");
+        build_localmaps_stereo(*g_ctx, pairs, num, *cam, max_iters, tol, out, iters_done);
+    });
 }
 
 int lsfm_run_stereo(const lsfm_map *maps, int num, lsfm_map *out)
