@@ -1,6 +1,6 @@
 """Stereo local-map builder: ctypes mirror of lsfm_build_localmaps_stereo and a
 seeded generator of the raw stereo observations it consumes.  The numpy twin used as the checker
-lives in oracle/builder_ref.py (no reference code exists for this step: parity unpinned)."""
+lives under oracle/ (no reference code exists for this step: parity unpinned); nothing here imports it."""
 from __future__ import annotations
 
 import ctypes as C

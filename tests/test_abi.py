@@ -44,4 +44,4 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "ref_oracle" not in txt and "oracle/_ref" not in txt and "libref_" not in txt, f
+                assert "ref_oracle" not in txt and "oracle/_ref" not in txt and "libref_" not in txt and "builder_ref" not in txt, f
