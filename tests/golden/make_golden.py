@@ -68,3 +68,22 @@ def main_mono():
 
 if __name__ == "__main__":
     main_mono()
+
+
+def main_root_pattern():
+    """Block pattern (upper CSC, as the reference hands it to cholmod_amd, LinearSFMImp.cpp:2529-2549)
+    of the reduced camera system of the ROOT join of the 3499-map headline scene, captured from the
+    reference through the shim (~1 minute of CPU)."""
+    ro.build()
+    maps = synth.make_stereo_scene(3499, feats_per_frame=128)
+    ro.capture_enable(True)
+    ro.run_tree_stereo(maps)
+    c = ro.capture()
+    ro.capture_enable(False)
+    np.savez_compressed(os.path.join(HERE, "root_pattern_3499.npz"), Ap=c["Ap"].astype(np.int32),
+                        Ai=c["Ai"].astype(np.int32))
+    print("wrote root_pattern_3499.npz m", c["m"], "blocks", len(c["Ai"]))
+
+
+if __name__ == "__main__" and "--root-pattern" in __import__("sys").argv:
+    main_root_pattern()

@@ -46,3 +46,17 @@ def test_ordering_random(oracle, m, dens):
     pairs = [(i, j) for i in range(m) for j in range(i + 1, m) if mask[i, j]]
     Ap, Ai = upper_csc(m, pairs)
     assert np.array_equal(api.block_ordering(Ap, Ai), oracle.shim_order(Ap, Ai))
+
+
+def test_ordering_on_the_headline_root_pattern(oracle):
+    """The block pattern of the reduced camera system of the ROOT join of the 3499-map headline scene
+    (captured from the reference through the shim, tests/golden/root_pattern_3499.npz: m = 3499,
+    50,115 blocks): the product's ordering equals the oracle's bit for bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "root_pattern_3499.npz"))
+    Ap, Ai = g["Ap"], g["Ai"]
+    assert Ap.shape[0] == 3500 and int(Ap[-1]) == 50115
+    p_ref = oracle.shim_order(Ap, Ai)
+    p_got = api.block_ordering(Ap, Ai)
+    assert sorted(p_got.tolist()) == list(range(3499))
+    assert np.array_equal(p_got, p_ref)
