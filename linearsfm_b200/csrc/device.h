@@ -170,6 +170,7 @@ struct Context {
     struct Pinned {
         char *p = nullptr;
         size_t cap = 0;
+        ~Pinned() { if (p) cudaFreeHost(p); }
         char *need(size_t bytes)
         {
             if (bytes > cap) {
