@@ -436,7 +436,7 @@ __global__ void k_front_rhs(const int *__restrict__ poseSn, const int *__restric
 // is staged in shared memory, factored there (6x6 diagonal blocks by one warp, row solves and the
 // in-panel updates by the whole CTA), applied ONCE to everything right of it in global memory
 // (left-looking rank-pc update, panel read from shared memory) and written back.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
                const int *__restrict__ childIdx, const int *__restrict__ relIdx,
                double *__restrict__ fronts, int *__restrict__ errflag, int pcMax)
@@ -631,7 +631,7 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
 // triangular solve is latency-bound: shared memory instead of L2 for every step).
 constexpr int BS_PC = 48;
 constexpr int BS_TS = BS_PC + 1;      // padded stride: a lane walks a ROW of the column-major triangle
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
                   const int *__restrict__ structIdx, const double *__restrict__ fronts,
                   double *__restrict__ xperm)
@@ -957,7 +957,10 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     for (int l = 0; l < nLevels; l++) {
         int cnt = sym.levelPtr[l + 1] - sym.levelPtr[l];
         if (cnt == 0) continue;
-        k_front_factor<<<cnt, 256, shf, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p, pcMax); nl++;
+        // few fronts on the level (the top of the assembly tree): twice the threads per front --
+        // the SMs are idle anyway and the extend-add / trailing update scale with the warps
+        const int thr = (cnt <= ctx.num_sms) ? 512 : 256;
+        k_front_factor<<<cnt, thr, shf, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p, pcMax); nl++;
     }
     size_t shb = sizeof(double) * (6 * (size_t)(sym.maxFdim + 1) + BS_PC * BS_TS);
     if (shb > 48 * 1024)
@@ -965,7 +968,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     for (int l = nLevels - 1; l >= 0; l--) {
         int cnt = sym.levelPtr[l + 1] - sym.levelPtr[l];
         if (cnt == 0) continue;
-        k_front_backsolve<<<cnt, 256, shb, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dStruct.p, fronts.p, xperm.p); nl++;
+        const int thr = (cnt <= ctx.num_sms) ? 512 : 256;
+        k_front_backsolve<<<cnt, thr, shb, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dStruct.p, fronts.p, xperm.p); nl++;
     }
     k_unpermute<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(J.d.p, J.dPosePre.p, K, J.totPose, dPerm.p, xperm.p); nl++;
     // the not-SPD flag is sticky in the context and checked once per API call (no sync here)
