@@ -142,6 +142,12 @@ int lsfm_load_localmap_stereo(const char *path, lsfm_map *out);
 /* lmj_readInformationMono (LinearSFMImp.cpp:6660-6754): header `Ref ScaP Fix Sign r`           */
 int lsfm_load_localmap_mono(const char *path, lsfm_map *out);
 /* lmj_SaveStateVector (2102-2117) and lmj_SavePoses_3DPF (7876-7967); NULL = skip              */
+/* Writes a map (state + block information) in the reference's localmap_<i>.txt format (the format
+ * lmj_readInformationStereo / lmj_readInformationMono parse, LinearSFMImp.cpp:3044-3132, 6660-6754),
+ * doubles with 17 significant digits.  The reference has no writer for it (it frees the joined map,
+ * LinearSFMImp.cpp:2081-2096); this is SURVEY 8(f)-3: the final information matrix as an output, so
+ * that a joined map can be joined again later.  CLI: -map <file>.                                  */
+int lsfm_save_localmap(const lsfm_map *m, const char *path, int mono);
 int lsfm_save_outputs(const lsfm_map *m, const char *state_path, const char *pose_path,
                       const char *feature_path);
 /* CLinearSFMImp::run(argc, argv) (LinearSFMImp.cpp:7972-8106): same flags

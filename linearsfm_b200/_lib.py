@@ -40,7 +40,7 @@ EXPORTS = [
     "lsfm_tree_result_shape", "lsfm_tree_download", "lsfm_tree_download_state", "lsfm_tree_set_maps",
     "lsfm_tree_free", "lsfm_tree_last_solve_ms", "lsfm_tree_adopt_result", "lsfm_tree_append_maps",
     "lsfm_tree_reset", "lsfm_map_device_bytes", "lsfm_tree_export_device", "lsfm_tree_append_device",
-    "lsfm_load_localmap_stereo", "lsfm_save_outputs", "lsfm_cli_main", "lsfm_build_localmaps_stereo",
+    "lsfm_load_localmap_stereo", "lsfm_save_outputs", "lsfm_cli_main", "lsfm_build_localmaps_stereo", "lsfm_save_localmap",
 ]
 
 _lib = None

@@ -125,6 +125,41 @@ int lsfm_load_localmap_mono(const char *path, lsfm_map *out)
     return load_map_impl(path, out, g_io_err, true);
 }
 
+int lsfm_save_localmap(const lsfm_map *M, const char *path, int mono)
+{
+    // the reference's localmap_<i>.txt format (readers LinearSFMImp.cpp:3044-3132,
+    // 6660-6754), doubles with 17 significant digits so they survive fscanf("%lf") bit for bit
+    FILE *fp = fopen(path, "w");
+    if (!fp) { g_io_err = std::string("cannot open ") + path; return LSFM_ERR_IO; }
+    std::vector<char> buf(1 << 20);
+    setvbuf(fp, buf.data(), _IOFBF, buf.size());
+    if (mono) fprintf(fp, "%d %d %d %d\n%d\n", M->Ref, M->ScaP, M->Fix, M->Sign, M->r);
+    else fprintf(fp, "%d\n%d\n", M->Ref, M->r);
+    for (int i = 0; i < M->r; i++) fprintf(fp, "%d %.17g\n", M->stno[i], M->stVal[i]);
+    fprintf(fp, "%d %d\n%d\n", M->m, M->n, M->nU);
+    auto doubles = [&](const double *x, size_t cnt, int per_line) {
+        for (size_t i = 0; i < cnt; i++) fprintf(fp, "%.17g%c", x[i], ((i + 1) % per_line == 0 || i + 1 == cnt) ? '\n' : ' ');
+        if (cnt == 0) fputc('\n', fp);
+    };
+    auto ints = [&](const int *x, size_t cnt) {
+        for (size_t i = 0; i < cnt; i++) fprintf(fp, "%d%c", x[i], (i + 1 == cnt) ? '\n' : ' ');
+        if (cnt == 0) fputc('\n', fp);
+    };
+    doubles(M->U, 36 * (size_t)M->nU, 6);
+    ints(M->Ui, M->nU);
+    ints(M->Uj, M->nU);
+    fprintf(fp, "%d\n", M->nW);
+    doubles(M->W, 18 * (size_t)M->nW, 3);
+    ints(M->photo, M->nW);
+    ints(M->feature, M->nW);
+    doubles(M->V, 9 * (size_t)M->n, 3);
+    ints(M->FBlock, M->n);
+    bool ok = !ferror(fp);
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok) { g_io_err = std::string("write failed: ") + path; return LSFM_ERR_IO; }
+    return LSFM_OK;
+}
+
 int lsfm_save_outputs(const lsfm_map *M, const char *st, const char *pose, const char *feat)
 {
     if (st) {
@@ -163,7 +198,7 @@ int lsfm_save_outputs(const lsfm_map *M, const char *st, const char *pose, const
 
 int lsfm_cli_main(int argc, char **argv)
 {
-    std::string path, st, pose, feat, type;
+    std::string path, st, pose, feat, type, mapout;
     int num = 0;
     bool hasPath = false, hasNum = false, hasType = false;
     for (int i = 1; i < argc; i++) {
@@ -177,6 +212,7 @@ int lsfm_cli_main(int argc, char **argv)
         else if (name == "st") arg(st);
         else if (name == "p") arg(pose);
         else if (name == "f") arg(feat);
+        else if (name == "map") arg(mapout);          // extension: the joined map (state + information) in localmap format
         else if (name == "num") { std::string v; arg(v); num = atoi(v.c_str()); hasNum = true; }
         else if (name == "type") {
             std::string v; arg(v);
@@ -219,6 +255,7 @@ int lsfm_cli_main(int argc, char **argv)
         for (auto &m : maps) lsfm_free_map(&m);
         if (!st.empty()) lsfm_save_outputs(&outm, st.c_str(), nullptr, nullptr);
         if (!pose.empty() && !feat.empty()) lsfm_save_outputs(&outm, nullptr, pose.c_str(), feat.c_str());
+        if (!mapout.empty()) lsfm_save_localmap(&outm, mapout.c_str(), 1);
         lsfm_free_map(&outm);
         return 0;
     }
@@ -241,6 +278,7 @@ int lsfm_cli_main(int argc, char **argv)
     if (!st.empty()) lsfm_save_outputs(&out, st.c_str(), nullptr, nullptr);
     if (!pose.empty() && !feat.empty())                     // both required, LinearSFMImp.cpp:2078
         lsfm_save_outputs(&out, nullptr, pose.c_str(), feat.c_str());
+    if (!mapout.empty()) lsfm_save_localmap(&out, mapout.c_str(), 0);
     lsfm_free_map(&out);
     return 0;
 }

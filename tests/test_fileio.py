@@ -60,3 +60,20 @@ def test_mono_reader_matches_reference(oracle, tmp_path):
         assert_maps_match(got, ref, tol_state=0, tol_info=0, what="mono reader")
         for k in ("ScaP", "Fix", "Sign", "FScaP", "FFix"):
             assert getattr(got, k) == getattr(ref, k) == getattr(lm, k), k
+
+
+def test_localmap_writer_is_read_back_by_the_reference(oracle, tmp_path):
+    # lsfm_save_localmap (the joined map with its information matrix as an output):
+    # the REFERENCE's own reader (fscanf) and ours get every number back bit for bit
+    maps = synth.make_stereo_scene(4, feats_per_frame=12, seed=6)
+    joined, _, _ = oracle.run_tree_stereo(maps)            # a map with several poses and W fill-in
+    for k, lm in enumerate([maps[0], joined]):
+        p = str(tmp_path / f"out_{k}.txt")
+        c, keep = api.to_c(lm)
+        _lib.check(_lib.lib().lsfm_save_localmap(C.byref(c), p.encode(), C.c_int(0)))
+        ref = oracle.load_localmap_stereo(p)
+        assert_maps_match(ref, lm, tol_state=0, tol_info=0, what="reference reads our localmap file")
+        out = _lib.LsfmMap()
+        _lib.check(_lib.lib().lsfm_load_localmap_stereo(p.encode(), C.byref(out)))
+        assert_maps_match(api.from_c(out), lm, tol_state=0, tol_info=0, what="our reader, our writer")
+    assert _lib.lib().lsfm_save_localmap(C.byref(c), str(tmp_path / "no_dir" / "x.txt").encode(), C.c_int(0)) == 5

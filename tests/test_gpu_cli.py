@@ -54,3 +54,22 @@ def test_cli_errors(gpu):
     assert r.returncode == 0 and "Please Input Right File Path" in r.stdout
     r = subprocess.run([_lib.CLI_PATH, "-help"], capture_output=True, text=True)
     assert "Linear SFM Solution General Options" in r.stdout
+
+
+def test_cli_map_output_can_be_joined_again(gpu, oracle, tmp_path):
+    # -map <file> (extension): the joined map with its information matrix in the
+    # reference's own localmap format -- the reference's reader gets back exactly what the tree computed
+    from linearsfm_b200 import api
+    from util import assert_maps_match
+    import tempfile
+    maps = synth.make_stereo_scene(6, 12, seed=32)
+    d = tempfile.mkdtemp(prefix="lsfm", dir="/tmp")
+    for i, lm in enumerate(maps):
+        write_localmap(os.path.join(d, f"localmap_{i + 1}.txt"), lm)
+    mp = os.path.join(d, "joined_map.txt")
+    r = subprocess.run([_lib.CLI_PATH, "-path", d, "-num", "6", "-type", "Stereo", "-map", mp],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and os.path.exists(mp), r.stderr
+    got = oracle.load_localmap_stereo(mp)                       # read by the REFERENCE's parser
+    ref, _, _ = oracle.run_tree_stereo(maps)
+    assert_maps_match(got, ref, tol_state=1e-8, tol_info=1e-8, what="-map output vs reference tree")
