@@ -77,3 +77,26 @@ def test_localmap_writer_is_read_back_by_the_reference(oracle, tmp_path):
         _lib.check(_lib.lib().lsfm_load_localmap_stereo(p.encode(), C.byref(out)))
         assert_maps_match(api.from_c(out), lm, tol_state=0, tol_info=0, what="our reader, our writer")
     assert _lib.lib().lsfm_save_localmap(C.byref(c), str(tmp_path / "no_dir" / "x.txt").encode(), C.c_int(0)) == 5
+
+
+def test_parallel_writers_byte_identical_on_a_large_map(oracle, tmp_path):
+    # the multi-threaded formatting path (>= 20000 rows) against the reference's fprintf loops: same bytes,
+    # including a repeated landmark id (the last occurrence wins, std::map semantics of 7907/7925),
+    # a huge value, a negative zero and a value that rounds to 0.000001
+    from linearsfm_b200.localmap import LocalMap
+    m, n = 300, 40000
+    rng = np.random.default_rng(0)
+    ids = rng.permutation(n) + 1
+    ids[1000] = ids[5]
+    stno = np.concatenate([np.repeat(-np.arange(2, m + 2), 6), np.repeat(ids, 3)]).astype(np.int32)
+    stVal = rng.normal(0, 50, 6 * m + 3 * n)
+    stVal[7], stVal[8], stVal[9] = 1e300, -0.0, 5e-7
+    lm = LocalMap(Ref=1, stno=stno, stVal=stVal, m=m, n=n, U=np.zeros((1, 6, 6)), Ui=[0], Uj=[0],
+                  W=np.zeros((1, 6, 3)), photo=[0], feature=[0], V=np.zeros((n, 3, 3)), FBlock=np.zeros(n, np.int32))
+    c, keep = api.to_c(lm)
+    got = {k: str(tmp_path / f"got_{k}.txt") for k in ("st", "p", "f")}
+    ref = {k: str(tmp_path / f"ref_{k}.txt") for k in ("st", "p", "f")}
+    _lib.check(_lib.lib().lsfm_save_outputs(C.byref(c), got["st"].encode(), got["p"].encode(), got["f"].encode()))
+    oracle.save_outputs(lm, st=ref["st"], pose=ref["p"], feat=ref["f"])
+    for k in got:
+        assert filecmp.cmp(got[k], ref[k], shallow=False), k
