@@ -311,8 +311,21 @@ int lsfm_cli_main(int argc, char **argv)
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     printf("Total Used Time:  %lf  sec\n\n", sec);          // LinearSFMImp.cpp:2072
     lsfm_map out;
-    if (lsfm_tree_download(tree, 0, &out) != LSFM_OK) {
-        fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+    if (!mapout.empty()) {
+        if (lsfm_tree_download(tree, 0, &out) != LSFM_OK) {
+            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+        }
+    } else {
+        // the reference's outputs only need the state vector: 12 bytes per row come back from the
+        // device instead of the whole information matrix (~1 GB of W blocks at the NC3500 size)
+        if (lsfm_tree_result_shape(tree, 0, &out) != LSFM_OK) {
+            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+        }
+        out.stno = (int *)malloc(sizeof(int) * (size_t)std::max(out.r, 1));
+        out.stVal = (double *)malloc(sizeof(double) * (size_t)std::max(out.r, 1));
+        if (lsfm_tree_download_state(tree, 0, out.stno, out.stVal) != LSFM_OK) {
+            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+        }
     }
     lsfm_tree_free(tree);
     if (!st.empty()) lsfm_save_outputs(&out, st.c_str(), nullptr, nullptr);
