@@ -35,7 +35,7 @@ def test_pack_roundtrip():
     assert (got.Ref, got.FRef, got.m, got.n) == (lm.Ref, lm.FRef, lm.m, lm.n)
 
 
-@pytest.mark.parametrize("world,n", [(2, 5), (2, 8), (2, 11), (4, 7), (4, 13)])
+@pytest.mark.parametrize("world,n", [(2, 5), (2, 8), (2, 11), (4, 7), (4, 13), (4, 5), (8, 27)])   # the last two leave a rank without maps (like 3499 maps on 8 GPUs)
 def test_sharded_schedule_matches_sequential(oracle, tmp_path, world, n):
     out = str(tmp_path / "fin.npz")
     port = free_port()
