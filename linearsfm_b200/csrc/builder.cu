@@ -260,7 +260,7 @@ void build_localmaps_stereo(Context &ctx, const lsfm_stereo_pair *pairs, int K, 
     for (int k = 0; k < K; k++)
         if (hStatus[k])
             throw LsfmError(LSFM_ERR_NOT_SPD, "builder: pose system of pair " + std::to_string(k) + " is not positive definite");
-    auto A_ = [](size_t n, size_t sz) { return malloc((n * sz) ? (n * sz) : 1); };
+    auto A_ = [](size_t n, size_t sz) { return malloc((n * sz) != 0 ? (n * sz) : 1); };
     for (int k = 0; k < K; k++) {
         const int n = pairs[k].n;
         const size_t o = (size_t)featPre[k];

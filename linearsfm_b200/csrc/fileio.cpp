@@ -65,7 +65,7 @@ int load_map_impl(const char *path, lsfm_map *M, std::string &err, bool mono)
     }
     M->r = (int)t.next_int();
     if (t.fail || M->r < 0) { err = std::string(path) + ": bad header"; return LSFM_ERR_FORMAT; }
-    auto A = [](size_t n, size_t s) { return malloc((n * s) ? (n * s) : 1); };
+    auto A = [](size_t n, size_t s) { return malloc((n * s) != 0 ? (n * s) : 1); };
     M->stno = (int *)A(M->r, sizeof(int));
     M->stVal = (double *)A(M->r, sizeof(double));
     for (int i = 0; i < M->r; i++) { M->stno[i] = (int)t.next_int(); M->stVal[i] = t.next_dbl(); }

@@ -176,7 +176,7 @@ static void alloc_host_map(lsfm_map *o, const DMap &d)
     o->Ref = d.Ref; o->FRef = d.FRef; o->m = d.m; o->n = d.n; o->nU = d.nU; o->nW = d.nW;
     o->r = 6 * d.m + 3 * d.n;
     o->ScaP = d.ScaP; o->Fix = d.Fix; o->Sign = d.Sign; o->FScaP = d.FScaP; o->FFix = d.FFix;
-    auto A = [](size_t n, size_t sz) { return malloc((n * sz) ? (n * sz) : 1); };
+    auto A = [](size_t n, size_t sz) { return malloc((n * sz) != 0 ? (n * sz) : 1); };
     o->stno = (int *)A(o->r, sizeof(int));
     o->stVal = (double *)A(o->r, sizeof(double));
     o->U = (double *)A(36 * (size_t)d.nU, sizeof(double));
