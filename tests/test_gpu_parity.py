@@ -81,7 +81,7 @@ def test_tree_slow_paths(gpu, oracle, env):
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     e = dict(os.environ); e.update(env)
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_tree.py"), "37", "30"],
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "check_tree.py"), "37", "30"],
                        env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 

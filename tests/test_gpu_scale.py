@@ -4,7 +4,7 @@ Integer arrays (state labels, block lists, S pattern order) must match the oracl
 size.  Floating point: the reference's stereo chain is well conditioned up to a few hundred maps
 (1e-15 relative input noise moves its own final state by ~1e-9), but on the NC3500-shape synthetic
 scene the same perturbation moves the REFERENCE's result by 3e-6 at 1200 maps and 1.6e-3 at 3499 maps
-(tools/ref_sensitivity.py).  The 1e-6 bar of BASELINE.json is therefore asserted
+(tests/tools/ref_sensitivity.py).  The 1e-6 bar of BASELINE.json is therefore asserted
 directly where it is meaningful (466 maps) and relative to the reference's own sensitivity beyond.
 """
 import copy

@@ -1,7 +1,7 @@
 """Run one stereo merge tree on the GPU and compare with the oracle (used by tests that need a fresh
 process, e.g. with LSFM_FORCE_OVERFLOW=1 / LSFM_TF_V3=1 which are read once per process)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from linearsfm_b200 import api, synth  # noqa: E402
 import ref_oracle as ro  # noqa: E402

@@ -1,7 +1,7 @@
 """Developer script: mono merge tree at RS90 / RS468 sizes, GPU vs oracle."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from linearsfm_b200 import api, synth
 from linearsfm_b200.localmap import maps_equal_int

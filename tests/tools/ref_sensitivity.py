@@ -2,10 +2,10 @@
 on the scene and on a copy whose W blocks carry 1e-15 relative noise; print how far its own final
 state / information blocks move.  Measured here (seed of synth.make_stereo_scene, 128 landmarks/frame):
     N= 466: state 4.6e-09  N=1200: state 2.8e-06, U/W 7.9e-06     N=3499: state 1.6e-03, U/W 2.2e-03
-Usage: python tools/ref_sensitivity.py N [landmarks_per_frame]"""
+Usage: python tests/tools/ref_sensitivity.py N [landmarks_per_frame]"""
 import copy, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from linearsfm_b200 import synth  # noqa: E402
 import ref_oracle as ro  # noqa: E402

@@ -1,7 +1,7 @@
 """Developer script: raw stereo observations -> CUDA local-map builder -> merge tree, with timings."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np
 from linearsfm_b200 import api, builder
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 3499
