@@ -18,6 +18,10 @@ SolveDebug g_dbg;
 bool g_dbg_valid = false;
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
+} // namespace
+// the one error string lsfm_last_error() returns; file I/O (fileio.cpp) reports through it too
+void lsfm_set_error(const std::string &msg) { g_err = msg; }
+namespace {
 
 int ensure_ctx()
 {
@@ -68,6 +72,7 @@ int lsfm_init(int device)
         if (g_ctx && g_ctx->device == device) return LSFM_OK;
         if (g_ctx) lsfm_shutdown();
         CUDA_CHECK(cudaSetDevice(device));
+        DevicePool::get().set_device(device);
         Context *c = new Context();
         c->device = device;
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -92,6 +97,9 @@ void lsfm_shutdown(void)
 {
     if (!g_ctx) return;
     cudaStreamSynchronize(g_ctx->stream);
+    mapio_shutdown();                       // upload event / staging state belong to this device
+    g_ctx->release_error_flag();
+    DevicePool::get().release_cached();     // cached blocks of this device go back to the driver
     cudaEventDestroy(g_ctx->ev0);
     cudaEventDestroy(g_ctx->ev1);
     cudaStreamDestroy(g_ctx->stream);

@@ -14,9 +14,14 @@
 // context lives; a merge-tree solve repeats the same size sequence, so after the first solve no
 // cudaMalloc is issued at all.  (cudaMallocAsync showed 2x run-to-run variation of the whole solve.)
 struct DevicePool {
-    std::multimap<size_t, void *> free_;
-    std::map<void *, size_t> live_;
+    // cached and live blocks carry the device they were allocated on: after lsfm_init() switches to
+    // another GPU, blocks of the previous one are never handed out (and lsfm_shutdown drains the cache)
+    struct Live { size_t bytes; int dev; };
+    std::map<int, std::multimap<size_t, void *>> freeByDev_;
+    std::map<void *, Live> live_;
+    int dev_ = 0;                          // device of the current context
     size_t reserved = 0;
+    void set_device(int d) { dev_ = d; }
     static size_t round_up(size_t b)
     {
         if (b < 4096) return (b + 511) & ~(size_t)511;
@@ -27,11 +32,12 @@ struct DevicePool {
     void *alloc(size_t bytes)
     {
         size_t need = round_up(bytes ? bytes : 1);
+        std::multimap<size_t, void *> &free_ = freeByDev_[dev_];
         auto it = free_.lower_bound(need);
         // accept a cached block unless it wastes more than 25 % (+64 MB slack for the big arenas)
         if (it != free_.end() && it->first <= need + need / 4 + (need >= (1u << 26) ? (1u << 26) : 0)) {
             void *p = it->second;
-            live_[p] = it->first;
+            live_[p] = Live{it->first, dev_};
             free_.erase(it);
             return p;
         }
@@ -48,21 +54,23 @@ struct DevicePool {
                 throw LsfmError(LSFM_ERR_CUDA, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
         }
         reserved += need;
-        live_[p] = need;
+        live_[p] = Live{need, dev_};
         return p;
     }
     void free(void *p)
     {
         auto it = live_.find(p);
         if (it == live_.end()) return;
-        free_.insert({it->second, p});
+        freeByDev_[it->second.dev].insert({it->second.bytes, p});
         live_.erase(it);
     }
     void release_cached()
     {
         cudaDeviceSynchronize();
-        for (auto &kv : free_) { cudaFree(kv.second); reserved -= kv.first; }
-        free_.clear();
+        for (auto &dv : freeByDev_) {
+            for (auto &kv : dv.second) { cudaFree(kv.second); reserved -= kv.first; }
+            dv.second.clear();
+        }
     }
     static DevicePool &get()
     {
@@ -182,6 +190,18 @@ struct Context {
         }
     } pinDown;
 
+    // largest dynamic shared-memory size already granted per kernel on THIS context's device
+    std::map<const void *, size_t> smemGranted;
+    void ensure_smem(const void *func, size_t bytes)
+    {
+        if (bytes <= 48 * 1024) return;
+        size_t &g = smemGranted[func];
+        if (bytes > g) {
+            CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            g = bytes;
+        }
+    }
+
     // sticky device-side error flag (bit 0: non-positive pivot in the Cholesky); read by check_errors()
     int *d_err = nullptr;
     int *error_flag()
@@ -191,6 +211,11 @@ struct Context {
             CUDA_CHECK(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
         }
         return d_err;
+    }
+    void release_error_flag()
+    {
+        if (d_err) DevicePool::get().free(d_err);
+        d_err = nullptr;
     }
     void check_errors()
     {

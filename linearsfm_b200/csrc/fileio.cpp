@@ -18,9 +18,16 @@
 #include <chrono>
 #include <algorithm>
 
+void lsfm_set_error(const std::string &msg);          // capi.cu: the string lsfm_last_error() returns
+
 namespace {
 
-std::string g_io_err;
+// I/O errors of the single-map entry points go to lsfm_last_error(); the CLI's per-thread loaders keep
+// their own strings
+struct IoErr {
+    std::string s;
+    IoErr &operator=(const std::string &m) { s = m; lsfm_set_error(m); return *this; }
+} g_io_err;
 
 struct Tok {
     char *p, *end;
@@ -50,6 +57,10 @@ int load_map_impl(const char *path, lsfm_map *M, std::string &err, bool mono)
     fseek(f, 0, SEEK_END);
     long sz = ftell(f);
     fseek(f, 0, SEEK_SET);
+    if (sz < 0) { fclose(f); err = std::string("cannot determine the size of ") + path; return LSFM_ERR_IO; }
+    // every count in the file is bounded by the file size (each entry takes >= 2 bytes of text), so a
+    // corrupt header cannot trigger a huge allocation
+    const size_t maxCount = (size_t)sz / 2 + 1;
     std::vector<char> buf(sz + 1);
     size_t got = fread(buf.data(), 1, sz, f);
     fclose(f);
@@ -64,34 +75,38 @@ int load_map_impl(const char *path, lsfm_map *M, std::string &err, bool mono)
         M->Sign = (int)t.next_int();
     }
     M->r = (int)t.next_int();
-    if (t.fail || M->r < 0) { err = std::string(path) + ": bad header"; return LSFM_ERR_FORMAT; }
-    auto A = [](size_t n, size_t s) { return malloc((n * s) != 0 ? (n * s) : 1); };
+    if (t.fail || M->r < 0 || (size_t)M->r > maxCount) { err = std::string(path) + ": bad header"; M->r = 0; return LSFM_ERR_FORMAT; }
+    bool oom = false;
+    auto A = [&oom](size_t n, size_t s) { void *q = malloc((n * s) != 0 ? (n * s) : 1); if (!q) oom = true; return q; };
     M->stno = (int *)A(M->r, sizeof(int));
     M->stVal = (double *)A(M->r, sizeof(double));
+    if (oom) { err = std::string(path) + ": out of host memory"; lsfm_free_map(M); return LSFM_ERR_IO; }
     for (int i = 0; i < M->r; i++) { M->stno[i] = (int)t.next_int(); M->stVal[i] = t.next_dbl(); }
     M->m = (int)t.next_int();
     M->n = (int)t.next_int();
     M->nU = (int)t.next_int();
-    if (t.fail || M->m < 0 || M->n < 0 || M->nU < 0 || M->r != 6 * M->m + 3 * M->n) {
+    if (t.fail || M->m < 0 || M->n < 0 || M->nU < 0 || M->r != 6 * M->m + 3 * M->n || 36 * (size_t)M->nU > maxCount) {
         err = std::string(path) + ": inconsistent sizes"; lsfm_free_map(M); return LSFM_ERR_FORMAT;
     }
     M->U = (double *)A(36 * (size_t)M->nU, sizeof(double));
     M->Ui = (int *)A(M->nU, sizeof(int));
     M->Uj = (int *)A(M->nU, sizeof(int));
+    if (oom) { err = std::string(path) + ": out of host memory"; lsfm_free_map(M); return LSFM_ERR_IO; }
     for (size_t i = 0; i < 36 * (size_t)M->nU; i++) M->U[i] = t.next_dbl();
     for (int i = 0; i < M->nU; i++) M->Ui[i] = (int)t.next_int();
     for (int i = 0; i < M->nU; i++) M->Uj[i] = (int)t.next_int();
     M->nW = (int)t.next_int();
-    if (t.fail || M->nW < 0) { err = std::string(path) + ": bad nW"; lsfm_free_map(M); return LSFM_ERR_FORMAT; }
+    if (t.fail || M->nW < 0 || 18 * (size_t)M->nW > maxCount) { err = std::string(path) + ": bad nW"; lsfm_free_map(M); return LSFM_ERR_FORMAT; }
     M->W = (double *)A(18 * (size_t)M->nW, sizeof(double));
     M->photo = (int *)A(M->nW, sizeof(int));
     M->feature = (int *)A(M->nW, sizeof(int));
+    M->V = (double *)A(9 * (size_t)M->n, sizeof(double));
+    M->FBlock = (int *)A(M->n, sizeof(int));
+    if (oom) { err = std::string(path) + ": out of host memory"; lsfm_free_map(M); return LSFM_ERR_IO; }
     for (size_t i = 0; i < 18 * (size_t)M->nW; i++) M->W[i] = t.next_dbl();
     for (int i = 0; i < M->nW; i++) M->photo[i] = (int)t.next_int();
     for (int i = 0; i < M->nW; i++) M->feature[i] = (int)t.next_int();
-    M->V = (double *)A(9 * (size_t)M->n, sizeof(double));
     for (size_t i = 0; i < 9 * (size_t)M->n; i++) M->V[i] = t.next_dbl();
-    M->FBlock = (int *)A(M->n, sizeof(int));
     for (int i = 0; i < M->n; i++) M->FBlock[i] = (int)t.next_int();
     if (t.fail) { err = std::string(path) + ": truncated file"; lsfm_free_map(M); return LSFM_ERR_FORMAT; }
     return LSFM_OK;
@@ -118,12 +133,12 @@ extern "C" {
 
 int lsfm_load_localmap_stereo(const char *path, lsfm_map *out)
 {
-    return load_map_impl(path, out, g_io_err, false);
+    { std::string e; int rc = load_map_impl(path, out, e, false); if (rc != LSFM_OK) g_io_err = e; return rc; }
 }
 
 int lsfm_load_localmap_mono(const char *path, lsfm_map *out)
 {
-    return load_map_impl(path, out, g_io_err, true);
+    { std::string e; int rc = load_map_impl(path, out, e, true); if (rc != LSFM_OK) g_io_err = e; return rc; }
 }
 
 int lsfm_save_localmap(const lsfm_map *M, const char *path, int mono)
@@ -169,7 +184,7 @@ int lsfm_save_outputs(const lsfm_map *M, const char *st, const char *pose, const
     // NC3500 size (1.3 M feature rows) the single-threaded fprintf loop took 0.8 s, 20x the solve.
     auto write_rows = [&](const char *path, size_t nrows, const std::function<int(size_t, char *, size_t)> &fmt) -> int {
         FILE *fp = fopen(path, "w");
-        if (!fp) return LSFM_ERR_IO;
+        if (!fp) { g_io_err = std::string("cannot open ") + path; return LSFM_ERR_IO; }
         int nth = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
         if (nrows < 20000) nth = 1;
         const size_t per = (nrows + nth - 1) / std::max(nth, 1);
@@ -264,7 +279,7 @@ int lsfm_cli_main(int argc, char **argv)
     if (!hasType) { printf("LinerSFM Error: Please Set Data Type:\n"); return 0; }
     const bool mono = (type == "Monocular");
     if (num < 1) return 0;
-    if (lsfm_init(0) != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0; }
+    if (lsfm_init(0) != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1; }
 
     std::vector<lsfm_map> maps(num);
     std::vector<int> rc(num, LSFM_OK);
@@ -281,58 +296,63 @@ int lsfm_cli_main(int argc, char **argv)
     for (int t = 0; t < nth; t++) th.emplace_back(work, t);
     for (auto &t : th) t.join();
     for (int i = 0; i < num; i++)
-        if (rc[i] != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", errs[i].c_str()); return 0; }
+        if (rc[i] != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", errs[i].c_str()); return 1; }
 
     if (mono) {
         // CLinearSFMImp::runMono (LinearSFMImp.cpp:3136-3152)
         lsfm_map outm;
         auto tm0 = std::chrono::steady_clock::now();
         if (lsfm_run_mono_ex(maps.data(), num, 1, &outm) != LSFM_OK) {
-            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1;
         }
         double secm = std::chrono::duration<double>(std::chrono::steady_clock::now() - tm0).count();
         printf("Total Used Time:  %lf  sec\n\n", secm);        // LinearSFMImp.cpp:6639 (incl. H2D/D2H here)
         for (auto &m : maps) lsfm_free_map(&m);
-        if (!st.empty()) lsfm_save_outputs(&outm, st.c_str(), nullptr, nullptr);
-        if (!pose.empty() && !feat.empty()) lsfm_save_outputs(&outm, nullptr, pose.c_str(), feat.c_str());
-        if (!mapout.empty()) lsfm_save_localmap(&outm, mapout.c_str(), 1);
+        int wrc = LSFM_OK;
+        if (!st.empty()) wrc |= lsfm_save_outputs(&outm, st.c_str(), nullptr, nullptr);
+        if (!pose.empty() && !feat.empty()) wrc |= lsfm_save_outputs(&outm, nullptr, pose.c_str(), feat.c_str());
+        if (!mapout.empty()) wrc |= lsfm_save_localmap(&outm, mapout.c_str(), 1);
         lsfm_free_map(&outm);
+        if (wrc != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1; }
         return 0;
     }
     lsfm_tree *tree = nullptr;
     if (lsfm_tree_create_stereo(maps.data(), num, &tree) != LSFM_OK) {
-        fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+        fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1;
     }
     for (auto &m : maps) lsfm_free_map(&m);
     auto t0 = std::chrono::steady_clock::now();
     if (lsfm_tree_solve(tree, 1, 0, -1) != LSFM_OK) {
-        fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+        fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1;
     }
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     printf("Total Used Time:  %lf  sec\n\n", sec);          // LinearSFMImp.cpp:2072
     lsfm_map out;
     if (!mapout.empty()) {
         if (lsfm_tree_download(tree, 0, &out) != LSFM_OK) {
-            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1;
         }
     } else {
         // the reference's outputs only need the state vector: 12 bytes per row come back from the
         // device instead of the whole information matrix (~1 GB of W blocks at the NC3500 size)
         if (lsfm_tree_result_shape(tree, 0, &out) != LSFM_OK) {
-            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1;
         }
         out.stno = (int *)malloc(sizeof(int) * (size_t)std::max(out.r, 1));
         out.stVal = (double *)malloc(sizeof(double) * (size_t)std::max(out.r, 1));
         if (lsfm_tree_download_state(tree, 0, out.stno, out.stVal) != LSFM_OK) {
-            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 0;
+            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1;
         }
     }
     lsfm_tree_free(tree);
-    if (!st.empty()) lsfm_save_outputs(&out, st.c_str(), nullptr, nullptr);
+    // usage problems return 0 like the reference (LinearSFM.cpp:17); I/O and solve failures return 1
+    int wrc = LSFM_OK;
+    if (!st.empty()) wrc |= lsfm_save_outputs(&out, st.c_str(), nullptr, nullptr);
     if (!pose.empty() && !feat.empty())                     // both required, LinearSFMImp.cpp:2078
-        lsfm_save_outputs(&out, nullptr, pose.c_str(), feat.c_str());
-    if (!mapout.empty()) lsfm_save_localmap(&out, mapout.c_str(), 0);
+        wrc |= lsfm_save_outputs(&out, nullptr, pose.c_str(), feat.c_str());
+    if (!mapout.empty()) wrc |= lsfm_save_localmap(&out, mapout.c_str(), 0);
     lsfm_free_map(&out);
+    if (wrc != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1; }
     return 0;
 }
 

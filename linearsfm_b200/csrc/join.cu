@@ -10,6 +10,7 @@
 // feature the End blocks then the Cur blocks.
 #include "ops.h"
 #include "small_mat.cuh"
+#include "det_accum.cuh"
 #include <cub/cub.cuh>
 
 namespace {
@@ -116,10 +117,12 @@ __global__ void k_join_pose(const DMap *__restrict__ E, const DMap *__restrict__
     J[k].poseNo[p] = p < m1 ? E[k].poseNo[p] : C[k].poseNo[p - m1];
 }
 
-// U list = End's then Cur's (+m1); eP += U xhat (and the transposed product for off-diagonal blocks)
+// U list = End's then Cur's (+m1); eP += U xhat (and the transposed product for off-diagonal blocks):
+// two 6-vector records per block (targets: joint pose rows i and j), added up in a fixed order by
+// det::reduce -- no FP64 atomics
 __global__ void k_join_u(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__restrict__ J,
                          const int *__restrict__ uPreJ, const int *__restrict__ posePreJ, int K, int totU,
-                         double *__restrict__ eP)
+                         int *__restrict__ rkey, double *__restrict__ rval, int none)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= totU) return;
@@ -137,17 +140,22 @@ __global__ void k_join_u(const DMap *__restrict__ E, const DMap *__restrict__ C,
     double xi[6], xj[6], y[6];
     sm::load<6>(S.poseVal + 6 * (size_t)j, xj);
     sm::mm<6, 6, 1>(U, xj, y);
-    double *e = eP + 6 * (size_t)(posePreJ[k] + i + off);
-#pragma unroll
-    for (int q = 0; q < 6; q++) atomicAdd(e + q, y[q]);
+    rkey[2 * (size_t)g] = posePreJ[k] + i + off;
+    sm::store<6>(rval + 12 * (size_t)g, y);
     if (i != j) {
         sm::load<6>(S.poseVal + 6 * (size_t)i, xi);
         sm::mtm<6, 6, 1>(U, xi, y);
-        e = eP + 6 * (size_t)(posePreJ[k] + j + off);
-#pragma unroll
-        for (int q = 0; q < 6; q++) atomicAdd(e + q, y[q]);
+        rkey[2 * (size_t)g + 1] = posePreJ[k] + j + off;
+        sm::store<6>(rval + 12 * (size_t)g + 6, y);
+    } else {
+        rkey[2 * (size_t)g + 1] = none;
     }
 }
+
+struct ApplyEP {
+    double *eP;
+    __device__ void operator()(int t, int q, double sum, int) const { eP[6 * (size_t)t + q] = sum; }
+};
 
 // one thread per joint feature: V merge, labels, CSR start, the V part of eF, and the feature's two
 // estimates (End side, Cur side) for the solver's d vectors (2747-2930)
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(128)
 k_join_w(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__restrict__ J,
          const int *__restrict__ wPreJ, const int *__restrict__ featPreJ,
          const int *__restrict__ featPreC, int K, int totW, const int *__restrict__ jointOfCur,
-         const int *__restrict__ dstOf, double *__restrict__ eF)
+         const int *__restrict__ dstOf, double *__restrict__ featSide, double *__restrict__ warpCont)
 {
     __shared__ double tile[4][32 * 19];
     const unsigned full = 0xffffffffu;
@@ -291,11 +299,42 @@ k_join_w(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__restric
             if (take) t[i] += ov;
         }
     }
+    // Run heads store their run's sum (no atomics): a run that starts at the first block of its
+    // feature in the source map -> featSide[2 gj + side]; a run cut by the warp boundary (lane 0, block
+    // in the middle of its feature) -> warpCont[warp].  k_join_ef_fin adds them up per feature in order.
     int pkey = __shfl_up_sync(full, key, 1);
     if (live && (lane == 0 || pkey != key)) {
-        double *e = eF + 3 * (size_t)gj;
-        atomicAdd(e, t[0]); atomicAdd(e + 1, t[1]); atomicAdd(e + 2, t[2]);
+        double *e = (sb == S.wPtr[f]) ? featSide + 3 * (size_t)(2 * gj + (fromE ? 0 : 1))
+                                      : warpCont + 3 * (size_t)(g >> 5);
+        e[0] = t[0]; e[1] = t[1]; e[2] = t[2];
     }
+}
+
+// eF_f = V part (k_join_featinit) + sum of the End-side runs + sum of the Cur-side runs, fixed order
+__global__ void k_join_ef_fin(const DMap *__restrict__ E, const DMap *__restrict__ C,
+                              const int *__restrict__ wPreJ, const int *__restrict__ featPreJ, int K, int totJ,
+                              const int *__restrict__ curOfJoint, const double *__restrict__ featSide,
+                              const double *__restrict__ warpCont, double *__restrict__ eF)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= totJ) return;
+    int k = seg_find(featPreJ, K, g);
+    int jf = g - featPreJ[k];
+    double s0 = eF[3 * (size_t)g], s1 = eF[3 * (size_t)g + 1], s2 = eF[3 * (size_t)g + 2];
+    auto side = [&](int ga, int gb, int sd) {
+        if (gb <= ga) return;
+        const double *h = featSide + 3 * (size_t)(2 * g + sd);
+        double a0 = h[0], a1 = h[1], a2 = h[2];
+        for (int w = (ga >> 5) + 1; w <= ((gb - 1) >> 5); w++) {
+            const double *c = warpCont + 3 * (size_t)w;
+            a0 += c[0]; a1 += c[1]; a2 += c[2];
+        }
+        s0 += a0; s1 += a1; s2 += a2;
+    };
+    if (jf < E[k].n) side(wPreJ[k] + E[k].wPtr[jf], wPreJ[k] + E[k].wPtr[jf + 1], 0);
+    int c = curOfJoint[g];
+    if (c >= 0) side(wPreJ[k] + E[k].nW + C[k].wPtr[c], wPreJ[k] + E[k].nW + C[k].wPtr[c + 1], 1);
+    eF[3 * (size_t)g] = s0; eF[3 * (size_t)g + 1] = s1; eF[3 * (size_t)g + 2] = s2;
 }
 
 __global__ void k_wptr_end(DMap *__restrict__ J, int K)
@@ -460,10 +499,17 @@ std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHand
     // solver through the per-feature d vectors (SolveExtra, k_vinv)
     DevBuf<double> eP(6 * (size_t)J.totPose, s), eF(3 * (size_t)J.totFeat, s), xhat(6 * (size_t)J.totFeat, s);
     DevBuf<int> dstOf(std::max(J.totW, 1), s);
-    eP.zero();
     k_join_pose<<<ceil_div(J.totPose, TB), TB, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dPosePre.p, K, J.totPose); nl++;
-    if (J.totU > 0) {
-        k_join_u<<<ceil_div(J.totU, 128), 128, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dUPre.p, J.dPosePre.p, K, J.totU, eP.p); nl++;
+    {
+        DevBuf<int> rkey(2 * (size_t)std::max(J.totU, 1), s);
+        DevBuf<double> rval(12 * (size_t)std::max(J.totU, 1), s);
+        if (J.totU > 0) {
+            k_join_u<<<ceil_div(J.totU, 128), 128, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dUPre.p, J.dPosePre.p, K, J.totU,
+                                                          rkey.p, rval.p, J.totPose); nl++;
+        }
+        det::Sorted srt;
+        nl += det::sort_records(ctx, rkey.p, 2 * J.totU, J.totPose, srt);
+        det::reduce<6>(ctx, srt, rval.p, J.totPose, ApplyEP{eP.p}); nl++;
     }
     if (J.totFeat > 0) {
         k_join_featinit<<<ceil_div(J.totFeat, TB), TB, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dFeatPre.p, K, J.totFeat,
@@ -486,13 +532,17 @@ std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHand
     SolveExtra ex;
     ex.xhat = xhat.p;
     ex.split = dSplit.p;
+    DevBuf<double> featSide(6 * (size_t)std::max(J.totFeat, 1), s), warpCont(3 * (size_t)(J.totW / 32 + 1), s);
     ex.after_pattern = [&]() {
         ctx.begin("join.values");
-        if (J.totW > 0)
+        if (J.totW > 0) {
             k_join_w<<<ceil_div(J.totW, 128), 128, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dWPre.p, J.dFeatPre.p, C.dFeatPre.p, K,
-                                                          J.totW, jointOfCur.p, dstOf.p, eF.p);
+                                                          J.totW, jointOfCur.p, dstOf.p, featSide.p, warpCont.p);
+            k_join_ef_fin<<<ceil_div(J.totFeat, TB), TB, 0, s>>>(E.d.p, C.d.p, J.dWPre.p, J.dFeatPre.p, K, J.totFeat,
+                                                                curOfJoint.p, featSide.p, warpCont.p, eF.p);
+        }
         KERNEL_CHECK();
-        ctx.end(valueBytes, 0.0, 1);
+        ctx.end(valueBytes, 0.0, 2);
     };
     solve_stereo_batch(ctx, J, eP.p, eF.p, nullptr, nullptr, &ex);
 

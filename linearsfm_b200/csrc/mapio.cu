@@ -149,7 +149,13 @@ std::vector<MapHandle> upload_maps(Context &ctx, const lsfm_map *maps, int K, bo
                 done[g].store(1, std::memory_order_release);
             }
         };
-        std::vector<std::thread> th;
+        // the packing threads are joined on EVERY exit path (a throwing CUDA call below must surface as
+        // an error code, not as std::terminate on a joinable thread)
+        struct Joiner {
+            std::vector<std::thread> th;
+            ~Joiner() { for (auto &t : th) if (t.joinable()) t.join(); }
+        } joiner;
+        std::vector<std::thread> &th = joiner.th;
         for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
         bool failed = false;
         for (int g = 0; g < G; g++) {
@@ -168,6 +174,14 @@ std::vector<MapHandle> upload_maps(Context &ctx, const lsfm_map *maps, int K, bo
     CUDA_CHECK(cudaEventRecord(g_up_done, ctx.stream));
     g_up_pending = true;
     return out;
+}
+
+void mapio_shutdown()
+{
+    if (g_up_pending && g_up_done) cudaEventSynchronize(g_up_done);
+    g_up_pending = false;
+    if (g_up_done) cudaEventDestroy(g_up_done);
+    g_up_done = nullptr;
 }
 
 static void alloc_host_map(lsfm_map *o, const DMap &d)

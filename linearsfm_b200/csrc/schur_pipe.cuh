@@ -15,7 +15,9 @@
 //     re-layout   : one thread per (block, row): the row of W V^-1 -> a dense tile (W itself stays in
 //                   the raw buffer; both operands are read with 16-byte shared loads);
 //     pair update : thread (i,j) adds W V^-1|_i * W^T|_j for every feature that sees both poses.
-// One flush of 36 FP64 atomics per touched pair and chunk.  Three instantiations trade registers /
+// One 288-byte record per touched pair and chunk (diagonal pairs: upper triangle + the pose's share of E
+// in six lower-triangle entries); the records of an S block are added up in a fixed order afterwards
+// (det_accum.cuh) -- no FP64 atomics, results are bit-identical from run to run.  Three instantiations trade registers /
 // shared memory for resident CTAs: (CMAX 8, 64 thr) x4-5 per SM for the lower tree levels,
 // (16, 128 thr) x2, (31, 256 thr) x1 for the top levels.
 #pragma once
@@ -70,9 +72,11 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
              const int *__restrict__ wPre, const int *__restrict__ featPre, const int *__restrict__ posePre,
              const double *__restrict__ Vinv, const double *__restrict__ dvec, const int *__restrict__ split,
              const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
-             double *__restrict__ S, double *__restrict__ E)
+             double *__restrict__ S, double *__restrict__ E,
+             const int *__restrict__ recOff, int *__restrict__ rkey, double *__restrict__ rval)
 {
     static_assert(MAXBLK >= 2 * CMAX && MAXBLK <= 255, "block budget");
+    static_assert(SLOTS == 1, "one pair slot per thread");
     typedef Layout<CMAX, MAXBLK, NBMAX> L;
     constexpr int QBLK = MAXBLK;           // a batch ends at the last feature whose blocks still fit
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -104,16 +108,20 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         return;
     }
     const int npairs = nposes * (nposes + 1) / 2;
-    const int rep = max(1, min(NBMAX, (SLOTS * THREADS) / npairs));
-    // pair slots of one replica: the nposes diagonal pairs first (so they share warps: they run a
-    // different body), then the off-diagonal pairs (i<j) row by row
+    // Replicas: when the chunk has few pairs, rep threads share one pair (features dealt round-robin).
+    // rep is a power of two and the replicas of a pair sit in ADJACENT lanes, so that their partial
+    // blocks are combined by a fixed shuffle butterfly before the flush (no atomics, same bits every run).
+    int rep = 1;
+    while (2 * rep <= min(min(32, NBMAX), THREADS / npairs)) rep *= 2;
+    // pair slots: the nposes diagonal pairs first (so they share warps: they run a different body),
+    // then the off-diagonal pairs (i<j) row by row
     int pi[SLOTS], pj[SLOTS], pr0[SLOTS];
 #pragma unroll
     for (int u = 0; u < SLOTS; u++) {
         pi[u] = -1; pj[u] = -1; pr0[u] = 0;
         int q = tid + u * THREADS;
-        int r = q / npairs, t = q - r * npairs;
-        if (r < rep) {
+        int t = q / rep, r = q - t * rep;
+        if (t < npairs) {
             pr0[u] = r;
             if (t < nposes) { pi[u] = t; pj[u] = t; }
             else {
@@ -202,13 +210,26 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         }
         __syncthreads();
         const double *rE = rawEf + buf * (NBMAX * 6);
-#pragma unroll
-        for (int u = 0; u < SLOTS; u++) {
-            if (pi[u] < 0) continue;
-            for (int fb = pr0[u]; fb < nbf; fb += rep) {
-                unsigned pr = present[buf * NBMAX + fb];
-                if (((pr >> pi[u]) & (pr >> pj[u]) & 1u) == 0u) continue;
+        {
+            // Every lane walks ITS OWN list of features that see both poses of its pair: the search for
+            // the next hit is a cheap divergent scan, the 108-FMA update below runs with all lanes that
+            // still have work (before: the warp executed the body whenever ANY lane hit, at ~20 % density)
+            constexpr int u = 0;
+            const unsigned *prs = present + buf * NBMAX;
+            const int mi = pi[u] < 0 ? 0 : pi[u], mj = pi[u] < 0 ? 0 : pj[u];
+            auto next_hit = [&](int fb) {
+                while (fb < nbf) {
+                    const unsigned pr = prs[fb];
+                    if ((pr >> mi) & (pr >> mj) & 1u) break;
+                    fb += rep;
+                }
+                return fb;
+            };
+            int fb = pi[u] < 0 ? nbf : next_hit(pr0[u]);
+            while (__any_sync(0xffffffffu, fb < nbf)) {
+              if (fb < nbf) {
                 touched[u] = true;
+
                 const double2 *wv2 = reinterpret_cast<const double2 *>(WVsm + (int)blkOf[fb * 32 + pi[u]] * LD);
                 const double2 *w2 = reinterpret_cast<const double2 *>(rW + (int)blkOf[fb * 32 + pj[u]] * 18);
                 double b[18];
@@ -246,30 +267,36 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
                         }
                     }
                 }
+                fb = next_hit(fb + rep);
+              }
             }
         }
         fa = fa2; fe = fe2;
     }
+    // combine the replicas of a pair (adjacent lanes, rep a power of two <= 32): after the butterfly
+    // every replica holds the same bits; replica 0 writes the pair's record
+    if (rep > 1) {
+        for (int o = 1; o < rep; o <<= 1) {
 #pragma unroll
-    for (int u = 0; u < SLOTS; u++) {
-        if (!touched[u]) continue;
-        int gi = poses[pi[u]], gj = poses[pj[u]];
-        int slot = find_slot(keys, rowPtr, posePre[k] + gi, pair_key(k, gi, gj));
-        double *sp = S + 36 * (size_t)slot;
-        if (pi[u] == pj[u]) {
+            for (int q = 0; q < 36; q++) acc[0][q] += __shfl_xor_sync(0xffffffffu, acc[0][q], o);
+        }
+    }
+    (void)touched;
+    if (pi[0] >= 0 && pr0[0] == 0) {
+        // the pattern kernel's bitmap of the chunk's pairs (row-major upper triangle incl. diagonal)
+        // decides which pairs exist; the record position is the pair's rank in that bitmap
+        const int i = pi[0], j = pj[0];
+        const int idx = i * nposes - (i * (i - 1)) / 2 + (j - i);
+        const unsigned wbit = (unsigned)ci[32 + (idx >> 5)];
+        if ((wbit >> (idx & 31)) & 1u) {
+            int rank = __popc(wbit & ((1u << (idx & 31)) - 1u));
+            for (int w = 0; w < (idx >> 5); w++) rank += __popc((unsigned)ci[32 + w]);
+            const size_t r = (size_t)recOff[blockIdx.x] + rank;
+            const int gi = poses[i], gj = poses[j];
+            rkey[r] = find_slot(keys, rowPtr, posePre[k] + gi, pair_key(k, gi, gj));
+            double2 *dst = reinterpret_cast<double2 *>(rval + 36 * r);
 #pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-                for (int c = r; c < 6; c++) {
-                    atomicAdd(sp + 6 * r + c, -acc[u][6 * r + c]);
-                    if (c > r) atomicAdd(sp + 6 * c + r, -acc[u][6 * r + c]);
-                }
-            double *e = E + 6 * (size_t)(posePre[k] + gi);
-#pragma unroll
-            for (int q = 0; q < 6; q++) atomicAdd(e + q, -acc[u][EIDX[q]]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 36; q++) atomicAdd(sp + q, -acc[u][q]);
+            for (int q = 0; q < 18; q++) dst[q] = make_double2(acc[0][2 * q], acc[0][2 * q + 1]);
         }
     }
 }

@@ -10,6 +10,7 @@
 #include "ops.h"
 #include "chol_symbolic.h"
 #include "small_mat.cuh"
+#include "det_accum.cuh"
 #include <cub/cub.cuh>
 #include <thread>
 #include <chrono>
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(PAT_THREADS)
 k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
             unsigned *__restrict__ bm, const int *__restrict__ bmOff,
             int *__restrict__ maxNposes, int pat_cmax, int *__restrict__ chunkInfo,
-            int *__restrict__ blkInfo, const int *__restrict__ wPre)
+            int *__restrict__ blkInfo, const int *__restrict__ wPre, int *__restrict__ recCnt)
 {
     extern __shared__ unsigned smu[];
     const FeatChunk ch = chunks[blockIdx.x];
@@ -115,6 +116,14 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
             while (b) { int bit = __ffs(b) - 1; poses[r] = i * 32 + bit; ci[r] = i * 32 + bit; r++; b &= b - 1; }
         }
         __syncthreads();
+        // the chunk's pair bitmap stays behind for the Schur kernel ([32..47]); its popcount is the number
+        // of S-block records the chunk will write (deterministic accumulation, det_accum.cuh)
+        if (tid < 16) ci[32 + tid] = (int)pairBits[tid];
+        if (tid == 0) {
+            int c = 0;
+            for (int w = 0; w < 16; w++) c += __popc(pairBits[w]);
+            recCnt[blockIdx.x] = c;
+        }
         // the chunk's distinct pairs -> the join's pose-pair bitmap (exact dedupe across chunks)
         const int npairs = nposes * (nposes + 1) / 2;
         for (int t = tid; t < npairs; t += nt) {
@@ -126,6 +135,7 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         return;
     }
     // overflow: too many distinct poses in this chunk -> per-feature pairs straight to the bitmap
+    if (tid == 0) recCnt[blockIdx.x] = 0;
     for (int f = ch.f0 + tid; f < ch.f1; f += nt) {
         int a0 = M.wPtr[f], a1 = M.wPtr[f + 1];
         for (int a = a0; a < a1; a++)
@@ -343,6 +353,30 @@ __device__ __noinline__ void schur_block_slow(const DMap &M, int k, int a, const
 }
 
 constexpr int SCH_FCHUNK = 128;        // features per chunk (pattern + Schur kernels)
+
+// det::reduce target t = S block slot.  Off-diagonal blocks: all 36 sums.  Diagonal blocks: the records
+// carry the upper triangle (mirrored here) and, in six lower-triangle entries, the pose's share of E.
+struct ApplyS {
+    const u64 *keys;
+    const int *posePre;
+    double *S, *E;
+    __device__ void operator()(int t, int q, double sum, int cnt) const
+    {
+        if (cnt == 0) return;
+        const u64 key = keys[t];
+        const int k = (int)(key >> 44), lo = (int)((key >> 22) & ((1u << 22) - 1)), hi = (int)(key & ((1u << 22) - 1));
+        double *sp = S + 36 * (size_t)t;
+        if (lo != hi) { sp[q] -= sum; return; }
+        const int r = q / 6, c = q - 6 * r;
+        if (c >= r) {
+            sp[6 * r + c] -= sum;
+            if (c > r) sp[6 * c + r] -= sum;
+        } else {
+            const int e = (q == 6) ? 0 : (q == 12) ? 1 : (q == 13) ? 2 : (q == 18) ? 3 : (q == 19) ? 4 : (q == 20) ? 5 : -1;
+            if (e >= 0) E[6 * (size_t)(posePre[k] + lo) + e] -= sum;
+        }
+    }
+};
 } // namespace
 #include "schur_pipe.cuh"
 namespace {
@@ -786,6 +820,9 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     int maxNposes = 1 << 30;             // max distinct poses of any chunk (measured by k_pat_chunk)
     DevBuf<int> dMaxNp(1, s);
     DevBuf<int> chunkInfo((size_t)CHUNK_INFO_INTS * std::max(nChunks, 1), s), blkInfo((size_t)std::max(J.totW, 1), s);
+    // S-block records per chunk (deterministic accumulation of the Schur complement): counts from the
+    // pattern kernel, offsets by one scan, the total comes to the host with the pattern
+    DevBuf<int> recCnt((size_t)nChunks + 1, s), recOff((size_t)nChunks + 1, s);
     // test hook: LSFM_FORCE_OVERFLOW=1 sends every chunk with > 4 poses down the overflow paths
     static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
     const int pat_cmax_used = force_ovf ? 4 : PAT_CMAX;
@@ -812,8 +849,10 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
         dMaxNp.zero();
         k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, bm.p, dBmOff.p, dMaxNp.p, pat_cmax_used,
-                                                      chunkInfo.p, blkInfo.p, J.dWPre.p); nl++;
+                                                      chunkInfo.p, blkInfo.p, J.dWPre.p, recCnt.p); nl++;
     }
+    CUDA_CHECK(cudaMemsetAsync(recCnt.p + nChunks, 0, sizeof(int), s));
+    exclusive_scan(ctx, recCnt.p, recOff.p, nChunks + 1); nl += 2;
     if (gauge) {   // mono: the zero pose has no block at all after the join; keep every diagonal
         k_pat_diag<<<ceil_div(J.totPose, TB), TB, 0, s>>>(J.d.p, J.dPosePre.p, K, J.totPose, bm.p, dBmOff.p); nl++;
     }
@@ -833,13 +872,16 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     u64 *hKeys = (u64 *)pin;
     int *hRowPtr = (int *)(pin + sizeof(u64) * ((size_t)keyCap + 1));
     int *hMaxNp = hRowPtr + J.totPose + 1;
+    int *hNrec = hMaxNp + 1;
     *hMaxNp = 0;
     if (nChunks > 0) CUDA_CHECK(cudaMemcpyAsync(hMaxNp, dMaxNp.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(hNrec, recOff.p + nChunks, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (keyCap) CUDA_CHECK(cudaMemcpyAsync(hKeys, keys.p, sizeof(u64) * keyCap, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(hRowPtr, rowPtr.p, sizeof(int) * (J.totPose + 1), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     ctx.idle_begin();
     nuis = hRowPtr[J.totPose];
+    const int nrec = *hNrec;
     if (nChunks > 0) maxNposes = *hMaxNp;
     if (nuis > keyCap) {                  // bound overshot: emit and fetch again with the exact size
         keys.alloc((size_t)nuis, s);
@@ -875,6 +917,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     ctx.end(72.0 * J.totFeat * 2 + 576.0 * J.totU, 0.0, nl);
     nl = 0;
     ctx.begin("solve.schur");
+    DevBuf<int> rkey((size_t)std::max(nrec, 1), s);
+    DevBuf<double> rval(36 * (size_t)std::max(nrec, 1), s);
     if (J.totW > 0) {
         static const bool use_v1 = getenv("LSFM_SCHUR_V1") != nullptr;
         if (use_v1) {
@@ -886,7 +930,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
                 if (shb > 48 * 1024)
                     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
                 kern<<<nChunks, threads, shb, s>>>(J.d.p, dChunks.p, chunkInfo.p, blkInfo.p, pat_cmax_used, J.dWPre.p,
-                                                  J.dFeatPre.p, J.dPosePre.p, Vinv.p, dvec.p, split, keys.p, rowPtr.p, S.p, E.p);
+                                                  J.dFeatPre.p, J.dPosePre.p, Vinv.p, dvec.p, split, keys.p, rowPtr.p, S.p, E.p,
+                                                  recOff.p, rkey.p, rval.p);
             };
             static const bool force_ovf2 = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
             if (maxNposes <= 8 || force_ovf2)
@@ -896,6 +941,10 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             else
                 launch(schur_pipe::k_schur_pipe<31, 248, 32, 512, 1>, schur_pipe::Layout<31, 248, 32>::bytes(), 512);
             nl++;
+            // S(a,b) -= sum of the block's records, E_p -= the share carried by the diagonal records
+            det::Sorted srt;
+            nl += det::sort_records(ctx, rkey.p, nrec, nuis, srt);
+            det::reduce<36>(ctx, srt, rval.p, nuis, ApplyS{keys.p, J.dPosePre.p, S.p, E.p}); nl++;
         }
     }
     KERNEL_CHECK();

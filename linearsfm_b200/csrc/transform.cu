@@ -19,6 +19,7 @@
 #include "ops.h"
 #include "geom.cuh"
 #include "small_mat.cuh"
+#include "det_accum.cuh"
 #include <cub/cub.cuh>
 #include <climits>
 #include <type_traits>
@@ -192,10 +193,7 @@ __global__ void k_tf_uinit(DMap *__restrict__ out, const int *__restrict__ poseP
     int i = g - posePre[k];
     int pid = posID[k];
     out[k].Ui[i] = i <= pid ? i : pid;
-    out[k].Uj[i] = i <= pid ? pid : i;
-    double *u = out[k].U + 36 * (size_t)i;      // shared accumulation targets start from zero
-#pragma unroll
-    for (int q = 0; q < 36; q++) u[q] = 0.0;
+    out[k].Uj[i] = i <= pid ? pid : i;          // the block values come from the record reduction
 }
 
 __device__ __forceinline__ void dense_jac(const TfConst &c, const PoseJac &J, bool isPos,
@@ -213,21 +211,48 @@ __device__ __forceinline__ void dense_jac(const TfConst &c, const PoseJac &J, bo
         }
 }
 
-__device__ __forceinline__ void add_block(double *dst, const double *P, bool transpose)
+// Record writers of the deterministic U' accumulation (det_accum.cuh).  The new U list's slots [0,m)
+// (pairs with posID) are shared targets: every old U block, every pose sum and every feature chunk
+// adds into them.  Target index = global pose index of the slot; `none` = no contribution.
+__device__ __forceinline__ void rec_write(int *__restrict__ key, double *__restrict__ val, size_t r, int target,
+                                          const double *P)
 {
+    key[r] = target;
+    double2 *dst = reinterpret_cast<double2 *>(val + 36 * r);
 #pragma unroll
-    for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int q = 0; q < 6; q++) atomicAdd(dst + 6 * r + q, transpose ? P[6 * q + r] : P[6 * r + q]);
+    for (int q = 0; q < 18; q++) dst[q] = make_double2(P[2 * q], P[2 * q + 1]);
 }
 
-// one thread per old U block (LinearSFMImp.cpp:725-1266). U blocks are few (nU << nW), but EVERY
-// block adds into the (pos,pos) slot of its map: that sum is reduced across the warp first
-// (warp_agg_atomic_add), otherwise the root map's 38k blocks serialise on 36 addresses.
+// record for the (pos,pos) slot: when the whole warp adds into the same target the 36 values are
+// butterfly-reduced first (fixed order) and only the leader's record carries a key
+__device__ __forceinline__ void rec_write_hot(int *__restrict__ key, double *__restrict__ val, size_t r,
+                                              int target, int none, double *Q, bool active)
+{
+    const unsigned full = 0xffffffffu;
+    const unsigned amask = __ballot_sync(full, active);
+    if (amask == 0u) return;
+    const int leader = __ffs(amask) - 1;
+    const int t0 = __shfl_sync(full, target, leader);
+    const bool uniform = __all_sync(full, !active || target == t0);
+    if (uniform) {
+#pragma unroll
+        for (int i = 0; i < 36; i++) Q[i] = sm::warp_sum(active ? Q[i] : 0.0);
+        if (!active) return;
+        if ((int)(threadIdx.x & 31) == leader) rec_write(key, val, r, target, Q);
+        else key[r] = none;
+    } else if (active) {
+        rec_write(key, val, r, target, Q);
+    }
+}
+
+// one thread per old U block (LinearSFMImp.cpp:725-1266): four products per block, written as records
+// 4g .. 4g+3 (targets: (pos,pos); slot j; slot i or j; slot i) -- survivors (neither index == posID) are
+// stored straight into their own slot.
 __global__ void __launch_bounds__(128)
 k_ucong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ uPre,
         const int *__restrict__ posePre, int K, int totU, const TfConst *__restrict__ tc,
-        const PoseJac *__restrict__ pj, const int *__restrict__ uScan)
+        const PoseJac *__restrict__ pj, const int *__restrict__ uScan,
+        int *__restrict__ rkey, double *__restrict__ rval, int none)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = g < totU;                     // no early return: the warp stays converged
@@ -238,6 +263,7 @@ k_ucong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restri
     const TfConst &c = tc[k];
     int pid = c.posID;
     int i = M.Ui[b], j = M.Uj[b];
+    const int base = posePre[k];
     double I[36];
     sm::load<36>(M.U + 36 * (size_t)b, I);
     double J1i[36], J2i[36], J1j[36], J2j[36];
@@ -245,6 +271,7 @@ k_ucong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restri
     dense_jac(c, pj[posePre[k] + j], j == pid, J1j, J2j);
     double *Un = out[k].U;
     double T[36], P[36];
+    const size_t r0 = 4 * (size_t)gg;
 
     // C_i^T I C_j -> (pos,pos)
     sm::mtm<6, 6, 6>(J2i, I, T);
@@ -255,19 +282,27 @@ k_ucong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restri
         for (int r = 0; r < 6; r++)
 #pragma unroll
             for (int q = 0; q < 6; q++) Q[6 * r + q] = P[6 * r + q] + (i != j ? P[6 * q + r] : 0.0);
-        sm::warp_agg_atomic_add<36>(Un + 36 * (size_t)pid, Q, active);
+        rec_write_hot(rkey, rval, r0, base + pid, none, Q, active);
     }
     if (!active) return;
-    // C_i^T I D_j -> (pos,j), stored in slot j
+    // C_i^T I D_j -> (pos,j), stored in slot j (transposed when j < pos; both orientations when j == pos)
     sm::mm<6, 6, 6>(T, J1j, P);
-    if (j >= pid) add_block(Un + 36 * (size_t)j, P, false);
-    if (j <= pid && i != j) add_block(Un + 36 * (size_t)j, P, true);
+    {
+        const bool a = j >= pid, bt = (j <= pid && i != j);
+        double Q[36];
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int q = 0; q < 6; q++) Q[6 * r + q] = (a ? P[6 * r + q] : 0.0) + (bt ? P[6 * q + r] : 0.0);
+        rec_write(rkey, rval, r0 + 1, base + j, Q);
+    }
     // D_i^T I D_j -> (i,j)
     sm::mtm<6, 6, 6>(J1i, I, T);
     sm::mm<6, 6, 6>(T, J1j, P);
-    if (i == pid) add_block(Un + 36 * (size_t)j, P, false);
-    else if (j == pid) add_block(Un + 36 * (size_t)i, P, false);
+    if (i == pid) rec_write(rkey, rval, r0 + 2, base + j, P);
+    else if (j == pid) rec_write(rkey, rval, r0 + 2, base + i, P);
     else {
+        rkey[r0 + 2] = none;
         int slot = M.m + (uScan[g] - uScan[uPre[k]]);
         sm::store<36>(Un + 36 * (size_t)slot, P);
         out[k].Ui[slot] = i;
@@ -275,8 +310,15 @@ k_ucong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restri
     }
     // D_i^T I C_j -> (i,pos), stored in slot i
     sm::mm<6, 6, 6>(T, J2j, P);
-    if (i <= pid) add_block(Un + 36 * (size_t)i, P, false);
-    if (i >= pid && i != j) add_block(Un + 36 * (size_t)i, P, true);
+    {
+        const bool a = i <= pid, bt = (i >= pid && i != j);
+        double Q[36];
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int q = 0; q < 6; q++) Q[6 * r + q] = (a ? P[6 * r + q] : 0.0) + (bt ? P[6 * q + r] : 0.0);
+        rec_write(rkey, rval, r0 + 3, base + i, Q);
+    }
 }
 
 // X = [Xt; Xb] (6 x N).  out = Jp^T X for the block-triangular pose Jacobian [[a,b],[0,c]]:
@@ -292,259 +334,101 @@ __device__ __forceinline__ void jt_mul(const double *a, double sgn, const double
     if (has_b) sm::mtm_acc<3, 3, N>(b, X, out + 3 * N);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Cross-check variant of the W/V congruence (LSFM_TF_V3=1; the default is k_tf_chunk,
-// transform_chunk.cuh): separate kernels that read W twice.
-//   k_tf_featprep : one thread per feature  -> X', V', T_f scratch, the V part of W'(pos,f) and of
-//                   U'(pos,pos), output CSR/labels of the new (posID,f) block.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_tf_featprep(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ featPre,
-              int K, int totFeat, const TfConst *__restrict__ tc, const int *__restrict__ fScan,
-              double *__restrict__ TfBuf)
-{
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = g < totFeat;
-    int k = live ? seg_find(featPre, K, g) : 0;
-    int f = live ? g - featPre[k] : 0;
-    const DMap &M = in[k];
-    const DMap &O = out[k];
-    const TfConst &c = tc[k];
-    double S[36];
-#pragma unroll
-    for (int i = 0; i < 36; i++) S[i] = 0.0;
-    if (live) {
-        const double *x = M.featVal + 3 * (size_t)f;
-        double d0[3] = {x[0] - c.t[0], x[1] - c.t[1], x[2] - c.t[2]};
-        double xn[3];
-        geom::mat3_vec(c.R, d0, xn);
-        double *y = O.featVal + 3 * (size_t)f;
-        y[0] = xn[0]; y[1] = xn[1]; y[2] = xn[2];
-        O.featNo[f] = M.featNo[f];
-        double d[3] = {xn[0] - c.tn[0], xn[1] - c.tn[1], xn[2] - c.tn[2]};
-        double Tf[9], v[3];
-        geom::mat3_vec(c.QA, d, v); Tf[0] = v[0]; Tf[3] = v[1]; Tf[6] = v[2];
-        geom::mat3_vec(c.QB, d, v); Tf[1] = v[0]; Tf[4] = v[1]; Tf[7] = v[2];
-        geom::mat3_vec(c.QG, d, v); Tf[2] = v[0]; Tf[5] = v[1]; Tf[8] = v[2];
-        sm::store<9>(TfBuf + 9 * (size_t)g, Tf);
-        double Q[9], V[9], VQ[9], VT[9], Vn[9], M1[9], M2[9];
-        sm::load<9>(c.Q, Q);
-        sm::load<9>(M.V + 9 * (size_t)f, V);
-        sm::mm<3, 3, 3>(V, Q, VQ);
-        sm::mm<3, 3, 3>(V, Tf, VT);
-        sm::mtm<3, 3, 3>(Q, VQ, Vn);
-        sm::mtm<3, 3, 3>(Tf, VQ, M1);
-        sm::mtm<3, 3, 3>(Tf, VT, M2);
-        sm::store<9>(O.V + 9 * (size_t)f, Vn);
-        int o0 = fScan[g] - fScan[featPre[k]];
-        O.wPtr[f] = o0;
-        O.photo[o0] = c.posID;
-        O.feature[o0] = f;
-        // the (posID,f) block starts as C_f^T V D_f = [-V'; M1]; k_tf_wblock adds the W terms
-        double *wp = O.W + 18 * (size_t)o0;
-#pragma unroll
-        for (int i = 0; i < 9; i++) { wp[i] = -Vn[i]; wp[9 + i] = M1[i]; }
-        // C_f^T V C_f = [[V', -M1^T],[-M1, M2]]
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                S[6 * r + q] = Vn[3 * r + q];
-                S[6 * r + 3 + q] = -M1[3 * q + r];
-                S[6 * (r + 3) + q] = -M1[3 * r + q];
-                S[6 * (r + 3) + 3 + q] = M2[3 * r + q];
-            }
-    }
-    sm::warp_agg_atomic_add<36>(O.U + 36 * (size_t)c.posID, S, live);
-}
+#include "transform_chunk.cuh"
 
-// ---------------------------------------------------------------------------------------------
-// the pose-major sums are taken out of the block-major kernel.
-//   U'(p,pos) and the W part of U'(pos,pos) only need, per pose p,
-//       SW_p = sum_f W_pf          SWT_p = sum_f W_pf T_f            (two 6x3 sums)
-//   because D_p / C_p / Q factor out of the sums:
-//       sum_f D_p^T W_pf C_f = [ -D_p^T SW_p Q | D_p^T SWT_p ],   same with C_p for U'(pos,pos).
-//   k_tf_wblock3  : block-major, coalesced: writes D_p^T W Q, segment-reduces C_p^T W Q into W'(pos,f),
-//                   emits (pose key, block index) pairs for the sort.
-//   cub radix sort of the pairs (keys = global pose index, <= 13 bits here)
-//   k_tf_posesum  : pose-major gather, one warp per chunk of a pose's blocks -> SW, SWT
-//   k_tf_posefin  : one thread per pose: applies the pose Jacobians once and adds the 6x6 blocks.
-// ---------------------------------------------------------------------------------------------
+// One WARP per pose: gathers the pose's sums SW_p = sum_f W_pf, SWT_p = sum_f W_pf T_f from the records
+// the chunk kernel left behind (chunk-local pose tables are sorted: binary search per chunk of the
+// pose's map, chunks strided over the lanes, lane-private partial sums combined by a fixed butterfly:
+// bit-identical from run to run), then applies the pose Jacobians ONCE:
+//     U'(p,pos) += oriented [-D_p^T SW Q | D_p^T SWT]   ->  record 2 gp     (target: slot p)
+//     U'(pos,pos) += G + G^T, G = C_p^T [-SW Q | SWT]   ->  record 2 gp + 1 (target: slot pos)
 __global__ void __launch_bounds__(128)
-k_tf_wblock3(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ wPre,
-             const int *__restrict__ featPre, const int *__restrict__ posePre, int K, int totW,
+k_tf_posefin(const int *__restrict__ posePre, int K, int totPose,
              const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj,
-             int *__restrict__ sortKey, int *__restrict__ sortVal)
-{
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool live = g < totW;
-    int k = live ? seg_find(wPre, K, g) : 0;
-    int j = live ? g - wPre[k] : 0;
-    const DMap &M = in[k];
-    const DMap &O = out[k];
-    const TfConst &c = tc[k];
-    const int pid = c.posID;
-    int f = 0, gf = -1 - lane;
-    double wadd[18];
-#pragma unroll
-    for (int i = 0; i < 18; i++) wadd[i] = 0.0;
-    if (live) {
-        f = M.feature[j];
-        int p = M.photo[j];
-        gf = featPre[k] + f;
-        sortKey[g] = posePre[k] + p;
-        sortVal[g] = g;
-        bool isPos = (p == pid);
-        double Q[9], W[18], X[18];
-        sm::load<9>(c.Q, Q);
-        sm::load<18>(M.W + 18 * (size_t)j, W);
-        const PoseJac &J = pj[posePre[k] + p];
-        sm::mm<6, 3, 3>(W, Q, X);                                       // W Q
-        if (isPos) {
-            jt_mul<3>(Q, -1.0, J.b1, J.c1, true, X, wadd);              // D_pos^T W Q, folded into (posID,f)
-        } else {
-            double a1[18];
-            jt_mul<3>(Q, 1.0, J.b1, J.c1, false, X, a1);                // D_p^T W Q
-            int w0 = M.wPtr[f], skip = 0;
-            for (int i = w0; i < j; i++) skip += (M.photo[i] == pid);
-            int o = O.wPtr[f] + 1 + (j - w0) - skip;
-            sm::store<18>(O.W + 18 * (size_t)o, a1);
-            O.photo[o] = p;
-            O.feature[o] = f;
-            jt_mul<3>(Q, -1.0, J.f2, J.g2, true, X, wadd);              // C_p^T W Q
-        }
-    }
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        int okey = __shfl_down_sync(0xffffffffu, gf, off);
-        bool take = (lane + off < 32) && (okey == gf);
-#pragma unroll
-        for (int i = 0; i < 18; i++) {
-            double ov = __shfl_down_sync(0xffffffffu, wadd[i], off);
-            if (take) wadd[i] += ov;
-        }
-    }
-    int pkey = __shfl_up_sync(0xffffffffu, gf, 1);
-    if (live && (lane == 0 || pkey != gf)) {
-        double *wp = O.W + 18 * (size_t)O.wPtr[f];
-#pragma unroll
-        for (int i = 0; i < 18; i++) atomicAdd(wp + i, wadd[i]);
-    }
-}
-
-__global__ void k_pose_start(const int *__restrict__ sortedKey, int totW, int totPose,
-                             int *__restrict__ poseStart)
-{
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g > totPose) return;
-    int lo = 0, hi = totW;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (sortedKey[mid] < g) lo = mid + 1; else hi = mid; }
-    poseStart[g] = lo;
-}
-
-constexpr int PS_CHUNK = 256;          // blocks of one pose summed by one warp
-
-__global__ void k_pose_nchunks(const int *__restrict__ poseStart, int totPose, int *__restrict__ nch)
-{
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g > totPose) return;
-    nch[g] = (g < totPose) ? (poseStart[g + 1] - poseStart[g] + PS_CHUNK - 1) / PS_CHUNK : 0;
-}
-
-// one warp per chunk (<= PS_CHUNK blocks of one pose): SW += W, SWT += W T_f
-__global__ void __launch_bounds__(128)
-k_tf_posesum(const DMap *__restrict__ in, const int *__restrict__ wPre, const int *__restrict__ featPre,
-             const int *__restrict__ posePre, int K, int totPose, const int *__restrict__ poseStart,
-             const int *__restrict__ chScan, const int *__restrict__ sortedVal,
-             const double *__restrict__ TfBuf, double *__restrict__ poseAcc)
+             const int *__restrict__ chunkPre, const int *__restrict__ chunkPoses,
+             const double *__restrict__ chunkRec, const double *__restrict__ poseAccSlow,
+             int *__restrict__ rkey, double *__restrict__ rval, int none)
 {
     const int lane = threadIdx.x & 31;
-    int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wid >= chScan[totPose]) return;
-    int gp = seg_find(chScan, totPose, wid);
-    int b0 = poseStart[gp] + (wid - chScan[gp]) * PS_CHUNK;
-    int b1 = min(b0 + PS_CHUNK, poseStart[gp + 1]);
-    int k = seg_find(posePre, K, gp);
-    const DMap &M = in[k];
+    const int gp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gp >= totPose) return;                   // whole warps leave together
+    const int k = seg_find(posePre, K, gp);
+    const int p = gp - posePre[k];
     double acc[36];
 #pragma unroll
-    for (int i = 0; i < 36; i++) acc[i] = 0.0;
-    for (int b = b0 + lane; b < b1; b += 32) {
-        int j = sortedVal[b] - wPre[k];
-        double W[18], Tf[9], WT[18];
-        sm::load<18>(M.W + 18 * (size_t)j, W);
-        sm::load<9>(TfBuf + 9 * (size_t)(featPre[k] + M.feature[j]), Tf);
-        sm::mm<6, 3, 3>(W, Tf, WT);
+    for (int q = 0; q < 36; q++) acc[q] = 0.0;
+    for (int c = chunkPre[k] + lane; c < chunkPre[k + 1]; c += 32) {
+        const int *tab = chunkPoses + 32 * (size_t)c;
+        const int np = tab[31];
+        int lo = 0, hi = np;                     // np == 0: slow-path chunk, nothing recorded
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (tab[mid] < p) lo = mid + 1; else hi = mid; }
+        if (lo < np && tab[lo] == p) {
+            const double2 *r = reinterpret_cast<const double2 *>(chunkRec + 36 * (32 * (size_t)c + lo));
 #pragma unroll
-        for (int i = 0; i < 18; i++) { acc[i] += W[i]; acc[18 + i] += WT[i]; }
+            for (int q = 0; q < 18; q++) { double2 v = r[q]; acc[2 * q] += v.x; acc[2 * q + 1] += v.y; }
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 36; i++) {
-        double s = sm::warp_sum(acc[i]);
-        if (lane == 0) atomicAdd(poseAcc + 36 * (size_t)gp + i, s);
-    }
-}
-
-// one thread per pose: U'(p,pos) += oriented [-D_p^T SW Q | D_p^T SWT];  U'(pos,pos) += G + G^T with
-// G = C_p^T [-SW Q | SWT]
-__global__ void __launch_bounds__(128)
-k_tf_posefin(DMap *__restrict__ out, const int *__restrict__ posePre, int K, int totPose,
-             const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj,
-             const double *__restrict__ poseAcc)
-{
-    int gp0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = gp0 < totPose;             // no early return: the warp stays converged
-    const int gp = live ? gp0 : totPose - 1;
-    int k = seg_find(posePre, K, gp);
-    int p = gp - posePre[k];
+    for (int q = 0; q < 36; q++) acc[q] = sm::warp_sum(acc[q]);
+    if (lane != 0) return;
     const TfConst &c = tc[k];
     const int pid = c.posID;
     const bool isPos = (p == pid);
     double Q[9], SW[18], SWT[18], SWQ[18];
     sm::load<9>(c.Q, Q);
-    sm::load<18>(poseAcc + 36 * (size_t)gp, SW);
-    sm::load<18>(poseAcc + 36 * (size_t)gp + 18, SWT);
+#pragma unroll
+    for (int q = 0; q < 18; q++) {
+        SW[q] = acc[q] + poseAccSlow[36 * (size_t)gp + q];
+        SWT[q] = acc[18 + q] + poseAccSlow[36 * (size_t)gp + 18 + q];
+    }
     sm::mm<6, 3, 3>(SW, Q, SWQ);
     const PoseJac &J = pj[gp];
     double a1[18], a3[18];
     jt_mul<3>(Q, isPos ? -1.0 : 1.0, J.b1, J.c1, isPos, SWQ, a1);
     jt_mul<3>(Q, isPos ? -1.0 : 1.0, J.b1, J.c1, isPos, SWT, a3);
-    double *u = out[k].U + 36 * (size_t)p;
-    // every pose of a map adds into the map's (pos,pos) block: reduced across the warp first
-    // (lanes of one warp mostly belong to one map), otherwise the root map's 3499 poses serialise
-    // on 36 addresses
-    double G2[36];
+    double X[36], G2[36];
 #pragma unroll
-    for (int q = 0; q < 36; q++) G2[q] = 0.0;
-    if (live) {
+    for (int q = 0; q < 36; q++) { X[q] = 0.0; G2[q] = 0.0; }
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            double xrq = (q < 3) ? -a1[3 * r + q] : a3[3 * r + q - 3];
+            if (p < pid) X[6 * r + q] = xrq;
+            else if (p > pid) X[6 * q + r] = xrq;
+            else { G2[6 * r + q] += xrq; G2[6 * q + r] += xrq; }
+        }
+    if (!isPos) {
+        double a2[18], a4[18];
+        jt_mul<3>(Q, -1.0, J.f2, J.g2, true, SWQ, a2);
+        jt_mul<3>(Q, -1.0, J.f2, J.g2, true, SWT, a4);
 #pragma unroll
         for (int r = 0; r < 6; r++)
 #pragma unroll
             for (int q = 0; q < 6; q++) {
-                double xrq = (q < 3) ? -a1[3 * r + q] : a3[3 * r + q - 3];
-                if (p < pid) atomicAdd(u + 6 * r + q, xrq);
-                else if (p > pid) atomicAdd(u + 6 * q + r, xrq);
-                else { G2[6 * r + q] += xrq; G2[6 * q + r] += xrq; }
+                double grq = (q < 3) ? -a2[3 * r + q] : a4[3 * r + q - 3];
+                G2[6 * r + q] += grq;
+                G2[6 * q + r] += grq;
             }
-        if (!isPos) {
-            double a2[18], a4[18];
-            jt_mul<3>(Q, -1.0, J.f2, J.g2, true, SWQ, a2);
-            jt_mul<3>(Q, -1.0, J.f2, J.g2, true, SWT, a4);
-#pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-                for (int q = 0; q < 6; q++) {
-                    double grq = (q < 3) ? -a2[3 * r + q] : a4[3 * r + q - 3];
-                    G2[6 * r + q] += grq;
-                    G2[6 * q + r] += grq;
-                }
-        }
     }
-    sm::warp_agg_atomic_add<36>(out[k].U + 36 * (size_t)pid, G2, live);
+    const size_t r0 = 2 * (size_t)gp;
+    if (!isPos) rec_write(rkey, rval, r0, posePre[k] + p, X); else rkey[r0] = none;
+    rec_write(rkey, rval, r0 + 1, posePre[k] + pid, G2);
 }
 
-#include "transform_chunk.cuh"
+// target t = global pose index = slot t - posePre[k] of map k's new U list
+struct ApplyU {
+    DMap *out;
+    const int *posePre;
+    int K;
+    __device__ void operator()(int t, int q, double sum, int) const
+    {
+        const int k = seg_find(posePre, K, t);
+        out[k].U[36 * (size_t)(t - posePre[k]) + q] = sum;
+    }
+};
+
+
 
 } // namespace
 
@@ -701,87 +585,66 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
     k_tf_const<<<ceil_div(K, 64), 64, 0, s>>>(A.d.p, B.d.p, A.dPosePre.p, K, dPos.p, dSizes.p + K, tc.p, pj.p); nl++;
     k_tf_pose<<<ceil_div(A.totPose, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dPosePre.p, K, A.totPose, tc.p, pj.p); nl++;
     k_tf_uinit<<<ceil_div(A.totPose, TB), TB, 0, s>>>(B.d.p, A.dPosePre.p, K, A.totPose, dPos.p); nl++;
+    // feature chunks of the one-pass W/V kernel (transform_chunk.cuh): CTA per <= 128 consecutive features
+    std::vector<tfc::Chunk> chunks;
+    std::vector<int> chunkPre(K + 1, 0);
+    int maxWords = 1;
+    for (int k = 0; k < K; k++) {
+        maxWords = std::max(maxWords, (A.h[k].m + 31) / 32);
+        for (int f0 = 0; f0 < A.h[k].n; f0 += tfc::TC_FCH)
+            chunks.push_back({k, f0, std::min(A.h[k].n, f0 + tfc::TC_FCH)});
+        chunkPre[k + 1] = (int)chunks.size();
+    }
+    const int nChunks = (int)chunks.size();
+    // Records of the deterministic U' accumulation (det_accum.cuh), target = global pose index of the
+    // slot, `none` = totPose:  [0, 4 totU) k_ucong | [.., + 2 totPose) k_tf_posefin | [.., + nChunks) chunks
+    const int none = A.totPose;
+    const size_t recU = 0, recP = 4 * (size_t)A.totU, recC = recP + 2 * (size_t)A.totPose;
+    const size_t nrec = recC + (size_t)nChunks;
+    if (nrec > 0x7fffffffull) throw LsfmError(LSFM_ERR_ARG, "level too large for 32-bit record indices");
+    DevBuf<int> rkey(nrec, s);
+    DevBuf<double> rval(36 * nrec, s);
     if (A.totU > 0) {
         k_ucong<<<ceil_div(A.totU, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dUPre.p, A.dPosePre.p, K, A.totU,
-                                                     tc.p, pj.p, uScan.p); nl++;
+                                                     tc.p, pj.p, uScan.p, rkey.p + recU, rval.p + 36 * recU, none); nl++;
     }
-    if (A.totFeat > 0) {
-        static const bool tf_v3 = getenv("LSFM_TF_V3") != nullptr;
-        if (!tf_v3) {
-            // default: one pass over W, CTA per chunk of consecutive features (transform_chunk.cuh)
-            std::vector<tfc::Chunk> chunks;
-            int maxWords = 1;
-            for (int k = 0; k < K; k++) {
-                maxWords = std::max(maxWords, (A.h[k].m + 31) / 32);
-                for (int f0 = 0; f0 < A.h[k].n; f0 += tfc::TC_FCH)
-                    chunks.push_back({k, f0, std::min(A.h[k].n, f0 + tfc::TC_FCH)});
-            }
-            const int nChunks = (int)chunks.size();
-            DevBuf<tfc::Chunk> dChunks(nChunks, s);
-            dChunks.upload(chunks);
-            DevBuf<double> poseAcc(36 * (size_t)A.totPose, s);
-            poseAcc.zero();
-            static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;   // test hook: slow path
-            const int cmaxUse = force_ovf ? 4 : tfc::TC_CMAX;
-            const size_t shb = tfc::Layout::bytes(maxWords);
-            static size_t shb_set = 0;
-            if (shb > shb_set) {
-                CUDA_CHECK(cudaFuncSetAttribute(tfc::k_tf_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
-                shb_set = shb;
-            }
-            // stage timer of its own: this one kernel carries the W/V bytes of the transform
-            //   in : W 144 + photo 4 per block; V 72 + X 24 + id 4 + wPtr 4 per feature
-            //   out: W 144 + photo/feature 8 per block; V 72 + X 24 + id 4 + wPtr 4 per feature
-            ctx.end(0.0, 0.0, nl);
-            nl = 0;
-            ctx.begin("transform.wv");
-            tfc::k_tf_chunk<<<nChunks, tfc::TC_THREADS, shb, s>>>(A.d.p, B.d.p, dChunks.p, A.dFeatPre.p, A.dPosePre.p,
-                                                                tc.p, pj.p, fScan.p, poseAcc.p, cmaxUse);
-            {
-                double wvBytes = 0.0;
-                for (int k = 0; k < K; k++)
-                    wvBytes += 148.0 * A.h[k].nW + 152.0 * out[k].d.nW + 2.0 * 104.0 * A.h[k].n;
-                bytes -= wvBytes;
-                ctx.end(wvBytes, 0.0, 1);
-            }
-            ctx.begin("transform");
-            k_tf_posefin<<<ceil_div(A.totPose, 128), 128, 0, s>>>(B.d.p, A.dPosePre.p, K, A.totPose, tc.p, pj.p,
-                                                                 poseAcc.p); nl++;
-        } else {
-            DevBuf<double> TfBuf(9 * (size_t)A.totFeat, s);
-            k_tf_featprep<<<ceil_div(A.totFeat, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dFeatPre.p, K, A.totFeat,
-                                                                  tc.p, fScan.p, TfBuf.p); nl++;
-            if (A.totW > 0) {
-                const int totW = A.totW, totP = A.totPose;
-                DevBuf<int> sortKey(totW, s), sortVal(totW, s), sortedKey(totW, s), sortedVal(totW, s);
-                k_tf_wblock3<<<ceil_div(totW, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dWPre.p, A.dFeatPre.p,
-                                                               A.dPosePre.p, K, totW, tc.p, pj.p,
-                                                               sortKey.p, sortVal.p); nl++;
-                int bits = 1;
-                while ((1ll << bits) < (long long)totP + 1) bits++;
-                {
-                    size_t tb = 0;
-                    cub::DeviceRadixSort::SortPairs(nullptr, tb, sortKey.p, sortedKey.p, sortVal.p, sortedVal.p,
-                                                    totW, 0, bits, s);
-                    DevBuf<char> tmp(tb, s);
-                    cub::DeviceRadixSort::SortPairs(tmp.p, tb, sortKey.p, sortedKey.p, sortVal.p, sortedVal.p,
-                                                    totW, 0, bits, s); nl += 3;
-                }
-                DevBuf<int> poseStart(totP + 2, s), nch(totP + 2, s), chScan(totP + 2, s);
-                k_pose_start<<<ceil_div(totP + 1, TB), TB, 0, s>>>(sortedKey.p, totW, totP, poseStart.p); nl++;
-                k_pose_nchunks<<<ceil_div(totP + 1, TB), TB, 0, s>>>(poseStart.p, totP, nch.p); nl++;
-                exclusive_scan(ctx, nch.p, chScan.p, totP + 1); nl += 2;
-                DevBuf<double> poseAcc(36 * (size_t)totP, s);
-                poseAcc.zero();
-                long long maxChunks = (long long)totW / PS_CHUNK + totP + 1;
-                k_tf_posesum<<<ceil_div(maxChunks * 32, 128), 128, 0, s>>>(A.d.p, A.dWPre.p, A.dFeatPre.p,
-                                                                         A.dPosePre.p, K, totP, poseStart.p,
-                                                                         chScan.p, sortedVal.p, TfBuf.p,
-                                                                         poseAcc.p); nl++;
-                k_tf_posefin<<<ceil_div(totP, 128), 128, 0, s>>>(B.d.p, A.dPosePre.p, K, totP, tc.p, pj.p,
-                                                               poseAcc.p); nl++;
-            }
+    DevBuf<tfc::Chunk> dChunks(std::max(nChunks, 1), s);
+    DevBuf<int> dChunkPre(K + 1, s), chunkPoses(32 * (size_t)std::max(nChunks, 1), s);
+    DevBuf<double> chunkRec(36 * 32 * (size_t)std::max(nChunks, 1), s);
+    DevBuf<double> poseAcc(36 * (size_t)A.totPose, s);      // slow-path (chunk overflow) sums only
+    dChunkPre.upload(chunkPre);
+    poseAcc.zero();
+    if (nChunks > 0) {
+        dChunks.upload(chunks);
+        static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;   // test hook: slow path
+        const int cmaxUse = force_ovf ? 4 : tfc::TC_CMAX;
+        const size_t shb = tfc::Layout::bytes(maxWords);
+        ctx.ensure_smem((const void *)tfc::k_tf_chunk, shb);
+        // stage timer of its own: this one kernel carries the W/V bytes of the transform
+        //   in : W 144 + photo 4 per block; V 72 + X 24 + id 4 + wPtr 4 per feature
+        //   out: W 144 + photo/feature 8 per block; V 72 + X 24 + id 4 + wPtr 4 per feature
+        ctx.end(0.0, 0.0, nl);
+        nl = 0;
+        ctx.begin("transform.wv");
+        tfc::k_tf_chunk<<<nChunks, tfc::TC_THREADS, shb, s>>>(A.d.p, B.d.p, dChunks.p, A.dFeatPre.p, A.dPosePre.p,
+                                                            tc.p, pj.p, fScan.p, poseAcc.p, cmaxUse,
+                                                            chunkPoses.p, chunkRec.p, rkey.p + recC, rval.p + 36 * recC);
+        {
+            double wvBytes = 0.0;
+            for (int k = 0; k < K; k++)
+                wvBytes += 148.0 * A.h[k].nW + 152.0 * out[k].d.nW + 2.0 * 104.0 * A.h[k].n;
+            bytes -= wvBytes;
+            ctx.end(wvBytes, 0.0, 1);
         }
+        ctx.begin("transform");
+    }
+    k_tf_posefin<<<ceil_div(32ll * A.totPose, 128), 128, 0, s>>>(A.dPosePre.p, K, A.totPose, tc.p, pj.p, dChunkPre.p,
+                                                              chunkPoses.p, chunkRec.p, poseAcc.p,
+                                                              rkey.p + recP, rval.p + 36 * recP, none); nl++;
+    {
+        det::Sorted srt;
+        nl += det::sort_records(ctx, rkey.p, (int)nrec, none, srt);
+        det::reduce<36>(ctx, srt, rval.p, A.totPose, ApplyU{B.d.p, A.dPosePre.p, K}); nl++;
     }
     KERNEL_CHECK();
     ctx.end(bytes, 0.0, nl);

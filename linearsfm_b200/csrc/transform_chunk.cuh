@@ -19,7 +19,8 @@
 //         (from the W and W T_f tiles);
 //         thread per (feature, element): the feature's wadd rows of this batch -> W'(pos,f)
 // Two barriers per batch; W is read once from HBM and written once.  At the end the pose sums are
-// flushed with one atomic per (local pose, element).
+// written as one record per (chunk, local pose) next to the chunk's sorted pose table; k_tf_posefin
+// gathers them per pose in a fixed order (no FP64 atomics: bit-identical results run to run).
 // Chunks with more than 31 distinct poses take a slow path (thread per block, global atomics).
 #pragma once
 
@@ -52,10 +53,10 @@ struct Layout {
     static constexpr int wptr = Cst + 36 * 8;                              // [FCH+4] int
     static constexpr int optr = wptr + (TC_FCH + 4) * 4;                   // [FCH+4] int
     static constexpr int pidPos = optr + (TC_FCH + 4) * 4;                 // [FCH] int
-    static constexpr int lcnt = pidPos + TC_FCH * 4;                       // [2][32] int: blocks per local pose in the batch
-    static constexpr int poses = lcnt + 2 * 32 * 4;                        // [32] int
+    static constexpr int lcnt = pidPos + TC_FCH * 4;                       // [2][4][32] int: blocks per (warp, local pose) in the batch
+    static constexpr int poses = lcnt + 2 * 4 * 32 * 4;                    // [32] int
     static constexpr int misc = poses + 32 * 4;                            // [4] int
-    static constexpr int lst = misc + 16;                                  // [32][BATCH] uchar: the batch's blocks per local pose
+    static constexpr int lst = misc + 16;                                  // [4][32][32] uchar: the batch's blocks per (warp, local pose), lane order
     static constexpr int bitmap = lst + 32 * TC_BATCH;                     // [words] unsigned + [words] int
     static size_t bytes(int words) { return (size_t)bitmap + 8 * (size_t)words + 16; }
 };
@@ -95,7 +96,9 @@ __global__ void __launch_bounds__(TC_THREADS, 3)
 k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__restrict__ chunks,
            const int *__restrict__ featPre, const int *__restrict__ posePre,
            const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj, const int *__restrict__ fScan,
-           double *__restrict__ poseAcc, int cmaxUse)
+           double *__restrict__ poseAcc, int cmaxUse,
+           int *__restrict__ chunkPoses, double *__restrict__ chunkRec,
+           int *__restrict__ ppKey, double *__restrict__ ppVal)
 {
     typedef Layout L;
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -137,7 +140,7 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     }
     for (int i = tid; i < nfeat; i += TC_THREADS) pidPos[i] = 0x7fffffff;
     for (int i = tid; i < words; i += TC_THREADS) bitmap[i] = 0u;
-    if (tid < 64) lcnt[tid] = 0;
+    for (int i = tid; i < 256; i += TC_THREADS) lcnt[i] = 0;
     if (tid < 9) {
         Cst[tid] = c.Q[tid]; Cst[9 + tid] = c.QA[tid]; Cst[18 + tid] = c.QB[tid]; Cst[27 + tid] = c.QG[tid];
     }
@@ -172,11 +175,13 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     __syncthreads();
     const int nposes = misc[0];
     const bool fast = nposes <= cmaxUse;
+    int *ctab = chunkPoses + 32 * (size_t)blockIdx.x;      // sorted local pose table, [31] = count (0: slow path)
+    if (tid == 0) ctab[31] = fast ? nposes : 0;
     if (fast)
         for (int i = tid; i < words; i += TC_THREADS) {
             unsigned b = bitmap[i];
             int r = prefix[i];
-            while (b) { int bit = __ffs(b) - 1; poses[r++] = i * 32 + bit; b &= b - 1; }
+            while (b) { int bit = __ffs(b) - 1; ctab[r] = i * 32 + bit; poses[r++] = i * 32 + bit; b &= b - 1; }
         }
     double Q[9];
 #pragma unroll
@@ -251,12 +256,14 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
             s += __shfl_down_sync(0xffffffffu, s, 2, 4);
             s += __shfl_down_sync(0xffffffffu, s, 1, 4);
             if (part == 0 && i < 21) {
+                // the chunk's share of U'(pos,pos): one record per chunk (deterministic reduction later)
                 int r = 0, rem = i;
                 while (rem >= 6 - r) { rem -= 6 - r; r++; }
                 int cc = r + rem;
-                double *u = O.U + 36 * (size_t)pid;
-                atomicAdd(u + 6 * r + cc, s);
-                if (cc != r) atomicAdd(u + 6 * cc + r, s);
+                double *u = ppVal + 36 * (size_t)blockIdx.x;
+                u[6 * r + cc] = s;
+                if (cc != r) u[6 * cc + r] = s;
+                if (i == 0) ppKey[blockIdx.x] = posePre[k] + pid;
             }
         }
         __syncthreads();
@@ -271,7 +278,7 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     // ---------------- batches: one thread per W block ----------------
     // phase A for one block; FAST: chunk-local pose slots (lists, Jacobians from shared memory, W
     // through the warp's private part of the Wr tile), else global Jacobians / atomics
-    auto phase_a = [&](auto fast_tag, const int j, int *lc) {
+    auto phase_a = [&](auto fast_tag, const int j, int *lc, const unsigned act) {
         constexpr bool FAST = decltype(fast_tag)::value;
         const int p = M.photo[j];
         int fb;
@@ -343,13 +350,20 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
             row[6] = make_double2(B1[3], B1[4]); row[7] = make_double2(B1[5], B1[6]);
             row[8] = make_double2(B1[7], B1[8]);
         }
-        if (FAST) lst[slot * TC_BATCH + atomicAdd(&lc[slot], 1)] = (unsigned char)tid;
+        if (FAST) {
+            // the batch's blocks per (warp, local pose) in LANE order: the pose sums below then add in
+            // an order that does not depend on the hardware's scheduling
+            const unsigned peers = __match_any_sync(act, slot);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            lst[(warp * 32 + slot) * 32 + rank] = (unsigned char)tid;
+            if (rank == 0) lc[warp * 32 + slot] = __popc(peers);
+        }
     };
 
     int bt = 0;
     for (int jb = w0; jb < w1; jb += TC_BATCH, bt++) {
         const int j = jb + tid;
-        int *lc = lcnt + (bt & 1) * 32;
+        int *lc = lcnt + (bt & 1) * 128;
         if (fast) {
             // the warp's 32 blocks = one contiguous 4.6 KB span: coalesced 16-byte async copies into
             // the warp's private part of the Wr tile; the next batch is pulled into L2 meanwhile
@@ -369,35 +383,39 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
             }
             cp_async_wait_all();
             __syncwarp();
-            if (j < w1) phase_a(std::true_type(), j, lc);
+            const unsigned act = __ballot_sync(0xffffffffu, j < w1);
+            if (j < w1) phase_a(std::true_type(), j, lc, act);
         } else if (j < w1) {
-            phase_a(std::false_type(), j, lc);
+            phase_a(std::false_type(), j, lc, 0u);
         }
         __syncthreads();
-        if (tid < 32) lcnt[((bt & 1) ^ 1) * 32 + tid] = 0;          // the next batch's counters
+        lcnt[((bt & 1) ^ 1) * 128 + tid] = 0;                       // the next batch's counters
         // pose sums (thread owns (local pose, element) pairs for the whole chunk)
 #pragma unroll
         for (int u = 0; u < TC_ACC; u++) {
             const int it = tid + u * TC_THREADS;
             if (it < nitems) {
                 const int slot = it / 36, el = it - 36 * slot;
-                const unsigned *ls4 = reinterpret_cast<const unsigned *>(lst + slot * TC_BATCH);
-                const int nl = lc[slot];
                 const double *src = (el < 18) ? (Wrt + el) : (WTt + (el - 18));
                 double s0 = acc[u], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int i = 0;
-                for (; i + 4 <= nl; i += 4) {             // four independent shared loads in flight
-                    const unsigned b4 = ls4[i >> 2];
-                    s0 += src[TC_LD * (int)(b4 & 255u)];
-                    s1 += src[TC_LD * (int)((b4 >> 8) & 255u)];
-                    s2 += src[TC_LD * (int)((b4 >> 16) & 255u)];
-                    s3 += src[TC_LD * (int)(b4 >> 24)];
-                }
-                if (i < nl) {
-                    const unsigned b4 = ls4[i >> 2];
-                    s0 += src[TC_LD * (int)(b4 & 255u)];
-                    if (i + 1 < nl) s1 += src[TC_LD * (int)((b4 >> 8) & 255u)];
-                    if (i + 2 < nl) s2 += src[TC_LD * (int)((b4 >> 16) & 255u)];
+#pragma unroll
+                for (int w = 0; w < 4; w++) {                 // warp-major, lane order inside: fixed
+                    const unsigned *ls4 = reinterpret_cast<const unsigned *>(lst + (w * 32 + slot) * 32);
+                    const int nl = lc[w * 32 + slot];
+                    int i = 0;
+                    for (; i + 4 <= nl; i += 4) {             // four independent shared loads in flight
+                        const unsigned b4 = ls4[i >> 2];
+                        s0 += src[TC_LD * (int)(b4 & 255u)];
+                        s1 += src[TC_LD * (int)((b4 >> 8) & 255u)];
+                        s2 += src[TC_LD * (int)((b4 >> 16) & 255u)];
+                        s3 += src[TC_LD * (int)(b4 >> 24)];
+                    }
+                    if (i < nl) {
+                        const unsigned b4 = ls4[i >> 2];
+                        s0 += src[TC_LD * (int)(b4 & 255u)];
+                        if (i + 1 < nl) s1 += src[TC_LD * (int)((b4 >> 8) & 255u)];
+                        if (i + 2 < nl) s2 += src[TC_LD * (int)((b4 >> 16) & 255u)];
+                    }
                 }
                 const double s = (s0 + s1) + (s2 + s3);
                 acc[u] = s;
@@ -426,10 +444,7 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
 #pragma unroll
     for (int u = 0; u < TC_ACC; u++) {
         const int it = tid + u * TC_THREADS;
-        if (it < nitems) {
-            const int slot = it / 36, el = it - 36 * slot;
-            atomicAdd(poseAcc + 36 * (size_t)(posePre[k] + poses[slot]) + el, acc[u]);
-        }
+        if (it < nitems) chunkRec[36 * 32 * (size_t)blockIdx.x + it] = acc[u];   // [chunk][slot][36]
     }
 }
 

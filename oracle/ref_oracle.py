@@ -241,3 +241,48 @@ def shim_times():
 
 def shim_reset_timers():
     lib().lsfm_shim_reset_timers()
+
+
+def run_levels_stereo(maps, teacher=None):
+    """The reference's merge tree (lmj_PF3D_Divide_ConquerStereo, LinearSFMImp.cpp:1926-2099) driven
+    level by level from Python with the reference's OWN operators, yielding every intermediate of a
+    level so that a test can feed exactly these inputs to the implementation under test
+    ("teacher forcing": errors of one level never reach the next).
+
+    Yields one dict per level:
+        level                    level number (0 = leaves)
+        E, C                     End / Cur inputs of every pair (lists of LocalMap)
+        Et                       End after lmj_Transform_PF3DStereo(End, Cur.Ref)      (1964)
+        J                        joined maps, lmj_LinearLS_PF3DStereo(Et, Cur)           (1991)
+        rb_idx, rb_in, rb_ref, rb_out   outputs re-based to their first frame           (1997-2025)
+        next                     the maps handed to the next level
+    and finally {'level': 'final', 'rb_in': [root], 'rb_ref': [FRef], 'rb_out': [result]} (2039-2063).
+    """
+    level = list(maps)
+    L = 0
+    while len(level) > 1:
+        cnt = len(level)
+        npairs = cnt // 2
+        E = [level[2 * i] for i in range(npairs)]
+        Cm = [level[2 * i + 1] for i in range(npairs)]
+        Et = [transform_stereo(e, c.Ref) for e, c in zip(E, Cm)]
+        J = [join_stereo(et, c) for et, c in zip(Et, Cm)]
+        nxt = list(J)
+        if cnt % 2:
+            nxt.append(level[cnt - 1])
+        rb_idx, rb_in, rb_ref, rb_out = [], [], [], []
+        for i in range(len(nxt)):
+            if (i + 1) % 2 == 0 and nxt[i].Ref > nxt[i].FRef:
+                rb_idx.append(i); rb_in.append(nxt[i]); rb_ref.append(nxt[i].FRef)
+                nxt[i] = transform_stereo(nxt[i], nxt[i].FRef)
+                rb_out.append(nxt[i])
+        yield dict(level=L, E=E, C=Cm, Et=Et, J=J, rb_idx=rb_idx, rb_in=rb_in, rb_ref=rb_ref,
+                   rb_out=rb_out, next=nxt)
+        level = nxt
+        L += 1
+    root = level[0]
+    if root.Ref > root.FRef:
+        out = transform_stereo(root, root.FRef)
+        yield dict(level="final", rb_in=[root], rb_ref=[root.FRef], rb_out=[out], next=[out])
+    else:
+        yield dict(level="final", rb_in=[], rb_ref=[], rb_out=[], next=[root])

@@ -23,3 +23,6 @@ def test_reference_arm_prints_one_json_line(oracle):
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    # the arm measures the stated config: nothing scaled from a prefix, timed solves are counted
+    assert d["extrapolated"] is False and "48 local maps" in d["config"]["workload"]
+    assert d["steps"] == 1 and d["warmup"] == 0 and "all 48 local maps" in d["cpu_baseline"]["sample"]
