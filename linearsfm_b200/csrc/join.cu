@@ -509,7 +509,7 @@ std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHand
         }
         det::Sorted srt;
         nl += det::sort_records(ctx, rkey.p, 2 * J.totU, J.totPose, srt);
-        det::reduce<6>(ctx, srt, rval.p, J.totPose, ApplyEP{eP.p}); nl++;
+        nl += det::reduce<6>(ctx, srt, rval.p, J.totPose, ApplyEP{eP.p});
     }
     if (J.totFeat > 0) {
         k_join_featinit<<<ceil_div(J.totFeat, TB), TB, 0, s>>>(E.d.p, C.d.p, J.d.p, J.dFeatPre.p, K, J.totFeat,

@@ -15,9 +15,10 @@
 //     re-layout   : one thread per (block, row): the row of W V^-1 -> a dense tile (W itself stays in
 //                   the raw buffer; both operands are read with 16-byte shared loads);
 //     pair update : thread (i,j) adds W V^-1|_i * W^T|_j for every feature that sees both poses.
-// One 288-byte record per touched pair and chunk (diagonal pairs: upper triangle + the pose's share of E
-// in six lower-triangle entries); the records of an S block are added up in a fixed order afterwards
-// (det_accum.cuh) -- no FP64 atomics, results are bit-identical from run to run.  Three instantiations trade registers /
+// One flush per touched pair and chunk: 36 fixed-point integer atomics into the S block (exact, hence
+// independent of the order in which the chunks arrive; scale from the diagonal of U, see solve.cu), and
+// for the diagonal pairs the pose's share of E as a 6-vector record that k_e_gather adds up per pose
+// in a fixed order -- no FP64 atomics, results are bit-identical from run to run.  Three instantiations trade registers /
 // shared memory for resident CTAs: (CMAX 8, 64 thr) x4-5 per SM for the lower tree levels,
 // (16, 128 thr) x2, (31, 256 thr) x1 for the top levels.
 #pragma once
@@ -73,7 +74,7 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
              const double *__restrict__ Vinv, const double *__restrict__ dvec, const int *__restrict__ split,
              const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
              double *__restrict__ S, double *__restrict__ E,
-             const int *__restrict__ recOff, int *__restrict__ rkey, double *__restrict__ rval)
+             const int *__restrict__ sexp, long long *__restrict__ Sfx, double *__restrict__ Erec)
 {
     static_assert(MAXBLK >= 2 * CMAX && MAXBLK <= 255, "block budget");
     static_assert(SLOTS == 1, "one pair slot per thread");
@@ -284,19 +285,42 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     (void)touched;
     if (pi[0] >= 0 && pr0[0] == 0) {
         // the pattern kernel's bitmap of the chunk's pairs (row-major upper triangle incl. diagonal)
-        // decides which pairs exist; the record position is the pair's rank in that bitmap
+        // decides which pairs exist
         const int i = pi[0], j = pj[0];
         const int idx = i * nposes - (i * (i - 1)) / 2 + (j - i);
-        const unsigned wbit = (unsigned)ci[32 + (idx >> 5)];
-        if ((wbit >> (idx & 31)) & 1u) {
-            int rank = __popc(wbit & ((1u << (idx & 31)) - 1u));
-            for (int w = 0; w < (idx >> 5); w++) rank += __popc((unsigned)ci[32 + w]);
-            const size_t r = (size_t)recOff[blockIdx.x] + rank;
+        if (((unsigned)ci[32 + (idx >> 5)] >> (idx & 31)) & 1u) {
             const int gi = poses[i], gj = poses[j];
-            rkey[r] = find_slot(keys, rowPtr, posePre[k] + gi, pair_key(k, gi, gj));
-            double2 *dst = reinterpret_cast<double2 *>(rval + 36 * r);
+            const int slot = find_slot(keys, rowPtr, posePre[k] + gi, pair_key(k, gi, gj));
+            unsigned long long *sp = reinterpret_cast<unsigned long long *>(Sfx) + 36 * (size_t)slot;
+            int ei[6], ej[6];
 #pragma unroll
-            for (int q = 0; q < 18; q++) dst[q] = make_double2(acc[0][2 * q], acc[0][2 * q + 1]);
+            for (int q = 0; q < 6; q++) {
+                ei[q] = sexp[6 * (size_t)(posePre[k] + gi) + q];
+                ej[q] = sexp[6 * (size_t)(posePre[k] + gj) + q];
+            }
+            // fixed point, integer atomics: exact, hence independent of the order the chunks arrive in
+            if (i == j) {
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int c = r; c < 6; c++) {
+                        const long long v = __double2ll_rn(acc[0][6 * r + c] * pow2(fx_shift(ei[r], ej[c])));
+                        atomicAdd(sp + 6 * r + c, (unsigned long long)v);
+                        if (c > r) atomicAdd(sp + 6 * c + r, (unsigned long long)v);
+                    }
+                // the pose's share of E from this chunk: a record, gathered per pose by k_e_gather
+                double *e = Erec + 6 * (32 * (size_t)blockIdx.x + i);
+#pragma unroll
+                for (int q = 0; q < 6; q++) e[q] = acc[0][EIDX[q]];
+            } else {
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int c = 0; c < 6; c++) {
+                        const long long v = __double2ll_rn(acc[0][6 * r + c] * pow2(fx_shift(ei[r], ej[c])));
+                        atomicAdd(sp + 6 * r + c, (unsigned long long)v);
+                    }
+            }
         }
     }
 }

@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(PAT_THREADS)
 k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
             unsigned *__restrict__ bm, const int *__restrict__ bmOff,
             int *__restrict__ maxNposes, int pat_cmax, int *__restrict__ chunkInfo,
-            int *__restrict__ blkInfo, const int *__restrict__ wPre, int *__restrict__ recCnt)
+            int *__restrict__ blkInfo, const int *__restrict__ wPre,
+            unsigned *__restrict__ patBits, int bitsStride)
 {
     extern __shared__ unsigned smu[];
     const FeatChunk ch = chunks[blockIdx.x];
@@ -93,6 +94,15 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     __syncthreads();
     const int nposes = misc[0];
     if (tid == 0) { atomicMax(maxNposes, nposes); ci[31] = nposes; }
+    // pose bitmap + popcount prefix of the chunk -> global: the E gather (k_e_gather) finds a pose's slot
+    // in this chunk with two loads (overflow chunks publish an empty bitmap: they record nothing)
+    {
+        unsigned *gb = patBits + (size_t)blockIdx.x * 2 * bitsStride;
+        for (int i = tid; i < words; i += nt) {
+            gb[i] = (nposes <= pat_cmax) ? bitmap[i] : 0u;
+            gb[bitsStride + i] = (unsigned)prefix[i];
+        }
+    }
     if (nposes <= pat_cmax) {
         int *bi = blkInfo + wPre[ch.k];
         for (int f = ch.f0 + tid; f < ch.f1; f += nt) {
@@ -116,14 +126,8 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
             while (b) { int bit = __ffs(b) - 1; poses[r] = i * 32 + bit; ci[r] = i * 32 + bit; r++; b &= b - 1; }
         }
         __syncthreads();
-        // the chunk's pair bitmap stays behind for the Schur kernel ([32..47]); its popcount is the number
-        // of S-block records the chunk will write (deterministic accumulation, det_accum.cuh)
+        // the chunk's pair bitmap stays behind for the Schur kernel ([32..47])
         if (tid < 16) ci[32 + tid] = (int)pairBits[tid];
-        if (tid == 0) {
-            int c = 0;
-            for (int w = 0; w < 16; w++) c += __popc(pairBits[w]);
-            recCnt[blockIdx.x] = c;
-        }
         // the chunk's distinct pairs -> the join's pose-pair bitmap (exact dedupe across chunks)
         const int npairs = nposes * (nposes + 1) / 2;
         for (int t = tid; t < npairs; t += nt) {
@@ -135,7 +139,6 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         return;
     }
     // overflow: too many distinct poses in this chunk -> per-feature pairs straight to the bitmap
-    if (tid == 0) recCnt[blockIdx.x] = 0;
     for (int f = ch.f0 + tid; f < ch.f1; f += nt) {
         int a0 = M.wPtr[f], a1 = M.wPtr[f + 1];
         for (int a = a0; a < a1; a++)
@@ -354,29 +357,86 @@ __device__ __noinline__ void schur_block_slow(const DMap &M, int k, int a, const
 
 constexpr int SCH_FCHUNK = 128;        // features per chunk (pattern + Schur kernels)
 
-// det::reduce target t = S block slot.  Off-diagonal blocks: all 36 sums.  Diagonal blocks: the records
-// carry the upper triangle (mirrored here) and, in six lower-triangle entries, the pose's share of E.
-struct ApplyS {
-    const u64 *keys;
-    const int *posePre;
-    double *S, *E;
-    __device__ void operator()(int t, int q, double sum, int cnt) const
-    {
-        if (cnt == 0) return;
-        const u64 key = keys[t];
-        const int k = (int)(key >> 44), lo = (int)((key >> 22) & ((1u << 22) - 1)), hi = (int)(key & ((1u << 22) - 1));
-        double *sp = S + 36 * (size_t)t;
-        if (lo != hi) { sp[q] -= sum; return; }
-        const int r = q / 6, c = q - 6 * r;
-        if (c >= r) {
-            sp[6 * r + c] -= sum;
-            if (c > r) sp[6 * c + r] -= sum;
-        } else {
-            const int e = (q == 6) ? 0 : (q == 12) ? 1 : (q == 13) ? 2 : (q == 18) ? 3 : (q == 19) ? 4 : (q == 20) ? 5 : -1;
-            if (e >= 0) E[6 * (size_t)(posePre[k] + lo) + e] -= sum;
+// ---- order-independent accumulation of S ------------------------------------------------------
+// The chunks' contributions to one S block arrive in an order the hardware chooses.  FP64 atomics would
+// make the last bits of S differ from run to run; instead every contribution is converted to 64-bit
+// FIXED POINT and added with integer atomics, which are exact and therefore order-independent.  The
+// scale of entry (6i+r, 6j+c) comes from a bound that holds for every partial sum: the subtracted
+// matrix D = sum_f W V^-1 W^T is positive semi-definite with D <= U on the diagonal (S = U - D must be
+// positive definite), so |D(ir,jc)| <= sqrt(U(ir,ir) U(jc,jc)).  With ex(x) = ilogb(x) + 1 the entry is
+// below 2^eb, eb = ceil((ex_ir + ex_jc) / 2), and is stored as round(x 2^(60 - eb)): |sum| < 2^60, the
+// quantum is 2^-60 of the bound (double's own quantum is 2^-53 of the value).
+__device__ __forceinline__ int row_exp_of(double u) { return (u > 0.0 && u < 1e300) ? ilogb(u) + 1 : 0; }
+__device__ __forceinline__ int fx_shift(int ea, int eb_) { return 60 - ((ea + eb_ + 1) >> 1); }
+__device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
+
+// one thread per (pose, row): exponent of the diagonal entry U(ir,ir), read from S after k_s_from_u
+__global__ void k_row_exp(const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
+                          const DMap *__restrict__ J, const int *__restrict__ posePre, int K, int totP,
+                          const double *__restrict__ S, int *__restrict__ sexp)
+{
+    int g6 = blockIdx.x * blockDim.x + threadIdx.x;
+    int g = g6 / 6, r = g6 - 6 * g;
+    if (g >= totP) return;
+    int k = seg_find(posePre, K, g);
+    int p = g - posePre[k];
+    int slot = rowPtr[g];
+    int e = 0;
+    if (slot < rowPtr[g + 1] && keys[slot] == pair_key(k, p, p)) e = row_exp_of(S[36 * (size_t)slot + 7 * r]);
+    sexp[g6] = e;
+}
+
+// S -= fixed-point sums (one thread per entry)
+__global__ void k_s_convert(const u64 *__restrict__ keys, int nuis, const int *__restrict__ posePre,
+                            const int *__restrict__ sexp, const long long *__restrict__ Sfx,
+                            double *__restrict__ S)
+{
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t t = g / 36;
+    if (t >= (size_t)nuis) return;
+    int q = (int)(g - 36 * t), r = q / 6, c = q - 6 * r;
+    const long long v = Sfx[g];
+    if (v == 0) return;
+    const u64 key = keys[t];
+    const int k = (int)(key >> 44), lo = (int)((key >> 22) & ((1u << 22) - 1)), hi = (int)(key & ((1u << 22) - 1));
+    const int sh = fx_shift(sexp[6 * (size_t)(posePre[k] + lo) + r], sexp[6 * (size_t)(posePre[k] + hi) + c]);
+    S[g] -= (double)v * pow2(-sh);
+}
+
+// E_p -= sum over the chunks of the pose's join of the chunk's share (record [chunk][slot][6]); one warp
+// per pose, chunks strided over the lanes, lane-private sums, fixed butterfly: bit-identical every run
+__global__ void __launch_bounds__(128)
+k_e_gather(const int *__restrict__ posePre, int K, int totP, const int *__restrict__ chunkPre,
+           const unsigned *__restrict__ patBits, int bitsStride, const double *__restrict__ Erec,
+           double *__restrict__ E)
+{
+    const int lane = threadIdx.x & 31;
+    const int gp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gp >= totP) return;
+    const int k = seg_find(posePre, K, gp);
+    const int p = gp - posePre[k];
+    const int pw = p >> 5;
+    const unsigned pbit = 1u << (p & 31);
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int c = chunkPre[k] + lane; c < chunkPre[k + 1]; c += 32) {
+        const unsigned *gb = patBits + (size_t)c * 2 * bitsStride;
+        const unsigned w = gb[pw];
+        if (w & pbit) {
+            const int slot = (int)gb[bitsStride + pw] + __popc(w & (pbit - 1u));
+            const double2 *r = reinterpret_cast<const double2 *>(Erec + 6 * (32 * (size_t)c + slot));
+            const double2 v0 = r[0], v1 = r[1], v2 = r[2];
+            acc[0] += v0.x; acc[1] += v0.y; acc[2] += v1.x; acc[3] += v1.y; acc[4] += v2.x; acc[5] += v2.y;
         }
     }
-};
+#pragma unroll
+    for (int q = 0; q < 6; q++) acc[q] = sm::warp_sum(acc[q]);
+    if (lane < 6) {
+        double v = acc[0];
+#pragma unroll
+        for (int q = 1; q < 6; q++) if (lane == q) v = acc[q];
+        E[6 * (size_t)gp + lane] -= v;
+    }
+}
 } // namespace
 #include "schur_pipe.cuh"
 namespace {
@@ -820,9 +880,14 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     int maxNposes = 1 << 30;             // max distinct poses of any chunk (measured by k_pat_chunk)
     DevBuf<int> dMaxNp(1, s);
     DevBuf<int> chunkInfo((size_t)CHUNK_INFO_INTS * std::max(nChunks, 1), s), blkInfo((size_t)std::max(J.totW, 1), s);
-    // S-block records per chunk (deterministic accumulation of the Schur complement): counts from the
-    // pattern kernel, offsets by one scan, the total comes to the host with the pattern
-    DevBuf<int> recCnt((size_t)nChunks + 1, s), recOff((size_t)nChunks + 1, s);
+    // per chunk: pose bitmap + popcount prefix (the E gather's index) and the chunks of every join
+    const int bitsStride = maxWords;
+    DevBuf<unsigned> patBits(2 * (size_t)bitsStride * std::max(nChunks, 1), s);
+    std::vector<int> chunkPre(K + 1, 0);
+    for (const FeatChunk &c : chunks) chunkPre[c.k + 1]++;
+    for (int k = 0; k < K; k++) chunkPre[k + 1] += chunkPre[k];
+    DevBuf<int> dChunkPre(K + 1, s);
+    dChunkPre.upload(chunkPre);
     // test hook: LSFM_FORCE_OVERFLOW=1 sends every chunk with > 4 poses down the overflow paths
     static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
     const int pat_cmax_used = force_ovf ? 4 : PAT_CMAX;
@@ -849,10 +914,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
         dMaxNp.zero();
         k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, bm.p, dBmOff.p, dMaxNp.p, pat_cmax_used,
-                                                      chunkInfo.p, blkInfo.p, J.dWPre.p, recCnt.p); nl++;
+                                                      chunkInfo.p, blkInfo.p, J.dWPre.p, patBits.p, bitsStride); nl++;
     }
-    CUDA_CHECK(cudaMemsetAsync(recCnt.p + nChunks, 0, sizeof(int), s));
-    exclusive_scan(ctx, recCnt.p, recOff.p, nChunks + 1); nl += 2;
     if (gauge) {   // mono: the zero pose has no block at all after the join; keep every diagonal
         k_pat_diag<<<ceil_div(J.totPose, TB), TB, 0, s>>>(J.d.p, J.dPosePre.p, K, J.totPose, bm.p, dBmOff.p); nl++;
     }
@@ -872,16 +935,13 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     u64 *hKeys = (u64 *)pin;
     int *hRowPtr = (int *)(pin + sizeof(u64) * ((size_t)keyCap + 1));
     int *hMaxNp = hRowPtr + J.totPose + 1;
-    int *hNrec = hMaxNp + 1;
     *hMaxNp = 0;
     if (nChunks > 0) CUDA_CHECK(cudaMemcpyAsync(hMaxNp, dMaxNp.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaMemcpyAsync(hNrec, recOff.p + nChunks, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (keyCap) CUDA_CHECK(cudaMemcpyAsync(hKeys, keys.p, sizeof(u64) * keyCap, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(hRowPtr, rowPtr.p, sizeof(int) * (J.totPose + 1), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     ctx.idle_begin();
     nuis = hRowPtr[J.totPose];
-    const int nrec = *hNrec;
     if (nChunks > 0) maxNposes = *hMaxNp;
     if (nuis > keyCap) {                  // bound overshot: emit and fetch again with the exact size
         keys.alloc((size_t)nuis, s);
@@ -914,11 +974,15 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     if (J.totU > 0) {
         k_s_from_u<<<ceil_div(J.totU, TB), TB, 0, s>>>(J.d.p, J.dUPre.p, J.dPosePre.p, K, J.totU, keys.p, rowPtr.p, S.p); nl++;
     }
+    // fixed-point accumulators of S (order-independent integer atomics) and their per-row exponents
+    DevBuf<long long> Sfx(36 * (size_t)std::max(nuis, 1), s);
+    DevBuf<int> sexp(6 * (size_t)std::max(J.totPose, 1), s);
+    DevBuf<double> Erec(6 * 32 * (size_t)std::max(nChunks, 1), s);
+    CUDA_CHECK(cudaMemsetAsync(Sfx.p, 0, sizeof(long long) * 36 * (size_t)std::max(nuis, 1), s));
+    k_row_exp<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(keys.p, rowPtr.p, J.d.p, J.dPosePre.p, K, J.totPose, S.p, sexp.p); nl++;
     ctx.end(72.0 * J.totFeat * 2 + 576.0 * J.totU, 0.0, nl);
     nl = 0;
     ctx.begin("solve.schur");
-    DevBuf<int> rkey((size_t)std::max(nrec, 1), s);
-    DevBuf<double> rval(36 * (size_t)std::max(nrec, 1), s);
     if (J.totW > 0) {
         static const bool use_v1 = getenv("LSFM_SCHUR_V1") != nullptr;
         if (use_v1) {
@@ -931,7 +995,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
                     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
                 kern<<<nChunks, threads, shb, s>>>(J.d.p, dChunks.p, chunkInfo.p, blkInfo.p, pat_cmax_used, J.dWPre.p,
                                                   J.dFeatPre.p, J.dPosePre.p, Vinv.p, dvec.p, split, keys.p, rowPtr.p, S.p, E.p,
-                                                  recOff.p, rkey.p, rval.p);
+                                                  sexp.p, Sfx.p, Erec.p);
             };
             static const bool force_ovf2 = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
             if (maxNposes <= 8 || force_ovf2)
@@ -941,10 +1005,10 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             else
                 launch(schur_pipe::k_schur_pipe<31, 248, 32, 512, 1>, schur_pipe::Layout<31, 248, 32>::bytes(), 512);
             nl++;
-            // S(a,b) -= sum of the block's records, E_p -= the share carried by the diagonal records
-            det::Sorted srt;
-            nl += det::sort_records(ctx, rkey.p, nrec, nuis, srt);
-            det::reduce<36>(ctx, srt, rval.p, nuis, ApplyS{keys.p, J.dPosePre.p, S.p, E.p}); nl++;
+            // S -= the fixed-point sums; E_p -= the chunks' shares, gathered per pose in a fixed order
+            k_s_convert<<<ceil_div(36ll * nuis, TB), TB, 0, s>>>(keys.p, nuis, J.dPosePre.p, sexp.p, Sfx.p, S.p); nl++;
+            k_e_gather<<<ceil_div(32ll * J.totPose, 128), 128, 0, s>>>(J.dPosePre.p, K, J.totPose, dChunkPre.p, patBits.p,
+                                                                    bitsStride, Erec.p, E.p); nl++;
         }
     }
     KERNEL_CHECK();

@@ -223,42 +223,22 @@ __device__ __forceinline__ void rec_write(int *__restrict__ key, double *__restr
     for (int q = 0; q < 18; q++) dst[q] = make_double2(P[2 * q], P[2 * q + 1]);
 }
 
-// record for the (pos,pos) slot: when the whole warp adds into the same target the 36 values are
-// butterfly-reduced first (fixed order) and only the leader's record carries a key
-__device__ __forceinline__ void rec_write_hot(int *__restrict__ key, double *__restrict__ val, size_t r,
-                                              int target, int none, double *Q, bool active)
-{
-    const unsigned full = 0xffffffffu;
-    const unsigned amask = __ballot_sync(full, active);
-    if (amask == 0u) return;
-    const int leader = __ffs(amask) - 1;
-    const int t0 = __shfl_sync(full, target, leader);
-    const bool uniform = __all_sync(full, !active || target == t0);
-    if (uniform) {
-#pragma unroll
-        for (int i = 0; i < 36; i++) Q[i] = sm::warp_sum(active ? Q[i] : 0.0);
-        if (!active) return;
-        if ((int)(threadIdx.x & 31) == leader) rec_write(key, val, r, target, Q);
-        else key[r] = none;
-    } else if (active) {
-        rec_write(key, val, r, target, Q);
-    }
-}
-
-// one thread per old U block (LinearSFMImp.cpp:725-1266): four products per block, written as records
-// 4g .. 4g+3 (targets: (pos,pos); slot j; slot i or j; slot i) -- survivors (neither index == posID) are
-// stored straight into their own slot.
+// one thread per old U block (LinearSFMImp.cpp:725-1266): four products per block.  Everything that
+// lands in the (pos,pos) slot is summed in the thread and written as ONE record of the map's hot-target
+// list (ppKey/ppVal, reduced per map by k_pp_reduce); the other products are records 3g .. 3g+2 of the
+// sorted list (targets: slot j; slot i or j; slot i) -- survivors (neither index == posID) are stored
+// straight into their own slot.
 __global__ void __launch_bounds__(128)
 k_ucong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restrict__ uPre,
         const int *__restrict__ posePre, int K, int totU, const TfConst *__restrict__ tc,
         const PoseJac *__restrict__ pj, const int *__restrict__ uScan,
-        int *__restrict__ rkey, double *__restrict__ rval, int none)
+        int *__restrict__ rkey, double *__restrict__ rval, int none,
+        int *__restrict__ ppKey, double *__restrict__ ppVal)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = g < totU;                     // no early return: the warp stays converged
-    int gg = active ? g : totU - 1;
-    int k = seg_find(uPre, K, gg);
-    int b = gg - uPre[k];
+    if (g >= totU) return;
+    int k = seg_find(uPre, K, g);
+    int b = g - uPre[k];
     const DMap &M = in[k];
     const TfConst &c = tc[k];
     int pid = c.posID;
@@ -270,39 +250,44 @@ k_ucong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restri
     dense_jac(c, pj[posePre[k] + i], i == pid, J1i, J2i);
     dense_jac(c, pj[posePre[k] + j], j == pid, J1j, J2j);
     double *Un = out[k].U;
-    double T[36], P[36];
-    const size_t r0 = 4 * (size_t)gg;
+    double T[36], P[36], PP[36];
+    const size_t r0 = 3 * (size_t)g;
+    // a product P (and/or its transpose) for slot `slot`: a record, or a term of PP when slot == pos
+    auto emit = [&](size_t r, int slot, bool plain, bool transposed) {
+        if (slot == pid) {
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int q = 0; q < 6; q++)
+                    PP[6 * a + q] += (plain ? P[6 * a + q] : 0.0) + (transposed ? P[6 * q + a] : 0.0);
+            rkey[r] = none;
+            return;
+        }
+        double Q[36];
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int q = 0; q < 6; q++) Q[6 * a + q] = (plain ? P[6 * a + q] : 0.0) + (transposed ? P[6 * q + a] : 0.0);
+        rec_write(rkey, rval, r, base + slot, Q);
+    };
 
     // C_i^T I C_j -> (pos,pos)
     sm::mtm<6, 6, 6>(J2i, I, T);
     sm::mm<6, 6, 6>(T, J2j, P);
-    {
-        double Q[36];
 #pragma unroll
-        for (int r = 0; r < 6; r++)
+    for (int r = 0; r < 6; r++)
 #pragma unroll
-            for (int q = 0; q < 6; q++) Q[6 * r + q] = P[6 * r + q] + (i != j ? P[6 * q + r] : 0.0);
-        rec_write_hot(rkey, rval, r0, base + pid, none, Q, active);
-    }
-    if (!active) return;
+        for (int q = 0; q < 6; q++) PP[6 * r + q] = P[6 * r + q] + (i != j ? P[6 * q + r] : 0.0);
     // C_i^T I D_j -> (pos,j), stored in slot j (transposed when j < pos; both orientations when j == pos)
     sm::mm<6, 6, 6>(T, J1j, P);
-    {
-        const bool a = j >= pid, bt = (j <= pid && i != j);
-        double Q[36];
-#pragma unroll
-        for (int r = 0; r < 6; r++)
-#pragma unroll
-            for (int q = 0; q < 6; q++) Q[6 * r + q] = (a ? P[6 * r + q] : 0.0) + (bt ? P[6 * q + r] : 0.0);
-        rec_write(rkey, rval, r0 + 1, base + j, Q);
-    }
+    emit(r0, j, j >= pid, j <= pid && i != j);
     // D_i^T I D_j -> (i,j)
     sm::mtm<6, 6, 6>(J1i, I, T);
     sm::mm<6, 6, 6>(T, J1j, P);
-    if (i == pid) rec_write(rkey, rval, r0 + 2, base + j, P);
-    else if (j == pid) rec_write(rkey, rval, r0 + 2, base + i, P);
+    if (i == pid) emit(r0 + 1, j, true, false);
+    else if (j == pid) emit(r0 + 1, i, true, false);
     else {
-        rkey[r0 + 2] = none;
+        rkey[r0 + 1] = none;
         int slot = M.m + (uScan[g] - uScan[uPre[k]]);
         sm::store<36>(Un + 36 * (size_t)slot, P);
         out[k].Ui[slot] = i;
@@ -310,15 +295,11 @@ k_ucong(const DMap *__restrict__ in, DMap *__restrict__ out, const int *__restri
     }
     // D_i^T I C_j -> (i,pos), stored in slot i
     sm::mm<6, 6, 6>(T, J2j, P);
-    {
-        const bool a = i <= pid, bt = (i >= pid && i != j);
-        double Q[36];
+    emit(r0 + 2, i, i <= pid, i >= pid && i != j);
+    ppKey[g] = k;
+    double2 *dst = reinterpret_cast<double2 *>(ppVal + 36 * (size_t)g);
 #pragma unroll
-        for (int r = 0; r < 6; r++)
-#pragma unroll
-            for (int q = 0; q < 6; q++) Q[6 * r + q] = (a ? P[6 * r + q] : 0.0) + (bt ? P[6 * q + r] : 0.0);
-        rec_write(rkey, rval, r0 + 3, base + i, Q);
-    }
+    for (int q = 0; q < 18; q++) dst[q] = make_double2(PP[2 * q], PP[2 * q + 1]);
 }
 
 // X = [Xt; Xb] (6 x N).  out = Jp^T X for the block-triangular pose Jacobian [[a,b],[0,c]]:
@@ -337,33 +318,35 @@ __device__ __forceinline__ void jt_mul(const double *a, double sgn, const double
 #include "transform_chunk.cuh"
 
 // One WARP per pose: gathers the pose's sums SW_p = sum_f W_pf, SWT_p = sum_f W_pf T_f from the records
-// the chunk kernel left behind (chunk-local pose tables are sorted: binary search per chunk of the
-// pose's map, chunks strided over the lanes, lane-private partial sums combined by a fixed butterfly:
+// the chunk kernel left behind (per chunk: pose bitmap + popcount prefix -> the pose's record slot with
+// two loads; chunks strided over the lanes, lane-private partial sums combined by a fixed butterfly:
 // bit-identical from run to run), then applies the pose Jacobians ONCE:
-//     U'(p,pos) += oriented [-D_p^T SW Q | D_p^T SWT]   ->  record 2 gp     (target: slot p)
-//     U'(pos,pos) += G + G^T, G = C_p^T [-SW Q | SWT]   ->  record 2 gp + 1 (target: slot pos)
+//     U'(p,pos) += oriented [-D_p^T SW Q | D_p^T SWT]   ->  record of the sorted list (target: slot p)
+//     U'(pos,pos) += G + G^T, G = C_p^T [-SW Q | SWT]   ->  record of the map's hot-target list
 __global__ void __launch_bounds__(128)
 k_tf_posefin(const int *__restrict__ posePre, int K, int totPose,
              const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj,
-             const int *__restrict__ chunkPre, const int *__restrict__ chunkPoses,
+             const int *__restrict__ chunkPre, const unsigned *__restrict__ chunkBits, int bitsStride,
              const double *__restrict__ chunkRec, const double *__restrict__ poseAccSlow,
-             int *__restrict__ rkey, double *__restrict__ rval, int none)
+             int *__restrict__ rkey, double *__restrict__ rval, int none,
+             int *__restrict__ ppKey, double *__restrict__ ppVal)
 {
     const int lane = threadIdx.x & 31;
     const int gp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gp >= totPose) return;                   // whole warps leave together
     const int k = seg_find(posePre, K, gp);
     const int p = gp - posePre[k];
+    const int pw = p >> 5;
+    const unsigned pbit = 1u << (p & 31);
     double acc[36];
 #pragma unroll
     for (int q = 0; q < 36; q++) acc[q] = 0.0;
     for (int c = chunkPre[k] + lane; c < chunkPre[k + 1]; c += 32) {
-        const int *tab = chunkPoses + 32 * (size_t)c;
-        const int np = tab[31];
-        int lo = 0, hi = np;                     // np == 0: slow-path chunk, nothing recorded
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (tab[mid] < p) lo = mid + 1; else hi = mid; }
-        if (lo < np && tab[lo] == p) {
-            const double2 *r = reinterpret_cast<const double2 *>(chunkRec + 36 * (32 * (size_t)c + lo));
+        const unsigned *gb = chunkBits + (size_t)c * 2 * bitsStride;
+        const unsigned w = gb[pw];
+        if (w & pbit) {
+            const int slot = (int)gb[bitsStride + pw] + __popc(w & (pbit - 1u));
+            const double2 *r = reinterpret_cast<const double2 *>(chunkRec + 36 * (32 * (size_t)c + slot));
 #pragma unroll
             for (int q = 0; q < 18; q++) { double2 v = r[q]; acc[2 * q] += v.x; acc[2 * q + 1] += v.y; }
         }
@@ -411,9 +394,70 @@ k_tf_posefin(const int *__restrict__ posePre, int K, int totPose,
                 G2[6 * q + r] += grq;
             }
     }
-    const size_t r0 = 2 * (size_t)gp;
-    if (!isPos) rec_write(rkey, rval, r0, posePre[k] + p, X); else rkey[r0] = none;
-    rec_write(rkey, rval, r0 + 1, posePre[k] + pid, G2);
+    if (!isPos) rec_write(rkey, rval, (size_t)gp, posePre[k] + p, X); else rkey[gp] = none;
+    rec_write(ppKey, ppVal, (size_t)gp, k, G2);
+}
+
+// U'(pos,pos) of map k = sum of the map's hot-target records: its U blocks' (run 0), its poses' (run 1)
+// and its feature chunks' (run 2).  Each run lies map-contiguously at a WIN-aligned offset, so whole
+// windows inside a map's range were pre-summed by det::k_window.  One CTA per map, fixed order.
+struct PPRuns { int off[3]; const int *pre[3]; };
+__global__ void __launch_bounds__(256)
+k_pp_reduce(PPRuns R, const double *__restrict__ val, const double *__restrict__ part,
+            const TfConst *__restrict__ tc, DMap *__restrict__ out)
+{
+    constexpr int NS = 7, WIN = det::WIN;
+    __shared__ double sh[NS][36];
+    const int k = blockIdx.x, tid = threadIdx.x;
+    int lo[3], nHead[3], c0[3], nWin[3], tailBeg[3], nIt[3];
+    int nItems = 0;
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const int a = R.off[u] + R.pre[u][k], b = R.off[u] + R.pre[u][k + 1];
+        int w0 = (a + WIN - 1) / WIN, w1 = b / WIN, he = b, tb = b;
+        if (w1 > w0) { he = w0 * WIN; tb = w1 * WIN; } else { w0 = w1 = 0; }
+        lo[u] = a; nHead[u] = he - a; c0[u] = w0; nWin[u] = w1 - w0; tailBeg[u] = tb;
+        nIt[u] = (he - a) + (w1 - w0) + (b - tb);
+        nItems += nIt[u];
+    }
+    const int s = tid / 36, q = tid - 36 * s;
+    if (s < NS) {
+        auto item = [&](int i) -> double {
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                if (i < nIt[u]) {
+                    if (i < nHead[u]) return val[36 * (size_t)(lo[u] + i) + q];
+                    i -= nHead[u];
+                    if (i < nWin[u]) return part[36 * (size_t)(c0[u] + i) + q];
+                    return val[36 * (size_t)(tailBeg[u] + (i - nWin[u])) + q];
+                }
+                i -= nIt[u];
+            }
+            return 0.0;
+        };
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = s;
+        for (; i + 3 * NS < nItems; i += 4 * NS) {
+            a0 += item(i); a1 += item(i + NS); a2 += item(i + 2 * NS); a3 += item(i + 3 * NS);
+        }
+        if (i < nItems) a0 += item(i);
+        if (i + NS < nItems) a1 += item(i + NS);
+        if (i + 2 * NS < nItems) a2 += item(i + 2 * NS);
+        sh[s][q] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+    if (tid < 36) {
+        double sum = 0.0;
+        const int ns = min(NS, nItems);
+        for (int i = 0; i < ns; i++) sum += sh[i][tid];
+        out[k].U[36 * (size_t)tc[k].posID + tid] = sum;
+    }
+}
+
+__global__ void k_fill_int(int *__restrict__ a, int n, int v)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) a[g] = v;
 }
 
 // target t = global pose index = slot t - posePre[k] of map k's new U list
@@ -421,8 +465,9 @@ struct ApplyU {
     DMap *out;
     const int *posePre;
     int K;
-    __device__ void operator()(int t, int q, double sum, int) const
+    __device__ void operator()(int t, int q, double sum, int cnt) const
     {
+        if (cnt == 0) return;            // only the (pos,pos) slot has no record here: k_pp_reduce writes it
         const int k = seg_find(posePre, K, t);
         out[k].U[36 * (size_t)(t - posePre[k]) + q] = sum;
     }
@@ -596,20 +641,30 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
         chunkPre[k + 1] = (int)chunks.size();
     }
     const int nChunks = (int)chunks.size();
-    // Records of the deterministic U' accumulation (det_accum.cuh), target = global pose index of the
-    // slot, `none` = totPose:  [0, 4 totU) k_ucong | [.., + 2 totPose) k_tf_posefin | [.., + nChunks) chunks
+    // Deterministic U' accumulation (det_accum.cuh).
+    //   sorted list : target = global pose index of the slot, `none` = totPose
+    //                 [0, 3 totU) k_ucong | [.., + totPose) k_tf_posefin
+    //   hot list    : everything that lands in a map's (pos,pos) slot, map-contiguous by construction:
+    //                 run 0 [0, totU) k_ucong | run 1 k_tf_posefin | run 2 the feature chunks;
+    //                 runs start at WIN-aligned offsets, key = map index (padding: K)
     const int none = A.totPose;
-    const size_t recU = 0, recP = 4 * (size_t)A.totU, recC = recP + 2 * (size_t)A.totPose;
-    const size_t nrec = recC + (size_t)nChunks;
-    if (nrec > 0x7fffffffull) throw LsfmError(LSFM_ERR_ARG, "level too large for 32-bit record indices");
-    DevBuf<int> rkey(nrec, s);
-    DevBuf<double> rval(36 * nrec, s);
+    const size_t recP = 3 * (size_t)A.totU;
+    const size_t nrec = recP + (size_t)A.totPose;
+    auto up = [](size_t v) { return (v + det::WIN - 1) / det::WIN * det::WIN; };
+    const size_t ppP = up((size_t)A.totU), ppC = ppP + up((size_t)A.totPose), ppN = ppC + up((size_t)nChunks);
+    if (nrec > 0x7fffffffull || ppN > 0x7fffffffull)
+        throw LsfmError(LSFM_ERR_ARG, "level too large for 32-bit record indices");
+    DevBuf<int> rkey(nrec, s), ppKey(ppN, s);
+    DevBuf<double> rval(36 * nrec, s), ppVal(36 * ppN, s);
+    k_fill_int<<<ceil_div((long long)ppN, TB), TB, 0, s>>>(ppKey.p, (int)ppN, K); nl++;
     if (A.totU > 0) {
         k_ucong<<<ceil_div(A.totU, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dUPre.p, A.dPosePre.p, K, A.totU,
-                                                     tc.p, pj.p, uScan.p, rkey.p + recU, rval.p + 36 * recU, none); nl++;
+                                                     tc.p, pj.p, uScan.p, rkey.p, rval.p, none, ppKey.p, ppVal.p); nl++;
     }
     DevBuf<tfc::Chunk> dChunks(std::max(nChunks, 1), s);
-    DevBuf<int> dChunkPre(K + 1, s), chunkPoses(32 * (size_t)std::max(nChunks, 1), s);
+    DevBuf<int> dChunkPre(K + 1, s);
+    const int bitsStride = maxWords;
+    DevBuf<unsigned> chunkBits(2 * (size_t)bitsStride * std::max(nChunks, 1), s);
     DevBuf<double> chunkRec(36 * 32 * (size_t)std::max(nChunks, 1), s);
     DevBuf<double> poseAcc(36 * (size_t)A.totPose, s);      // slow-path (chunk overflow) sums only
     dChunkPre.upload(chunkPre);
@@ -628,7 +683,8 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
         ctx.begin("transform.wv");
         tfc::k_tf_chunk<<<nChunks, tfc::TC_THREADS, shb, s>>>(A.d.p, B.d.p, dChunks.p, A.dFeatPre.p, A.dPosePre.p,
                                                             tc.p, pj.p, fScan.p, poseAcc.p, cmaxUse,
-                                                            chunkPoses.p, chunkRec.p, rkey.p + recC, rval.p + 36 * recC);
+                                                            chunkBits.p, bitsStride, chunkRec.p, ppKey.p + ppC,
+                                                            ppVal.p + 36 * ppC);
         {
             double wvBytes = 0.0;
             for (int k = 0; k < K; k++)
@@ -639,12 +695,22 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
         ctx.begin("transform");
     }
     k_tf_posefin<<<ceil_div(32ll * A.totPose, 128), 128, 0, s>>>(A.dPosePre.p, K, A.totPose, tc.p, pj.p, dChunkPre.p,
-                                                              chunkPoses.p, chunkRec.p, poseAcc.p,
-                                                              rkey.p + recP, rval.p + 36 * recP, none); nl++;
+                                                              chunkBits.p, bitsStride, chunkRec.p, poseAcc.p,
+                                                              rkey.p + recP, rval.p + 36 * recP, none,
+                                                              ppKey.p + ppP, ppVal.p + 36 * ppP); nl++;
     {
         det::Sorted srt;
         nl += det::sort_records(ctx, rkey.p, (int)nrec, none, srt);
-        det::reduce<36>(ctx, srt, rval.p, A.totPose, ApplyU{B.d.p, A.dPosePre.p, K}); nl++;
+        nl += det::reduce<36>(ctx, srt, rval.p, A.totPose, ApplyU{B.d.p, A.dPosePre.p, K});
+        // hot targets: window sums over the hot list as it lies (chunk keys are implied by the layout:
+        // a window is whole iff it lies inside one map's range, which k_pp_reduce decides from the prefixes)
+        const int nwin = (int)(ppN / det::WIN);
+        DevBuf<double> part(36 * (size_t)std::max(nwin, 1), s);
+        if (nwin > 0) { det::k_window<36><<<nwin, 256, 0, s>>>(ppKey.p, nullptr, (int)ppN, K, ppVal.p, part.p); nl++; }
+        PPRuns R;
+        R.off[0] = 0; R.off[1] = (int)ppP; R.off[2] = (int)ppC;
+        R.pre[0] = A.dUPre.p; R.pre[1] = A.dPosePre.p; R.pre[2] = dChunkPre.p;
+        k_pp_reduce<<<K, 256, 0, s>>>(R, ppVal.p, part.p, tc.p, B.d.p); nl++;
     }
     KERNEL_CHECK();
     ctx.end(bytes, 0.0, nl);

@@ -19,8 +19,8 @@
 //         (from the W and W T_f tiles);
 //         thread per (feature, element): the feature's wadd rows of this batch -> W'(pos,f)
 // Two barriers per batch; W is read once from HBM and written once.  At the end the pose sums are
-// written as one record per (chunk, local pose) next to the chunk's sorted pose table; k_tf_posefin
-// gathers them per pose in a fixed order (no FP64 atomics: bit-identical results run to run).
+// written as one record per (chunk, local pose) next to the chunk's pose bitmap; k_tf_posefin gathers
+// them per pose in a fixed order (no FP64 atomics: bit-identical results run to run).
 // Chunks with more than 31 distinct poses take a slow path (thread per block, global atomics).
 #pragma once
 
@@ -53,11 +53,10 @@ struct Layout {
     static constexpr int wptr = Cst + 36 * 8;                              // [FCH+4] int
     static constexpr int optr = wptr + (TC_FCH + 4) * 4;                   // [FCH+4] int
     static constexpr int pidPos = optr + (TC_FCH + 4) * 4;                 // [FCH] int
-    static constexpr int lcnt = pidPos + TC_FCH * 4;                       // [2][4][32] int: blocks per (warp, local pose) in the batch
+    static constexpr int lcnt = (pidPos + TC_FCH * 4 + 15) / 16 * 16;                       // [2][32][4] unsigned: per local pose, which lanes of each warp hold one of its blocks in the batch
     static constexpr int poses = lcnt + 2 * 4 * 32 * 4;                    // [32] int
     static constexpr int misc = poses + 32 * 4;                            // [4] int
-    static constexpr int lst = misc + 16;                                  // [4][32][32] uchar: the batch's blocks per (warp, local pose), lane order
-    static constexpr int bitmap = lst + 32 * TC_BATCH;                     // [words] unsigned + [words] int
+    static constexpr int bitmap = misc + 16;                               // [words] unsigned + [words] int
     static size_t bytes(int words) { return (size_t)bitmap + 8 * (size_t)words + 16; }
 };
 
@@ -97,7 +96,7 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
            const int *__restrict__ featPre, const int *__restrict__ posePre,
            const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj, const int *__restrict__ fScan,
            double *__restrict__ poseAcc, int cmaxUse,
-           int *__restrict__ chunkPoses, double *__restrict__ chunkRec,
+           unsigned *__restrict__ chunkBits, int bitsStride, double *__restrict__ chunkRec,
            int *__restrict__ ppKey, double *__restrict__ ppVal)
 {
     typedef Layout L;
@@ -114,7 +113,6 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     int *lcnt = (int *)(smraw + L::lcnt);
     int *poses = (int *)(smraw + L::poses);
     int *misc = (int *)(smraw + L::misc);
-    unsigned char *lst = smraw + L::lst;
     unsigned *bitmap = (unsigned *)(smraw + L::bitmap);
 
     const Chunk ch = chunks[blockIdx.x];
@@ -175,13 +173,20 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     __syncthreads();
     const int nposes = misc[0];
     const bool fast = nposes <= cmaxUse;
-    int *ctab = chunkPoses + 32 * (size_t)blockIdx.x;      // sorted local pose table, [31] = count (0: slow path)
-    if (tid == 0) ctab[31] = fast ? nposes : 0;
+    // the chunk's pose bitmap + popcount prefix go to global memory: k_tf_posefin finds a pose's record
+    // slot in this chunk with two loads (slow-path chunks publish an empty bitmap: nothing recorded)
+    {
+        unsigned *gb = chunkBits + (size_t)blockIdx.x * 2 * bitsStride;
+        for (int i = tid; i < words; i += TC_THREADS) {
+            gb[i] = fast ? bitmap[i] : 0u;
+            gb[bitsStride + i] = (unsigned)prefix[i];
+        }
+    }
     if (fast)
         for (int i = tid; i < words; i += TC_THREADS) {
             unsigned b = bitmap[i];
             int r = prefix[i];
-            while (b) { int bit = __ffs(b) - 1; ctab[r] = i * 32 + bit; poses[r++] = i * 32 + bit; b &= b - 1; }
+            while (b) { int bit = __ffs(b) - 1; poses[r++] = i * 32 + bit; b &= b - 1; }
         }
     double Q[9];
 #pragma unroll
@@ -263,7 +268,7 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
                 double *u = ppVal + 36 * (size_t)blockIdx.x;
                 u[6 * r + cc] = s;
                 if (cc != r) u[6 * cc + r] = s;
-                if (i == 0) ppKey[blockIdx.x] = posePre[k] + pid;
+                if (i == 0) ppKey[blockIdx.x] = k;              // hot-target list: key = map index
             }
         }
         __syncthreads();
@@ -351,12 +356,16 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
             row[8] = make_double2(B1[7], B1[8]);
         }
         if (FAST) {
-            // the batch's blocks per (warp, local pose) in LANE order: the pose sums below then add in
-            // an order that does not depend on the hardware's scheduling
-            const unsigned peers = __match_any_sync(act, slot);
-            const int rank = __popc(peers & ((1u << lane) - 1u));
-            lst[(warp * 32 + slot) * 32 + rank] = (unsigned char)tid;
-            if (rank == 0) lc[warp * 32 + slot] = __popc(peers);
+            // which lanes of this warp hold a block of the same local pose (five ballots, slot < 32);
+            // the lowest of them publishes the mask.  The pose sums below walk the set bits in
+            // ascending order: an order that does not depend on the hardware's scheduling.
+            unsigned peers = act;
+#pragma unroll
+            for (int b = 0; b < 5; b++) {
+                const unsigned v = __ballot_sync(act, (slot >> b) & 1);
+                peers &= ((slot >> b) & 1) ? v : ~v;
+            }
+            if ((peers & ((1u << lane) - 1u)) == 0u) lc[slot * 4 + warp] = (int)peers;
         }
     };
 
@@ -397,25 +406,16 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
             if (it < nitems) {
                 const int slot = it / 36, el = it - 36 * slot;
                 const double *src = (el < 18) ? (Wrt + el) : (WTt + (el - 18));
+                // one chain per warp of the batch (four independent shared loads in flight), set bits in
+                // ascending order
+                const uint4 m4 = *reinterpret_cast<const uint4 *>(lc + slot * 4);
+                unsigned m0 = m4.x, m1 = m4.y, m2 = m4.z, m3 = m4.w;
                 double s0 = acc[u], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-                for (int w = 0; w < 4; w++) {                 // warp-major, lane order inside: fixed
-                    const unsigned *ls4 = reinterpret_cast<const unsigned *>(lst + (w * 32 + slot) * 32);
-                    const int nl = lc[w * 32 + slot];
-                    int i = 0;
-                    for (; i + 4 <= nl; i += 4) {             // four independent shared loads in flight
-                        const unsigned b4 = ls4[i >> 2];
-                        s0 += src[TC_LD * (int)(b4 & 255u)];
-                        s1 += src[TC_LD * (int)((b4 >> 8) & 255u)];
-                        s2 += src[TC_LD * (int)((b4 >> 16) & 255u)];
-                        s3 += src[TC_LD * (int)(b4 >> 24)];
-                    }
-                    if (i < nl) {
-                        const unsigned b4 = ls4[i >> 2];
-                        s0 += src[TC_LD * (int)(b4 & 255u)];
-                        if (i + 1 < nl) s1 += src[TC_LD * (int)((b4 >> 8) & 255u)];
-                        if (i + 2 < nl) s2 += src[TC_LD * (int)((b4 >> 16) & 255u)];
-                    }
+                while (m0 | m1 | m2 | m3) {
+                    if (m0) { s0 += src[TC_LD * (__ffs(m0) - 1)]; m0 &= m0 - 1; }
+                    if (m1) { s1 += src[TC_LD * (32 + __ffs(m1) - 1)]; m1 &= m1 - 1; }
+                    if (m2) { s2 += src[TC_LD * (64 + __ffs(m2) - 1)]; m2 &= m2 - 1; }
+                    if (m3) { s3 += src[TC_LD * (96 + __ffs(m3) - 1)]; m3 &= m3 - 1; }
                 }
                 const double s = (s0 + s1) + (s2 + s3);
                 acc[u] = s;

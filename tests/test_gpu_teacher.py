@@ -11,11 +11,11 @@ overflow / bitmap paths differ from the small cases -- including the root join o
 Tolerances (relative to the largest entry of the array, `util.rel_err`):
   Transform  : state, U, W, V  <= 1e-9     (pure congruence / rigid transform, no solve)
   Join       : U, W, V         <= 1e-12    (copies and sums of two blocks)
-               state           <= 1e-9 where the reduced camera system allows it; the bound actually
-                               asserted is max(1e-9, 50 x the reference's OWN sensitivity of that join), the
-                               latter measured by re-running the reference's join on inputs whose W carries
-                               1e-15 relative noise (a solve cannot be reproduced more closely than the
-                               reference reproduces itself), and never looser than north_star's 1e-6.
+               state           <= 1e-9; a join that misses 1e-9 must stay within 50 x the reference's OWN
+                               sensitivity of THAT join (the reference's join re-run on inputs whose W
+                               carries 1e-15 relative noise: a solve cannot be reproduced more closely than
+                               the reference reproduces itself) and never looser than north_star's 1e-6.
+                               The report counts those joins per level.
   objective  : <= 1e-8 relative, every join of every level.
 """
 import copy
@@ -81,12 +81,6 @@ def run_teacher_forced(gpu, oracle, maps, tag, max_pairs_objective=64):
             row["transform"] = w
             del got
             # Join + solve on the ORACLE's transformed End maps; objective of every join
-            # the reference's own sensitivity of the worst-conditioned (largest) join of the level
-            big = int(np.argmax([j.m for j in J]))
-            e2 = copy.deepcopy(Et[big])
-            e2.W = e2.W * (1 + 1e-15 * rng.standard_normal(e2.W.shape))
-            sens = rel_err(oracle.join_stereo(e2, C[big]).stVal, J[big].stVal)
-            tol = min(1e-6, max(1e-9, 50.0 * sens))
             gpu.stats_reset(objective=True)
             try:
                 got = gpu.join_stereo_batch(Et, C)
@@ -94,8 +88,22 @@ def run_teacher_forced(gpu, oracle, maps, tag, max_pairs_objective=64):
             finally:
                 gpu.stats_reset()
             w = {}
+            nsens, worst_ratio = 0, 0.0
             for i, (g, r) in enumerate(zip(got, J)):
+                e = rel_err(g.stVal, r.stVal)
+                tol = 1e-9
+                if e > tol:
+                    # the reference's OWN sensitivity of this join: its result on inputs whose W blocks
+                    # carry 1e-15 relative noise
+                    e2 = copy.deepcopy(Et[i])
+                    e2.W = e2.W * (1 + 1e-15 * rng.standard_normal(e2.W.shape))
+                    sens = rel_err(oracle.join_stereo(e2, C[i]).stVal, r.stVal)
+                    tol = min(1e-6, max(1e-9, 50.0 * sens))
+                    nsens += 1
+                    worst_ratio = max(worst_ratio, e / max(sens, 1e-300))
                 _cmp(g, r, f"{tag} level {L} join {i}", w, tol, 1e-12)
+            w["joins_above_1e-9"] = nsens
+            w["worst_err_over_ref_self_sensitivity"] = worst_ratio
             assert len(obj) == len(J)
             wo = 0.0
             step = max(1, len(J) // max_pairs_objective)
@@ -104,8 +112,6 @@ def run_teacher_forced(gpu, oracle, maps, tag, max_pairs_objective=64):
                 wo = max(wo, abs(obj[i] - Fr) / max(Fr, 1e-300))
             assert wo <= 1e-8, f"{tag} level {L}: objective rel err {wo:.3e}"
             w["objective"] = wo
-            w["ref_self_sensitivity"] = sens
-            w["state_tol"] = tol
             row["join"] = w
             del got
         if rec["rb_in"]:
