@@ -35,8 +35,11 @@ constexpr int PAT_CMAX = 31;
 constexpr int PAT_THREADS = 128;
 struct FeatChunk { int k, f0, f1; };
 // Per chunk, written by pass 0 and reused by pass 1 and by the Schur kernel:
-//   [0..30] local pose table (ascending pose index), [31] #distinct poses, [32..47] pair bitmap
-constexpr int CHUNK_INFO_INTS = 48;
+//   [0..30] local pose table (ascending pose index), [31] #distinct poses, [32..47] pair bitmap,
+//   [48] mask of the chunk's DENSE local poses (seen by at least half of the chunk's features, at most
+//   SCH_HMAX of them: their pose pairs are handled as one dense DMMA contraction), [49] their number
+constexpr int CHUNK_INFO_INTS = 64;
+constexpr int SCH_HMAX = 16;
 
 // set bit (lo,hi) of join k's upper-triangular pose-pair bitmap (row lo, W words per row); the plain
 // read first keeps the hub pairs (set by every chunk of a map) from turning into atomic traffic
@@ -64,12 +67,14 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     unsigned *pairBits = (unsigned *)(prefix + words);   // [16]
     int *poses = (int *)(pairBits + 16);             // [PAT_CMAX + 1]
     int *misc = poses + PAT_CMAX + 1;                // [0] nposes
+    int *scnt = misc + 4;                            // [32] blocks per local pose
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     int *ci = chunkInfo + CHUNK_INFO_INTS * (size_t)blockIdx.x;
     const int boff = bmOff[ch.k];
     const int w0 = M.wPtr[ch.f0], w1 = M.wPtr[ch.f1];
     for (int i = tid; i < words; i += nt) bitmap[i] = 0u;
     if (tid < 16) pairBits[tid] = 0u;
+    if (tid < 32) scnt[tid] = 0;
     __syncthreads();
     for (int j = w0 + tid; j < w1; j += nt) {
         int p = M.photo[j];
@@ -111,6 +116,7 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
                 int pa = M.photo[a];
                 int sa = prefix[pa >> 5] + __popc(bitmap[pa >> 5] & ((1u << (pa & 31)) - 1u));
                 bi[a] = ((f - ch.f0) << 8) | sa;
+                atomicAdd(&scnt[sa], 1);
                 for (int b = a; b < a1; b++) {
                     int pb = M.photo[b];
                     int sb = prefix[pb >> 5] + __popc(bitmap[pb >> 5] & ((1u << (pb & 31)) - 1u));
@@ -128,6 +134,15 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         __syncthreads();
         // the chunk's pair bitmap stays behind for the Schur kernel ([32..47])
         if (tid < 16) ci[32 + tid] = (int)pairBits[tid];
+        if (tid == 0) {
+            unsigned dm = 0u;
+            int H = 0;
+            const int nf = ch.f1 - ch.f0;
+            for (int sl = 0; sl < nposes && H < SCH_HMAX; sl++)
+                if (2 * scnt[sl] >= nf) { dm |= 1u << sl; H++; }
+            ci[48] = (int)dm;
+            ci[49] = H;
+        }
         // the chunk's distinct pairs -> the join's pose-pair bitmap (exact dedupe across chunks)
         const int npairs = nposes * (nposes + 1) / 2;
         for (int t = tid; t < npairs; t += nt) {
@@ -439,6 +454,7 @@ k_e_gather(const int *__restrict__ posePre, int K, int totP, const int *__restri
 }
 } // namespace
 #include "schur_pipe.cuh"
+#include "schur_dense.cuh"
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -909,7 +925,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     DevBuf<unsigned> bm((size_t)std::max(bmOff[K], 1), s);
     bm.zero();
     if (nChunks > 0) {
-        size_t shb = sizeof(int) * (2 * (size_t)maxWords + 16 + PAT_CMAX + 1 + 4);
+        size_t shb = sizeof(int) * (2 * (size_t)maxWords + 16 + PAT_CMAX + 1 + 4 + 32);
         if (shb > 48 * 1024)
             CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
         dMaxNp.zero();
@@ -998,7 +1014,14 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
                                                   sexp.p, Sfx.p, Erec.p);
             };
             static const bool force_ovf2 = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
-            if (maxNposes <= 8 || force_ovf2)
+            static const bool use_pipe = getenv("LSFM_SCHUR_PIPE") != nullptr;     // previous kernel (scalar FMA only)
+            if (!use_pipe) {
+                // default: dense pose pairs of every chunk on the FP64 tensor cores (schur_dense.cuh)
+                if (maxNposes <= 16 || force_ovf2)
+                    launch(schur_dense::k_schur_dense<16, 160, 32, 256, 8>, schur_dense::Layout<16, 160, 32, 256>::bytes(), 256);
+                else
+                    launch(schur_dense::k_schur_dense<31, 248, 32, 512, 16>, schur_dense::Layout<31, 248, 32, 512>::bytes(), 512);
+            } else if (maxNposes <= 8 || force_ovf2)
                 launch(schur_pipe::k_schur_pipe<8, 64, 32, 128, 1>, schur_pipe::Layout<8, 64, 32>::bytes(), 128);
             else if (maxNposes <= 16)
                 launch(schur_pipe::k_schur_pipe<16, 128, 32, 256, 1>, schur_pipe::Layout<16, 128, 32>::bytes(), 256);
