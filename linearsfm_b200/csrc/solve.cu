@@ -1018,9 +1018,9 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             if (!use_pipe) {
                 // default: dense pose pairs of every chunk on the FP64 tensor cores (schur_dense.cuh)
                 if (maxNposes <= 16 || force_ovf2)
-                    launch(schur_dense::k_schur_dense<16, 160, 32, 256, 8>, schur_dense::Layout<16, 160, 32, 256>::bytes(), 256);
+                    launch(schur_dense::k_schur_dense<16, 160, 256, 2, 8>, schur_dense::Layout<16, 160, 256>::bytes(), 256);
                 else
-                    launch(schur_dense::k_schur_dense<31, 248, 32, 512, 16>, schur_dense::Layout<31, 248, 32, 512>::bytes(), 512);
+                    launch(schur_dense::k_schur_dense<31, 248, 512, 4, 16>, schur_dense::Layout<31, 248, 512>::bytes(), 512);
             } else if (maxNposes <= 8 || force_ovf2)
                 launch(schur_pipe::k_schur_pipe<8, 64, 32, 128, 1>, schur_pipe::Layout<8, 64, 32>::bytes(), 128);
             else if (maxNposes <= 16)
