@@ -50,6 +50,11 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# FP64 peak of this pool's B200s, measured with tools/ubench/dmma.cu (profiles/r2_dmma_ubench.txt):
+# mma.sync.m8n8k4.f64 (DMMA) 37.07 TFLOP/s, plain DFMA 33.6 TFLOP/s -- MEASURED_PEAKS.json has no FP64 entry
+FP64_PEAK_TFLOPS = 37.07
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -284,6 +289,12 @@ def main():
         # share of the GPU time of a step: the host-only stage (symbolic analysis, overlapped with
         # the Schur kernel when the stage timers are off) is left out, like in an ncu launch list
         total_ms = max(sum(v["ms"] for k, v in st.items() if k != "solve.symbolic"), 1e-9)
+        fp64 = None
+        if top[1].get("flops", 0) > 0:
+            tf = top[1]["flops"] / max(top[1]["ms"], 1e-9) / 1e9
+            fp64 = {"achieved_tflops": round(tf, 3), "peak_tflops": FP64_PEAK_TFLOPS, "frac": round(tf / FP64_PEAK_TFLOPS, 4),
+                    "algorithmic_flops_per_launch": round(top[1]["flops"] / top[1]["launches"]),
+                    "peak_source": "measured: tools/ubench/dmma.cu, profiles/r2_dmma_ubench.txt (DMMA m8n8k4)"}
         roof = {"kernel": single[top[0]], "stage": top[0], "bound": "hbm", "achieved": round(ach, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic, "traffic_launch": traffic_note,
                 "peak_source": how,
@@ -291,6 +302,7 @@ def main():
                 "avg_launch_ms": round(top[1]["ms"] / top[1]["launches"], 4),
                 "algorithmic_bytes_per_launch": round(top[1]["bytes"] / top[1]["launches"]),
                 "share_of_step": round(top[1]["ms"] / total_ms, 3),
+                "fp64": fp64,
                 "other_kernels": {single[k]: {"GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
                                               "frac": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6 / peak, 4),
                                               "ms_total": round(v["ms"], 3), "share_of_step": round(v["ms"] / total_ms, 3)}

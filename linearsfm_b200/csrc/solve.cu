@@ -56,7 +56,7 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
             unsigned *__restrict__ bm, const int *__restrict__ bmOff,
             int *__restrict__ maxNposes, int pat_cmax, int *__restrict__ chunkInfo,
             int *__restrict__ blkInfo, const int *__restrict__ wPre,
-            unsigned *__restrict__ patBits, int bitsStride)
+            unsigned *__restrict__ patBits, int bitsStride, unsigned long long *__restrict__ pairFeat)
 {
     extern __shared__ unsigned smu[];
     const FeatChunk ch = chunks[blockIdx.x];
@@ -99,6 +99,17 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     __syncthreads();
     const int nposes = misc[0];
     if (tid == 0) { atomicMax(maxNposes, nposes); ci[31] = nposes; }
+    // algorithmic work of the Schur complement: sum over the chunk's features of k_f (k_f + 1) / 2
+    // 6x3x6 products (LinearSFMImp.cpp:2275-2318) -- statistics only (FP64 roofline of the Schur kernel)
+    if (pairFeat) {
+        unsigned long long c = 0;
+        for (int f = ch.f0 + tid; f < ch.f1; f += nt) {
+            const unsigned long long kf = (unsigned long long)(M.wPtr[f + 1] - M.wPtr[f]);
+            c += kf * (kf + 1) / 2;
+        }
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0 && c) atomicAdd(pairFeat, c);
+    }
     // pose bitmap + popcount prefix of the chunk -> global: the E gather (k_e_gather) finds a pose's slot
     // in this chunk with two loads (overflow chunks publish an empty bitmap: they record nothing)
     {
@@ -894,7 +905,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     DevBuf<FeatChunk> dChunks(nChunks, s);
     dChunks.upload(chunks);
     int maxNposes = 1 << 30;             // max distinct poses of any chunk (measured by k_pat_chunk)
-    DevBuf<int> dMaxNp(1, s);
+    DevBuf<int> dMaxNp(4, s);            // [0] max #poses per chunk, [2..3] pair-feature count (stage timing only)
     DevBuf<int> chunkInfo((size_t)CHUNK_INFO_INTS * std::max(nChunks, 1), s), blkInfo((size_t)std::max(J.totW, 1), s);
     // per chunk: pose bitmap + popcount prefix (the E gather's index) and the chunks of every join
     const int bitsStride = maxWords;
@@ -930,7 +941,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
         dMaxNp.zero();
         k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, bm.p, dBmOff.p, dMaxNp.p, pat_cmax_used,
-                                                      chunkInfo.p, blkInfo.p, J.dWPre.p, patBits.p, bitsStride); nl++;
+                                                      chunkInfo.p, blkInfo.p, J.dWPre.p, patBits.p, bitsStride,
+                                                      ctx.timing ? (unsigned long long *)(dMaxNp.p + 2) : nullptr); nl++;
     }
     if (gauge) {   // mono: the zero pose has no block at all after the join; keep every diagonal
         k_pat_diag<<<ceil_div(J.totPose, TB), TB, 0, s>>>(J.d.p, J.dPosePre.p, K, J.totPose, bm.p, dBmOff.p); nl++;
@@ -947,18 +959,22 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     k_bm_emit<<<ceil_div(J.totPose * 32, TB), TB, 0, s>>>(bm.p, dBmOff.p, J.d.p, J.dPosePre.p, K, J.totPose, rowPtr.p, keys.p, keyCap); nl++;
     // one synchronisation for everything the host needs: keys, row pointers (#blocks = last entry)
     int nuis = 0;
-    char *pin = ctx.pinDown.need(sizeof(u64) * ((size_t)keyCap + 1) + sizeof(int) * ((size_t)J.totPose + 4));
+    char *pin = ctx.pinDown.need(sizeof(u64) * ((size_t)keyCap + 1) + sizeof(int) * ((size_t)J.totPose + 8));
     u64 *hKeys = (u64 *)pin;
     int *hRowPtr = (int *)(pin + sizeof(u64) * ((size_t)keyCap + 1));
     int *hMaxNp = hRowPtr + J.totPose + 1;
-    *hMaxNp = 0;
-    if (nChunks > 0) CUDA_CHECK(cudaMemcpyAsync(hMaxNp, dMaxNp.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    hMaxNp[0] = hMaxNp[2] = hMaxNp[3] = 0;
+    if (nChunks > 0) CUDA_CHECK(cudaMemcpyAsync(hMaxNp, dMaxNp.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (keyCap) CUDA_CHECK(cudaMemcpyAsync(hKeys, keys.p, sizeof(u64) * keyCap, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(hRowPtr, rowPtr.p, sizeof(int) * (J.totPose + 1), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     ctx.idle_begin();
     nuis = hRowPtr[J.totPose];
     if (nChunks > 0) maxNposes = *hMaxNp;
+    // FP64 work of the Schur stage: 216 flop per (pose pair, feature) product, 108 per block for W V^-1,
+    // 36 per block for the reduced right-hand side
+    const double schurFlops = 216.0 * (double)(((unsigned long long)(unsigned)hMaxNp[3] << 32) | (unsigned)hMaxNp[2]) +
+                              144.0 * J.totW;
     if (nuis > keyCap) {                  // bound overshot: emit and fetch again with the exact size
         keys.alloc((size_t)nuis, s);
         k_bm_emit<<<ceil_div(J.totPose * 32, TB), TB, 0, s>>>(bm.p, dBmOff.p, J.d.p, J.dPosePre.p, K, J.totPose, rowPtr.p, keys.p, nuis); nl++;
@@ -1014,9 +1030,13 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
                                                   sexp.p, Sfx.p, Erec.p);
             };
             static const bool force_ovf2 = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
-            static const bool use_pipe = getenv("LSFM_SCHUR_PIPE") != nullptr;     // previous kernel (scalar FMA only)
-            if (!use_pipe) {
-                // default: dense pose pairs of every chunk on the FP64 tensor cores (schur_dense.cuh)
+            // LSFM_SCHUR_DENSE=1: the chunk's dense pose pairs as one DMMA contraction (schur_dense.cuh).
+            // Parity-green, but on B200 the DMMA and DFMA peaks are equal (37 vs 33 TF/s measured,
+            // profiles/r2_dmma_ubench.txt) and the kernel is bound by its per-batch barriers, not by the
+            // FP64 pipe (profiles/r2_ncu_schur_dense.md): it is slower than the register-tiled scalar
+            // kernel at every tree level, so the latter stays the default.
+            static const bool use_dense = getenv("LSFM_SCHUR_DENSE") != nullptr;
+            if (use_dense) {
                 if (maxNposes <= 16 || force_ovf2)
                     launch(schur_dense::k_schur_dense<16, 160, 256, 2, 8>, schur_dense::Layout<16, 160, 256>::bytes(), 256);
                 else
@@ -1028,6 +1048,10 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             else
                 launch(schur_pipe::k_schur_pipe<31, 248, 32, 512, 1>, schur_pipe::Layout<31, 248, 32>::bytes(), 512);
             nl++;
+            KERNEL_CHECK();
+            ctx.end(152.0 * J.totW + 96.0 * J.totFeat + 288.0 * nuis + 48.0 * J.totPose, schurFlops, nl);
+            nl = 0;
+            ctx.begin("solve.schur_fin");
             // S -= the fixed-point sums; E_p -= the chunks' shares, gathered per pose in a fixed order
             k_s_convert<<<ceil_div(36ll * nuis, TB), TB, 0, s>>>(keys.p, nuis, J.dPosePre.p, sexp.p, Sfx.p, S.p); nl++;
             k_e_gather<<<ceil_div(32ll * J.totPose, 128), 128, 0, s>>>(J.dPosePre.p, K, J.totPose, dChunkPre.p, patBits.p,
@@ -1035,9 +1059,9 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         }
     }
     KERNEL_CHECK();
-    // algorithmic bytes of the Schur kernel: every W block + its feature's V^-1 and eF read once,
-    // S and E written once
-    ctx.end(152.0 * J.totW + 96.0 * J.totFeat + 288.0 * nuis + 48.0 * J.totPose, 0.0, nl);
+    // (algorithmic bytes of the Schur kernel: every W block + its feature's V^-1 and eF read once,
+    // S and E written once)
+    ctx.end(576.0 * nuis, 0.0, nl);
     nl = 0;
     if (gauge && nuis > 0) {
         k_mono_gauge<<<ceil_div(nuis, TB), TB, 0, s>>>(keys.p, nuis, gauge->refPose, gauge->fixScalar, S.p);

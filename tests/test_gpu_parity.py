@@ -74,15 +74,20 @@ def test_tree_88(gpu, oracle):
     assert state_rel_err(got, ref) <= 1e-6
 
 
-@pytest.mark.parametrize("env", [{"LSFM_FORCE_OVERFLOW": "1"}, {"LSFM_TF_V3": "1"}])
-def test_tree_slow_paths(gpu, oracle, env):
-    # chunks that see "too many" distinct poses (forced: > 4) take the thread-per-block paths of the
-    # Transform / pattern / Schur kernels; LSFM_TF_V3 selects the previous multi-kernel Transform.
+@pytest.mark.parametrize("env,size", [({"LSFM_FORCE_OVERFLOW": "1"}, ("37", "30")),
+                                      ({"LSFM_SCHUR_DENSE": "1"}, ("37", "30")),
+                                      ({"LSFM_SCHUR_DENSE": "1"}, ("300", "128")),
+                                      ({"LSFM_SCHUR_V1": "1"}, ("37", "30"))])
+def test_tree_alternative_paths(gpu, oracle, env, size):
+    # LSFM_FORCE_OVERFLOW: chunks that see "too many" distinct poses (forced: > 4) take the thread-per-block
+    # paths of the Transform / pattern / Schur kernels.  LSFM_SCHUR_DENSE: the DMMA Schur kernel
+    # (schur_dense.cuh; 300 maps reach the 512-thread instantiation with 12 dense poses per chunk).
+    # LSFM_SCHUR_V1: the first, atomics-only Schur kernel.  The switches are read once per process.
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     e = dict(os.environ); e.update(env)
-    r = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "check_tree.py"), "37", "30"],
-                       env=e, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "check_tree.py"), *size],
+                       env=e, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
