@@ -126,7 +126,7 @@ def run_reference(args, rank):
     from linearsfm_b200 import synth
     ro.build()
     nmaps = args.maps
-    maps = synth.make_stereo_scene(nmaps, feats_per_frame=FEATS)
+    maps = make_scene(args)
     times, cpu_times = [], []
     t_begin = time.perf_counter()
     while len(times) < max(1, args.steps):
@@ -142,7 +142,7 @@ def run_reference(args, rank):
         "ms_per_step": t * 1e3,
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "extrapolated": False,
-        "config": {"workload": workload_name(nmaps), "l2": "inputs larger than L2"},
+        "config": {"workload": workload_name(nmaps, args.feats, args.scene), "l2": "inputs larger than L2"},
         "cpu_baseline": {"value": t, "unit": "s", "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
                          "sample": f"all {nmaps} local maps, {len(times)} solve(s) timed, no warm-up "
                                    f"(wall {min(times):.2f}..{max(times):.2f} s; the reference's own clock() figure "
@@ -152,8 +152,17 @@ def run_reference(args, rank):
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
-def workload_name(nmaps):
-    return f"synthetic NC3500-shape stereo scene, {nmaps} local maps, {FEATS} new landmarks/frame"
+def workload_name(nmaps, feats=FEATS, scene="default"):
+    extra = "" if scene == "default" else ", loop closures every 500 frames (revisit 0.1), gated landmarks <= 15 m"
+    return f"synthetic NC3500-shape stereo scene, {nmaps} local maps, {feats} new landmarks/frame{extra}"
+
+
+def make_scene(args):
+    from linearsfm_b200 import synth
+    if args.scene == "closed":
+        return synth.make_stereo_scene(args.maps, feats_per_frame=args.feats, revisit=0.1, lap=500, max_depth=15.0,
+                                       gate=True)
+    return synth.make_stereo_scene(args.maps, feats_per_frame=args.feats)
 
 
 def main():
@@ -163,6 +172,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--maps", type=int, default=FULL_MAPS)
+    ap.add_argument("--feats", type=int, default=FEATS, help="new landmarks per frame")
+    ap.add_argument("--scene", default="default", choices=["default", "closed"],
+                    help="default: the round-1 open sequential chain; closed: loop closures every 500 frames, "
+                         "outlier-gated landmarks (well conditioned; the 50k-map config uses it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -183,7 +196,7 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     nmaps = args.maps
-    maps_all = synth.make_stereo_scene(nmaps, feats_per_frame=FEATS)
+    maps_all = make_scene(args)
     lo, hi = lsd.slice_of(nmaps, world, rank)
     mine = maps_all[lo:hi]
     arr, keep = api.to_c_array(mine)
@@ -326,7 +339,7 @@ def main():
             "metric": METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(nmaps),
+            "config": {"workload": workload_name(nmaps, args.feats, args.scene),
                        "l2": "inputs larger than L2 (leaf maps ~0.4 GB, upper levels > 1 GB)",
                        "parallelism": f"tree-level sharding x{world}" if world > 1 else "single GPU"},
             "device_ms_per_step": (dev_ms / args.steps) if world == 1 else None,

@@ -97,11 +97,29 @@ int lsfm_solve_stereo(double *stVal, const double *eb, const double *ea, const d
                       const double *W, const double *V, const int *Ui, const int *Uj,
                       const int *photo, const int *feature, int m, int n, int nU, int nW);
 
+/* void lmj_solveLinearSFMMono(double* stVal, double* eb, double* ea, double* U, double* W, double* V,
+ *      int* Ui, int* Uj, int* photo, int* feature, int m, int n, int nU, int nW,
+ *      int Ref, int ScaP, int Fix, int Sign, int FixBlk)     (LinearSFMImp.h:223, LinearSFMImp.cpp:6756-7041)
+ * Same argument order and meaning: Ref = block index of the all-zero pose, ScaP = its first scalar row
+ * (= 6 Ref; rows ScaP..ScaP+5 are removed from the system, 6981-7001), Fix = scalar row of the pinned
+ * translation component (also removed), Sign = its value written back at the end (7026).  FixBlk only
+ * steers the reference's scalar permutation and is ignored.  Here the gauge rows stay in the block
+ * system as identity rows with a zero right-hand side (same solution).          */
+int lsfm_solve_mono(double *stVal, const double *eb, const double *ea, const double *U, const double *W,
+                    const double *V, const int *Ui, const int *Uj, const int *photo, const int *feature,
+                    int m, int n, int nU, int nW, int Ref, int ScaP, int Fix, int Sign, int FixBlk);
+
 /* Debug capture of the last lsfm_solve_stereo / single join (integer parity tests):
  * block CRS of S (the reference's Sidxij, LinearSFMImp.cpp:2190-2205), block elimination ordering
  * (replaces cholmod_amd, LinearSFMImp.cpp:2413).  Pointers stay valid until the next solve.    */
 int lsfm_debug_last_solve(int *m, const int **rowptr, const int **colidx, const double **S,
                           const double **E, const int **perm);
+/* Block-Jacobi preconditioned conjugate gradients on S x = E (north_star: "block-Jacobi PCG as a
+ * cross-check" of the Cholesky that replaces pba_solveCholmodLM, LinearSFMImp.cpp:2380-2449).  S is the
+ * upper block triangle in block CRS exactly as lsfm_debug_last_solve() returns it (36 doubles per
+ * block, row-major, diagonal blocks full).  Stops at ||r|| <= tol ||E|| or after max_iters.        */
+int lsfm_pcg_block(int m, const int *rowptr, const int *colidx, const double *S, const double *E,
+                   double *x, double tol, int max_iters, int *iters_done, double *rel_residual);
 /* the ordering routine alone: upper block pattern (CSC: Ap[m+1], Ai) -> perm[m]               */
 int lsfm_block_ordering(int m, const int *Ap, const int *Ai, int *perm);
 

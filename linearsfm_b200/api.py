@@ -147,6 +147,20 @@ def debug_last_solve() -> dict:
                 perm=np.ctypeslib.as_array(pm, shape=(mm,)).copy())
 
 
+def pcg_block(rowptr, colidx, S, E, tol=1e-13, max_iters=None):
+    """Block-Jacobi PCG on the reduced camera system (cross-check of the Cholesky): returns
+    (x, iterations, relative residual)."""
+    rowptr = _c(rowptr, np.int32); colidx = _c(colidx, np.int32)
+    S = _c(S, np.float64); E = _c(E, np.float64)
+    m = rowptr.shape[0] - 1
+    x = np.zeros(6 * m)
+    it = C.c_int(0); rr = C.c_double(0.0)
+    check(lib().lsfm_pcg_block(C.c_int(m), rowptr.ctypes.data_as(_pi), colidx.ctypes.data_as(_pi),
+                               S.ctypes.data_as(_pd), E.ctypes.data_as(_pd), x.ctypes.data_as(_pd),
+                               C.c_double(tol), C.c_int(max_iters or 40 * 6 * m), C.byref(it), C.byref(rr)))
+    return x, it.value, rr.value
+
+
 class Tree:
     """Leaf maps resident in HBM; `solve()` runs the merge tree on the device."""
 
@@ -261,6 +275,21 @@ class CLinearSFMImp:
         p = lambda a: a.ctypes.data_as(_pi if a.dtype == np.int32 else _pd)
         check(lib().lsfm_solve_stereo(p(st), p(eb), p(ea), p(U), p(W), p(V), p(Ui), p(Uj), p(photo),
                                       p(feature), C.c_int(m), C.c_int(n), C.c_int(nU), C.c_int(nW)))
+        return st
+
+    def lmj_solveLinearSFMMono(self, eb, ea, U, W, V, Ui, Uj, photo, feature, m, n, Ref, ScaP, Fix, Sign,
+                               FixBlk=0) -> np.ndarray:
+        """LinearSFMImp.cpp:6756, same argument order after the output stVal (returned); nU / nW come
+        from the array lengths."""
+        ea = _c(ea, np.float64); eb = _c(eb, np.float64)
+        U = _c(U, np.float64); W = _c(W, np.float64); V = _c(V, np.float64)
+        Ui = _c(Ui, np.int32); Uj = _c(Uj, np.int32)
+        photo = _c(photo, np.int32); feature = _c(feature, np.int32)
+        st = np.zeros(6 * m + 3 * n)
+        p = lambda a: a.ctypes.data_as(_pi if a.dtype == np.int32 else _pd)
+        check(lib().lsfm_solve_mono(p(st), p(eb), p(ea), p(U), p(W), p(V), p(Ui), p(Uj), p(photo), p(feature),
+                                    C.c_int(m), C.c_int(n), C.c_int(Ui.shape[0]), C.c_int(photo.shape[0]),
+                                    C.c_int(Ref), C.c_int(ScaP), C.c_int(Fix), C.c_int(Sign), C.c_int(FixBlk)))
         return st
 
     def lmj_PF3D_Divide_ConquerStereo(self, maps) -> LocalMap:

@@ -21,6 +21,8 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 } // namespace
 // the one error string lsfm_last_error() returns; file I/O (fileio.cpp) reports through it too
 void lsfm_set_error(const std::string &msg) { g_err = msg; }
+// the process's context for library-internal tools (pcg.cu); nullptr without a device
+Context *lsfm_internal_ctx() { return (g_ctx || lsfm_init(0) == LSFM_OK) ? g_ctx : nullptr; }
 namespace {
 
 int ensure_ctx()
@@ -251,6 +253,47 @@ int lsfm_solve_stereo(double *stVal, const double *eb, const double *ea, const d
         if (n) eF.upload(eb, 3 * (size_t)n);
         g_dbg = SolveDebug();
         solve_stereo_batch(*g_ctx, J, eP.p, eF.p, &g_dbg);
+        g_ctx->check_errors();
+        g_dbg_valid = true;
+        std::vector<int> tmpno(M.r);
+        download_state(*g_ctx, h[0], tmpno.data(), stVal);
+    });
+}
+
+// one-element gauge arrays of the standalone mono solve operator
+static __global__ void k_set_gauge(int *g, int ref, int fix, int sign) { g[0] = ref; g[1] = fix; g[2] = sign; }
+
+int lsfm_solve_mono(double *stVal, const double *eb, const double *ea, const double *U, const double *W,
+                    const double *V, const int *Ui, const int *Uj, const int *photo, const int *feature,
+                    int m, int n, int nU, int nW, int Ref, int ScaP, int Fix, int Sign, int FixBlk)
+{
+    return guarded([&] {
+        if (m <= 0 || n < 0) throw LsfmError(LSFM_ERR_ARG, "solve: bad sizes");
+        if (Ref < 0 || Ref >= m || ScaP != 6 * Ref || Fix < 0 || Fix >= 6 * m)
+            throw LsfmError(LSFM_ERR_ARG, "solve_mono: gauge arguments out of range (ScaP must be 6 * Ref)");
+        (void)FixBlk;                     // only steers the reference's scalar permutation (7083-7105)
+        lsfm_map M;
+        memset(&M, 0, sizeof(M));
+        M.m = m; M.n = n; M.nU = nU; M.nW = nW; M.r = 6 * m + 3 * n;
+        std::vector<int> stno(M.r);
+        for (int i = 0; i < 6 * m; i++) stno[i] = -(i / 6 + 1);
+        for (int i = 0; i < 3 * n; i++) stno[6 * m + i] = i / 3 + 1;
+        std::vector<double> zeros(M.r, 0.0);
+        M.stno = stno.data(); M.stVal = zeros.data();
+        M.U = (double *)U; M.Ui = (int *)Ui; M.Uj = (int *)Uj;
+        M.W = (double *)W; M.photo = (int *)photo; M.feature = (int *)feature;
+        M.V = (double *)V; M.FBlock = nullptr;
+        std::vector<MapHandle> h = upload_maps(*g_ctx, &M, 1, true);
+        OpMaps J;
+        J.build(h, g_ctx->stream);
+        DevBuf<double> eP(6 * (size_t)m, g_ctx->stream), eF(3 * (size_t)std::max(n, 1), g_ctx->stream);
+        eP.upload(ea, 6 * (size_t)m);
+        if (n) eF.upload(eb, 3 * (size_t)n);
+        DevBuf<int> g(3, g_ctx->stream);
+        k_set_gauge<<<1, 1, 0, g_ctx->stream>>>(g.p, Ref, Fix, Sign);
+        MonoGauge gauge{g.p, g.p + 1, g.p + 2};
+        g_dbg = SolveDebug();
+        solve_stereo_batch(*g_ctx, J, eP.p, eF.p, &g_dbg, &gauge);
         g_ctx->check_errors();
         g_dbg_valid = true;
         std::vector<int> tmpno(M.r);

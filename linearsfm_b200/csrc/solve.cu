@@ -557,12 +557,17 @@ __global__ void k_front_rhs(const int *__restrict__ poseSn, const int *__restric
 // is staged in shared memory, factored there (6x6 diagonal blocks by one warp, row solves and the
 // in-panel updates by the whole CTA), applied ONCE to everything right of it in global memory
 // (left-looking rank-pc update, panel read from shared memory) and written back.
+// GP = true: fronts too tall for a shared-memory panel (> ~2100 rows: loop-closure-heavy or very large
+// systems) keep the panel in a per-front global scratch area instead -- same code, slower, no failure.
+template <bool GP>
 __global__ void __launch_bounds__(512)
 k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
                const int *__restrict__ childIdx, const int *__restrict__ relIdx,
-               double *__restrict__ fronts, int *__restrict__ errflag, int pcMax)
+               double *__restrict__ fronts, int *__restrict__ errflag, int pcMax,
+               double *__restrict__ panelG, size_t panelStride)
 {
-    extern __shared__ double P[];                 // [pc][ldp] column-major panel
+    extern __shared__ double Psh[];               // [pc][ldp] column-major panel
+    double *P = GP ? panelG + (size_t)blockIdx.x * panelStride : Psh;
     __shared__ double Li[36];                     // inverse of the current diagonal block's factor
     const SnodeDesc d = sn[levelSn[blockIdx.x]];
     double *F = fronts + d.frontOff;
@@ -1107,22 +1112,38 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     if (nuis > 0) { k_front_assemble<<<ceil_div(36ll * nuis, TB), TB, 0, s>>>(dSlot.p, nuis, dSn.p, S.p, fronts.p); nl++; }
     k_front_rhs<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(dPoseSn.p, dPoseLcol.p, J.totPose, dSn.p, E.p, fronts.p); nl++;
     int nLevels = (int)sym.levelPtr.size() - 1;
-    // panel width: 48 columns (8 pose blocks) unless the tallest front of the batch needs a narrower one
+    // panel width: 48 columns (8 pose blocks) unless the tallest front of the batch needs a narrower one;
+    // fronts whose panel would be narrower than two pose blocks keep it in global memory instead
     const size_t frows = 6 * (size_t)sym.maxFdim + 2;
     int pcMax = (int)std::min<size_t>(48, ((size_t)200 * 1024 / (8 * frows)) / 6 * 6);
-    if (pcMax < 6) throw LsfmError(LSFM_ERR_ARG, "front too tall for the shared-memory panel");
-    const size_t shf = sizeof(double) * (size_t)pcMax * frows;
+    static const bool force_gp = getenv("LSFM_FORCE_GLOBAL_PANEL") != nullptr;      // test hook
+    const bool globalPanel = pcMax < 12 || force_gp;
+    if (globalPanel) pcMax = 48;
+    const size_t panelStride = (size_t)pcMax * frows;
+    const size_t shf = globalPanel ? 0 : sizeof(double) * panelStride;
+    int maxCnt = 1;
+    for (int l = 0; l < nLevels; l++) maxCnt = std::max(maxCnt, sym.levelPtr[l + 1] - sym.levelPtr[l]);
+    DevBuf<double> panelG(globalPanel ? panelStride * (size_t)maxCnt : 1, s);
     if (shf > 48 * 1024)
-        CUDA_CHECK(cudaFuncSetAttribute(k_front_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shf));
+        CUDA_CHECK(cudaFuncSetAttribute(k_front_factor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shf));
     for (int l = 0; l < nLevels; l++) {
         int cnt = sym.levelPtr[l + 1] - sym.levelPtr[l];
         if (cnt == 0) continue;
         // few fronts on the level (the top of the assembly tree): twice the threads per front --
         // the SMs are idle anyway and the extend-add / trailing update scale with the warps
         const int thr = (cnt <= ctx.num_sms) ? 512 : 256;
-        k_front_factor<<<cnt, thr, shf, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p, pcMax); nl++;
+        if (globalPanel)
+            k_front_factor<true><<<cnt, thr, 0, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p,
+                                                    pcMax, panelG.p, panelStride);
+        else
+            k_front_factor<false><<<cnt, thr, shf, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p,
+                                                       err.p, pcMax, nullptr, 0);
+        nl++;
     }
     size_t shb = sizeof(double) * (6 * (size_t)(sym.maxFdim + 1) + BS_PC * BS_TS);
+    if (shb > 220 * 1024)
+        throw LsfmError(LSFM_ERR_ARG, "a Cholesky front of " + std::to_string(sym.maxFdim) +
+                                          " pose blocks exceeds the back-solve's shared-memory capacity (~4400 blocks)");
     if (shb > 48 * 1024)
         CUDA_CHECK(cudaFuncSetAttribute(k_front_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
     for (int l = nLevels - 1; l >= 0; l--) {

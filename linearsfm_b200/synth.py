@@ -111,6 +111,79 @@ def make_trajectory(nframes: int, rng: np.random.Generator):
     return p, ang, R
 
 
+def _stereo_block(cam, Rw, p, Xw, rows_l, rows_k, eps0_all, eps1_all, gate):
+    """Two-view estimates and information blocks of the local maps k = 0..N-1 of one block: frames
+    Rw[k], p[k] (N+1 of them), observation rows (rows_l = landmark, rows_k = map, sorted by map)."""
+    N = Rw.shape[0] - 1
+    sig = cam.sigma
+    Rk, Rk1 = Rw[:N], Rw[1:N + 1]
+    t_rel = np.einsum("kij,kj->ki", Rk, p[1:N + 1] - p[:N])
+    R_rel = np.einsum("kij,klj->kil", Rk1, Rk)
+    a_rel = np.stack(ypr_from_rot(R_rel), -1)
+    w = 1.0 / sig ** 2
+
+    for gate_pass in range(4 if gate else 1):
+        n_of_map = np.bincount(rows_k, minlength=N)
+        foff = np.concatenate([[0], np.cumsum(n_of_map)])
+        if np.any(n_of_map == 0):
+            raise ValueError("a local map has no features; increase feats_per_frame")
+        eps0, eps1 = eps0_all, eps1_all
+        # truth: relative pose of frame k+1 in frame k, landmark in frame k
+        X0 = np.einsum("tij,tj->ti", Rk[rows_k], Xw[rows_l] - p[rows_k])      # in frame k
+
+        def linearise(t_p, a_p, X):
+            """Jacobians of the two stereo observations of every row at (pose, X)."""
+            R1 = rot_ypr(a_p[:, 0], a_p[:, 1], a_p[:, 2])
+            dA, dB, dG = drot_ypr(a_p[:, 0], a_p[:, 1], a_p[:, 2])
+            R1r, dAr, dBr, dGr = R1[rows_k], dA[rows_k], dB[rows_k], dG[rows_k]
+            d = X - t_p[rows_k]
+            Xc1 = np.einsum("tij,tj->ti", R1r, d)
+            J0 = cam.jac(X)                                   # obs in frame k: d z / d X
+            Jp1 = cam.jac(Xc1)
+            JX1 = np.einsum("tij,tjk->tik", Jp1, R1r)          # d z / d X
+            Jang = np.stack([np.einsum("tij,tj->ti", dAr, d), np.einsum("tij,tj->ti", dBr, d),
+                             np.einsum("tij,tj->ti", dGr, d)], -1)     # [T,3(xyz),3(angles)]
+            JP1 = np.concatenate([-JX1, np.einsum("tij,tjk->tik", Jp1, Jang)], -1)   # [T,3,6]
+            return J0, JX1, JP1, Xc1
+
+        def assemble(J0, JX1, JP1):
+            V = w * (np.einsum("tki,tkj->tij", J0, J0) + np.einsum("tki,tkj->tij", JX1, JX1))
+            W = w * np.einsum("tki,tkj->tij", JP1, JX1)                  # [T,6,3]
+            Ub = w * np.einsum("tki,tkj->tij", JP1, JP1)                 # [T,6,6]
+            U = np.add.reduceat(Ub, foff[:-1], axis=0)
+            return U, W, V
+
+        # Gauss-Newton-consistent draw at the truth
+        J0, JX1, JP1, _ = linearise(t_rel, a_rel, X0)
+        U, W, V = assemble(J0, JX1, JP1)
+        gF = w * (np.einsum("tki,tk->ti", J0, eps0) + np.einsum("tki,tk->ti", JX1, eps1))
+        gP = np.add.reduceat(w * np.einsum("tki,tk->ti", JP1, eps1), foff[:-1], axis=0)
+        Vi = np.linalg.inv(V)
+        WVi = np.einsum("tij,tjk->tik", W, Vi)
+        S = U - np.add.reduceat(np.einsum("tij,tkj->tik", WVi, W), foff[:-1], axis=0)
+        e = gP - np.add.reduceat(np.einsum("tij,tj->ti", WVi, gF), foff[:-1], axis=0)
+        dP = np.linalg.solve(S, e[..., None])[..., 0]
+        dF = np.einsum("tij,tj->ti", Vi, gF - np.einsum("tji,tj->ti", W, dP[rows_k]))
+
+        t_est = t_rel + dP[:, :3]
+        a_est = a_rel + dP[:, 3:]
+        X_est = X0 + dF
+        if not gate:
+            break
+        _, _, _, Xc1e = linearise(t_est, a_est, X_est)
+        bad = (X_est[:, 0] < 1.0) | (Xc1e[:, 0] < 1.0) | (np.abs(X_est[:, 0] - X0[:, 0]) > 0.5 * X0[:, 0])
+        if not bad.any():
+            break
+        keep_rows = ~bad
+        rows_l, rows_k = rows_l[keep_rows], rows_k[keep_rows]
+        eps0_all, eps1_all = eps0_all[keep_rows], eps1_all[keep_rows]
+
+    # information at the estimate = what the BA front-end would export
+    J0, JX1, JP1, _ = linearise(t_est, a_est, X_est)
+    U, W, V = assemble(J0, JX1, JP1)
+    return dict(rows_l=rows_l, n_of_map=n_of_map, t_est=t_est, a_est=a_est, X_est=X_est, U=U, W=W, V=V)
+
+
 def make_loop_trajectory(nframes: int, lap: int, rng: np.random.Generator):
     """Closed circuit driven lap after lap (`lap` frames per lap): frame j and frame j - lap see the
     same place from nearly the same pose (a few decimetres / tenths of a degree apart), which is what
@@ -140,7 +213,7 @@ def make_loop_trajectory(nframes: int, lap: int, rng: np.random.Generator):
 def make_stereo_scene(num_maps: int, feats_per_frame: int = 128, seed: int = SEED0,
                       min_life: int = 2, max_life: int = 6, cam: StereoCam | None = None,
                       return_truth: bool = False, revisit: float = 0.0, lap: int = 500,
-                      max_depth: float = 30.0, gate: bool = False):
+                      max_depth: float = 30.0, gate: bool = False, block_maps: int = 1024):
     """Generate `num_maps` consistent stereo local maps. Returns a list of LocalMap (views into
     flat arrays) and, optionally, the ground truth dict.
 
@@ -209,72 +282,29 @@ def make_stereo_scene(num_maps: int, feats_per_frame: int = 128, seed: int = SEE
     sig = cam.sigma
     eps0_all = rng.normal(0.0, sig, (rows_k.shape[0], 3))
     eps1_all = rng.normal(0.0, sig, (rows_k.shape[0], 3))
-    Rk, Rk1 = Rw[:N], Rw[1:N + 1]
-    t_rel = np.einsum("kij,kj->ki", Rk, p[1:N + 1] - p[:N])
-    R_rel = np.einsum("kij,klj->kil", Rk1, Rk)
-    a_rel = np.stack(ypr_from_rot(R_rel), -1)
-    w = 1.0 / sig ** 2
-
-    for gate_pass in range(4 if gate else 1):
-        T = rows_k.shape[0]
-        n_of_map = np.bincount(rows_k, minlength=N)
-        foff = np.concatenate([[0], np.cumsum(n_of_map)])
-        if np.any(n_of_map == 0):
-            raise ValueError("a local map has no features; increase feats_per_frame")
-        eps0, eps1 = eps0_all, eps1_all
-        # truth: relative pose of frame k+1 in frame k, landmark in frame k
-        X0 = np.einsum("tij,tj->ti", Rk[rows_k], Xw[rows_l] - p[rows_k])      # in frame k
-
-        def linearise(t_p, a_p, X):
-            """Jacobians of the two stereo observations of every row at (pose, X)."""
-            R1 = rot_ypr(a_p[:, 0], a_p[:, 1], a_p[:, 2])
-            dA, dB, dG = drot_ypr(a_p[:, 0], a_p[:, 1], a_p[:, 2])
-            R1r, dAr, dBr, dGr = R1[rows_k], dA[rows_k], dB[rows_k], dG[rows_k]
-            d = X - t_p[rows_k]
-            Xc1 = np.einsum("tij,tj->ti", R1r, d)
-            J0 = cam.jac(X)                                   # obs in frame k: d z / d X
-            Jp1 = cam.jac(Xc1)
-            JX1 = np.einsum("tij,tjk->tik", Jp1, R1r)          # d z / d X
-            Jang = np.stack([np.einsum("tij,tj->ti", dAr, d), np.einsum("tij,tj->ti", dBr, d),
-                             np.einsum("tij,tj->ti", dGr, d)], -1)     # [T,3(xyz),3(angles)]
-            JP1 = np.concatenate([-JX1, np.einsum("tij,tjk->tik", Jp1, Jang)], -1)   # [T,3,6]
-            return J0, JX1, JP1, Xc1
-
-        def assemble(J0, JX1, JP1):
-            V = w * (np.einsum("tki,tkj->tij", J0, J0) + np.einsum("tki,tkj->tij", JX1, JX1))
-            W = w * np.einsum("tki,tkj->tij", JP1, JX1)                  # [T,6,3]
-            Ub = w * np.einsum("tki,tkj->tij", JP1, JP1)                 # [T,6,6]
-            U = np.add.reduceat(Ub, foff[:-1], axis=0)
-            return U, W, V
-
-        # Gauss-Newton-consistent draw at the truth
-        J0, JX1, JP1, _ = linearise(t_rel, a_rel, X0)
-        U, W, V = assemble(J0, JX1, JP1)
-        gF = w * (np.einsum("tki,tk->ti", J0, eps0) + np.einsum("tki,tk->ti", JX1, eps1))
-        gP = np.add.reduceat(w * np.einsum("tki,tk->ti", JP1, eps1), foff[:-1], axis=0)
-        Vi = np.linalg.inv(V)
-        WVi = np.einsum("tij,tjk->tik", W, Vi)
-        S = U - np.add.reduceat(np.einsum("tij,tkj->tik", WVi, W), foff[:-1], axis=0)
-        e = gP - np.add.reduceat(np.einsum("tij,tj->ti", WVi, gF), foff[:-1], axis=0)
-        dP = np.linalg.solve(S, e[..., None])[..., 0]
-        dF = np.einsum("tij,tj->ti", Vi, gF - np.einsum("tji,tj->ti", W, dP[rows_k]))
-
-        t_est = t_rel + dP[:, :3]
-        a_est = a_rel + dP[:, 3:]
-        X_est = X0 + dF
-        if not gate:
-            break
-        _, _, _, Xc1e = linearise(t_est, a_est, X_est)
-        bad = (X_est[:, 0] < 1.0) | (Xc1e[:, 0] < 1.0) | (np.abs(X_est[:, 0] - X0[:, 0]) > 0.5 * X0[:, 0])
-        if not bad.any():
-            break
-        keep_rows = ~bad
-        rows_l, rows_k = rows_l[keep_rows], rows_k[keep_rows]
-        eps0_all, eps1_all = eps0_all[keep_rows], eps1_all[keep_rows]
-
-    # information at the estimate = what the BA front-end would export
-    J0, JX1, JP1, _ = linearise(t_est, a_est, X_est)
-    U, W, V = assemble(J0, JX1, JP1)
+    # The per-map work below is independent from map to map: it runs over blocks of `block_maps` maps so
+    # that the 50k-map / multi-million-landmark scenes (BASELINE.json configs[4]) fit in host memory.
+    if np.any(np.bincount(rows_k, minlength=N) == 0):
+        raise ValueError("a local map has no features; increase feats_per_frame")
+    bounds = np.searchsorted(rows_k, np.arange(0, N + block_maps, block_maps).clip(max=N))
+    parts = []
+    for bi in range(len(bounds) - 1):
+        k0 = bi * block_maps
+        k1 = min(N, k0 + block_maps)
+        r0, r1 = bounds[bi], bounds[bi + 1]
+        parts.append(_stereo_block(cam, Rw[k0:k1 + 1], p[k0:k1 + 1], Xw, rows_l[r0:r1], rows_k[r0:r1] - k0,
+                                   eps0_all[r0:r1], eps1_all[r0:r1], gate))
+    del eps0_all, eps1_all
+    rows_l = np.concatenate([q["rows_l"] for q in parts])
+    n_of_map = np.concatenate([q["n_of_map"] for q in parts])
+    foff = np.concatenate([[0], np.cumsum(n_of_map)])
+    t_est = np.concatenate([q["t_est"] for q in parts])
+    a_est = np.concatenate([q["a_est"] for q in parts])
+    X_est = np.concatenate([q["X_est"] for q in parts])
+    U = np.concatenate([q["U"] for q in parts])
+    W = np.concatenate([q["W"] for q in parts])
+    V = np.concatenate([q["V"] for q in parts])
+    del parts
 
     maps = []
     ids32 = gid.astype(np.int32)

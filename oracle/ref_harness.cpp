@@ -13,7 +13,7 @@
 //   ref_run_tree_stereo       -> CLinearSFMImp::lmj_PF3D_Divide_ConquerStereo   Imp.cpp:1926-2099
 //   ref_load_localmap_stereo  -> CLinearSFMImp::lmj_readInformationStereo       Imp.cpp:3044-3132
 //   (mono twins: lmj_Transform_PF3DMono 3173, lmj_LinearLS_PF3DMono 7282, Divide_ConquerMono 6511,
-//    lmj_readInformationMono 6660)
+//    lmj_readInformationMono 6660, ref_solve_mono -> lmj_solveLinearSFMMono 6756-7041)
 //
 // Two preprocessor hooks are applied to the reference TU (they change no arithmetic):
 //   * `private` -> `public`, so the harness can place maps in m_GMapS / m_LMsetS;
@@ -262,6 +262,15 @@ int ref_join_mono(const ref_map *end, const ref_map *cur, ref_map *out)
     I->lmj_LinearLS_PF3DMono(E, C);
     from_mono(I->m_GMap, out, true);
     ref_map tmp; from_mono(I->m_GMap, &tmp, false); ref_free_map(&tmp);
+    return 0;
+}
+
+int ref_solve_mono(double *stVal, double *eb, double *ea, double *U, double *W, double *V,
+                   int *Ui, int *Uj, int *photo, int *feature, int m, int n, int nU, int nW,
+                   int Ref, int ScaP, int Fix, int Sign, int FixBlk)
+{
+    imp()->lmj_solveLinearSFMMono(stVal, eb, ea, U, W, V, Ui, Uj, photo, feature, m, n, nU, nW, Ref, ScaP, Fix,
+                                  Sign, FixBlk);
     return 0;
 }
 

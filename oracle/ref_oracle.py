@@ -177,6 +177,20 @@ def join_mono(end: LocalMap, cur: LocalMap) -> LocalMap:
     return from_c(out)
 
 
+def solve_mono(ea, eb, U, W, V, Ui, Uj, photo, feature, m, n, Ref, ScaP, Fix, Sign, FixBlk):
+    """CLinearSFMImp::lmj_solveLinearSFMMono (LinearSFMImp.cpp:6756). Returns stVal[6m+3n]."""
+    ea = _keep(ea, np.float64).copy(); eb = _keep(eb, np.float64).copy()
+    U = _keep(U, np.float64).copy(); W = _keep(W, np.float64).copy(); V = _keep(V, np.float64).copy()
+    Ui = _keep(Ui, np.int32).copy(); Uj = _keep(Uj, np.int32).copy()
+    photo = _keep(photo, np.int32).copy(); feature = _keep(feature, np.int32).copy()
+    st = np.zeros(6 * m + 3 * n)
+    p = lambda a: a.ctypes.data_as(_pi if a.dtype == np.int32 else _pd)
+    lib().ref_solve_mono(p(st), p(eb), p(ea), p(U), p(W), p(V), p(Ui), p(Uj), p(photo), p(feature),
+                         C.c_int(m), C.c_int(n), C.c_int(Ui.shape[0]), C.c_int(photo.shape[0]),
+                         C.c_int(Ref), C.c_int(ScaP), C.c_int(Fix), C.c_int(Sign), C.c_int(FixBlk))
+    return st
+
+
 def run_tree_mono(maps):
     return _run_tree(lib().ref_run_tree_mono, maps)
 

@@ -86,9 +86,9 @@ def test_mono_rs90_size(gpu, oracle):
     from linearsfm_b200.localmap import maps_equal_int
     from util import rel_err
     assert not maps_equal_int(got, ref)
-    # The reference's mono pipeline amplifies a 1e-15 relative perturbation of its INPUT to ~4e-7 on
-    # the final state at this size (tests/test_mono_conditioning.py); 1e-5 is the meaningful bar here.
-    assert rel_err(got.stVal, ref.stVal) <= 1e-5
+    # north_star's bar (measured: 1.3e-7; the reference's own sensitivity at this size is ~4e-7,
+    # tests/test_mono_conditioning.py)
+    assert rel_err(got.stVal, ref.stVal) <= 1e-6
 
 
 def test_mono_parity_relative_to_reference_conditioning(gpu, oracle):
@@ -110,3 +110,110 @@ def test_mono_parity_relative_to_reference_conditioning(gpu, oracle):
     got = gpu.run_mono(maps)
     assert not maps_equal_int(got, ref)
     assert rel_err(got.stVal, ref.stVal) <= max(1e-6, 30 * sens), (rel_err(got.stVal, ref.stVal), sens)
+
+
+def test_mono_rs468_size(gpu, oracle):
+    """RS468_C shape: 466 local maps (BASELINE.json configs[1]).  Integers bit-exact; the state is held to
+    the reference's own conditioning at this chain length (1e-15 relative input noise moves the
+    reference's result by ~4e-2 here) -- the 1e-6 bar is asserted on the shorter
+    chains above and teacher-forced per level in test_mono_teacher_forced_466."""
+    import copy
+    from util import rel_err
+    from linearsfm_b200.localmap import maps_equal_int
+    maps = synth.make_mono_scene(466, feats_per_frame=40, style="aerial", seed=468)
+    ref, _, _ = oracle.run_tree_mono(maps)
+    got = gpu.run_mono(maps)
+    assert not maps_equal_int(got, ref)
+    check_meta(got, ref)
+    rng = np.random.default_rng(0)
+    pert = []
+    for m in maps:
+        m2 = copy.deepcopy(m)
+        m2.W = m2.W * (1 + 1e-15 * rng.standard_normal(m2.W.shape))
+        pert.append(m2)
+    ref2, _, _ = oracle.run_tree_mono(pert)
+    sens = rel_err(ref.stVal, ref2.stVal)
+    err = rel_err(got.stVal, ref.stVal)
+    print(f"mono 466: state rel err {err:.3e}, reference self-sensitivity {sens:.3e}")
+    assert err <= max(1e-6, 30 * sens), (err, sens)
+
+
+def test_mono_teacher_forced_466(gpu, oracle):
+    """The mono tree of the RS468 size level by level (lmj_PF3D_Divide_ConquerMono, LinearSFMImp.cpp:
+    6511-6658) with the reference's own operators; every CUDA Transform / Join gets the ORACLE's inputs
+    of its level: integers exact, Transform <= 1e-9, join state <= 1e-6 (and <= 1e-8 on all but the
+    worst-conditioned joins), information blocks <= 1e-9."""
+    from util import rel_err
+    from linearsfm_b200.localmap import maps_equal_int
+    level = synth.make_mono_scene(466, feats_per_frame=40, style="aerial", seed=468)
+    L = 0
+    while len(level) > 1:
+        cnt = len(level)
+        E = [level[2 * i] for i in range(cnt // 2)]
+        Cm = [level[2 * i + 1] for i in range(cnt // 2)]
+        Et = [oracle.transform_mono(e, c.Ref, c.ScaP, c.Fix) for e, c in zip(E, Cm)]
+        J = [oracle.join_mono(et, c) for et, c in zip(Et, Cm)]
+        got = gpu.transform_mono_batch(E, [c.Ref for c in Cm], [c.ScaP for c in Cm], [c.Fix for c in Cm])
+        wt = 0.0
+        for g, r in zip(got, Et):
+            assert not maps_equal_int(g, r)
+            wt = max(wt, rel_err(g.stVal, r.stVal), rel_err(g.U, r.U), rel_err(g.W, r.W), rel_err(g.V, r.V))
+        assert wt <= 1e-9, f"mono level {L} transform {wt:.3e}"
+        got = gpu.join_mono_batch(Et, Cm)
+        wj, wi, loose = 0.0, 0.0, 0
+        for g, r in zip(got, J):
+            assert not maps_equal_int(g, r)
+            check_meta(g, r)
+            e = rel_err(g.stVal, r.stVal)
+            wj = max(wj, e)
+            loose += e > 1e-8
+            wi = max(wi, rel_err(g.U, r.U), rel_err(g.W, r.W), rel_err(g.V, r.V))
+        print(f"mono level {L}: pairs {len(J)} m {J[0].m} transform {wt:.2e} join state {wj:.2e} info {wi:.2e} (> 1e-8: {loose})")
+        assert wj <= 1e-6 and wi <= 1e-9
+        nxt = list(J)
+        if cnt % 2:
+            nxt.append(level[cnt - 1])
+        for i in range(len(nxt)):
+            if (i + 1) % 2 == 0 and nxt[i].Ref > nxt[i].FRef:
+                nxt[i] = oracle.transform_mono(nxt[i], nxt[i].FRef, nxt[i].FScaP, nxt[i].FFix)
+        level = nxt
+        L += 1
+
+
+def test_mono_solve_operator(gpu, oracle, mono8):
+    """lmj_solveLinearSFMMono (LinearSFMImp.h:223): the narrowest pure-array mono operator, same arrays
+    into the reference and into lsfm_solve_mono."""
+    j = []
+    for a in (0, 2):
+        e = oracle.transform_mono(mono8[a], mono8[a + 1].Ref, mono8[a + 1].ScaP, mono8[a + 1].Fix)
+        j.append(oracle.join_mono(e, mono8[a + 1]))
+    cur = oracle.transform_mono(j[1], j[1].FRef, j[1].FScaP, j[1].FFix)
+    end = oracle.transform_mono(j[0], cur.Ref, cur.ScaP, cur.Fix)
+    J = oracle.join_mono(end, cur)
+    # gauge of the joint system (LinearSFMImp.cpp:7383-7409, 7860-7864)
+    ids = list(end.pose_ids())
+    posID1, posID2 = ids.index(cur.Ref), ids.index(cur.ScaP)
+    Ref, ScaP, Fix, Sign, FixBlk = posID1, 6 * posID1, 6 * posID2 + end.Fix, end.Sign, posID2 - 1
+    m, n = J.m, J.n
+    # a right-hand side consistent with the joint information and a known solution (gauge entries zero)
+    x = J.stVal.copy()
+    x[ScaP:ScaP + 6] = 0.0
+    x[Fix] = 0.0
+    xp, xf = x[:6 * m].reshape(m, 6), x[6 * m:].reshape(n, 3)
+    ea = np.zeros((m, 6)); eb = np.zeros((n, 3))
+    for b in range(J.nU):
+        i, k = J.Ui[b], J.Uj[b]
+        ea[i] += J.U[b] @ xp[k]
+        if i != k:
+            ea[k] += J.U[b].T @ xp[i]
+    np.add.at(ea, J.photo, np.einsum("bij,bj->bi", J.W, xf[J.feature]))
+    np.add.at(eb, J.feature, np.einsum("bij,bi->bj", J.W, xp[J.photo]))
+    eb += np.einsum("fij,fj->fi", J.V, xf)
+    args = (J.U, J.W, J.V, J.Ui, J.Uj, J.photo, J.feature, m, n, Ref, ScaP, Fix, Sign, FixBlk)
+    ref = oracle.solve_mono(ea.reshape(-1), eb.reshape(-1), *args)
+    got = gpu.CLinearSFMImp().lmj_solveLinearSFMMono(eb.reshape(-1), ea.reshape(-1), *args)
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(got - ref)) <= 1e-8 * scale, np.max(np.abs(got - ref)) / scale
+    assert got[Fix] == Sign and np.all(got[ScaP:ScaP + 6] == 0.0)
+    x[Fix] = Sign
+    assert np.max(np.abs(got - x)) <= 1e-6 * scale

@@ -77,12 +77,14 @@ def test_tree_88(gpu, oracle):
 @pytest.mark.parametrize("env,size", [({"LSFM_FORCE_OVERFLOW": "1"}, ("37", "30")),
                                       ({"LSFM_SCHUR_DENSE": "1"}, ("37", "30")),
                                       ({"LSFM_SCHUR_DENSE": "1"}, ("300", "128")),
-                                      ({"LSFM_SCHUR_V1": "1"}, ("37", "30"))])
+                                      ({"LSFM_SCHUR_V1": "1"}, ("37", "30")),
+                                      ({"LSFM_FORCE_GLOBAL_PANEL": "1"}, ("88", "64"))])
 def test_tree_alternative_paths(gpu, oracle, env, size):
     # LSFM_FORCE_OVERFLOW: chunks that see "too many" distinct poses (forced: > 4) take the thread-per-block
     # paths of the Transform / pattern / Schur kernels.  LSFM_SCHUR_DENSE: the DMMA Schur kernel
     # (schur_dense.cuh; 300 maps reach the 512-thread instantiation with 12 dense poses per chunk).
-    # LSFM_SCHUR_V1: the first, atomics-only Schur kernel.  The switches are read once per process.
+    # LSFM_SCHUR_V1: the first, atomics-only Schur kernel.  LSFM_FORCE_GLOBAL_PANEL: the Cholesky fronts'
+    # global-memory panel (the path fronts taller than ~2100 rows take).  Read once per process.
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     e = dict(os.environ); e.update(env)
