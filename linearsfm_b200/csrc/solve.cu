@@ -466,6 +466,7 @@ k_e_gather(const int *__restrict__ posePre, int K, int totP, const int *__restri
 } // namespace
 #include "schur_pipe.cuh"
 #include "schur_dense.cuh"
+#include "schur_lock.cuh"
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -1028,8 +1029,11 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         } else {
             // pipelined kernel; instantiation chosen from the measured max #distinct poses per chunk
             auto launch = [&](auto kern, size_t shb, int threads) {
-                if (shb > 48 * 1024)
+                if (shb > 48 * 1024) {
                     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
+                    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                    (int)cudaSharedmemCarveoutMaxShared));
+                }
                 kern<<<nChunks, threads, shb, s>>>(J.d.p, dChunks.p, chunkInfo.p, blkInfo.p, pat_cmax_used, J.dWPre.p,
                                                   J.dFeatPre.p, J.dPosePre.p, Vinv.p, dvec.p, split, keys.p, rowPtr.p, S.p, E.p,
                                                   sexp.p, Sfx.p, Erec.p);
@@ -1041,6 +1045,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             // FP64 pipe (profiles/r2_ncu_schur_dense.md): it is slower than the register-tiled scalar
             // kernel at every tree level, so the latter stays the default.
             static const bool use_dense = getenv("LSFM_SCHUR_DENSE") != nullptr;
+            static const bool use_pipe = getenv("LSFM_SCHUR_PIPE") != nullptr;    // previous per-lane-list kernel
+            static const int lock_t = getenv("LSFM_SCHUR_LOCK_T") ? atoi(getenv("LSFM_SCHUR_LOCK_T")) : 0;
             if (use_dense) {
                 if (maxNposes <= 16 || force_ovf2)
                     launch(schur_dense::k_schur_dense<16, 160, 256, 2, 8>, schur_dense::Layout<16, 160, 256>::bytes(), 256);
@@ -1048,6 +1054,13 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
                     launch(schur_dense::k_schur_dense<31, 248, 512, 4, 16>, schur_dense::Layout<31, 248, 512>::bytes(), 512);
             } else if (maxNposes <= 8 || force_ovf2)
                 launch(schur_pipe::k_schur_pipe<8, 64, 32, 128, 1>, schur_pipe::Layout<8, 64, 32>::bytes(), 128);
+            else if (!use_pipe)
+                // upper levels (9-31 poses per chunk): lock-step kernel, two 256-thread CTAs per SM
+                // (LSFM_SCHUR_LOCK_T: 0 = pick by the level's maximum, 128 / 256 = force one instantiation)
+                if (lock_t == 128 || (lock_t == 0 && maxNposes <= 17))
+                    launch(schur_lock::k_schur_lock<96, 32, 128, 4>, schur_lock::Layout<96, 32>::bytes(), 128);
+                else
+                    launch(schur_lock::k_schur_lock<224, 32, 256, 2>, schur_lock::Layout<224, 32>::bytes(), 256);
             else if (maxNposes <= 16)
                 launch(schur_pipe::k_schur_pipe<16, 128, 32, 256, 1>, schur_pipe::Layout<16, 128, 32>::bytes(), 256);
             else
