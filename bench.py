@@ -284,7 +284,7 @@ def main():
         peak, how = load_peaks()
         # stages that are ONE kernel launched once per tree level (CUDA events on the library's
         # stream around that launch): the roofline object is the one with the most time
-        single = {"transform.wv": "tfc::k_tf_chunk", "solve.schur": "schur_pipe::k_schur_pipe",
+        single = {"transform.wv": "tfc::k_tf_chunk", "solve.schur": "schur_lock::k_schur_lock",
                   "join.values": "k_join_w", "solve.backsub": "k_backsub"}
         cand = {k: v for k, v in st.items() if k in single and v["launches"] > 0}
         top = max(cand.items(), key=lambda kv: kv[1]["ms"])
@@ -322,6 +322,25 @@ def main():
                                   for k, v in cand.items() if k != top[0]}}
         api.stats_reset(stage_timing=False)
 
+    # ---- N > 1: the sharded result against a single-GPU solve of the same leaves (rank 0, untimed) ----
+    verify = None
+    if world > 1:
+        root = lsd.run_sharded(be, nmaps, rank, world, dev)
+        barrier()
+        if rank == 0:
+            assert root
+            stno_s, st_s = be.tree.download_state(0)
+            single = api.Tree(maps_all)
+            single.solve()
+            stno_1, st_1 = single.download_state(0)
+            single.close()
+            ints_equal = bool(np.array_equal(stno_s, stno_1))
+            scale = float(np.max(np.abs(st_1)))
+            diff = float(np.max(np.abs(st_s - st_1)) / scale) if ints_equal else None
+            verify = {"against": "single-GPU solve of the same leaves on rank 0 (untimed)", "ints_equal": ints_equal,
+                      "state_max_rel_diff": diff, "bit_identical": bool(ints_equal and np.array_equal(st_s, st_1))}
+        barrier()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -343,6 +362,7 @@ def main():
                        "l2": "inputs larger than L2 (leaf maps ~0.4 GB, upper levels > 1 GB)",
                        "parallelism": f"tree-level sharding x{world}" if world > 1 else "single GPU"},
             "device_ms_per_step": (dev_ms / args.steps) if world == 1 else None,
+            "verify": verify,
             "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes)},
             "gpu_launches": int(launches),

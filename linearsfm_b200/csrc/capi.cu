@@ -329,7 +329,7 @@ int lsfm_block_ordering(int m, const int *Ap, const int *Ai, int *perm)
                 if (Ai[p] != j) { adj[fill[Ai[p]]++] = j; adj[fill[j]++] = Ai[p]; }
         for (int v = 0; v < m; v++) std::sort(adj.begin() + ptr[v], adj.begin() + ptr[v + 1]);
         std::vector<int> p, nodes;
-        lsfm_nd_order(m, ptr.data(), adj.data(), p, nodes);
+        lsfm_order(m, ptr.data(), adj.data(), p, nodes);
         for (int i = 0; i < m; i++) perm[i] = p[i];
         return LSFM_OK;
     } catch (const std::exception &e) {

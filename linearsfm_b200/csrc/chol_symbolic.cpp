@@ -95,6 +95,84 @@ void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm
     }
 }
 
+// LSFM-MD: exact minimum degree on the block graph, the fallback for patterns on which the index
+// bisection of LSFM-ND has no small separator (loop closures / multi-lap trajectories / dense aerial
+// overlap: poses far apart in the index order share features, the cross edges of an index cut need a
+// vertex cover of hundreds of poses and the fill explodes).  Spec (the oracle's twin restates it):
+//   adjacency sets as bit rows; repeat m times: v = the remaining vertex of minimum degree (tie:
+//   smallest index); emit v; every neighbour u of v gets adj(u) |= adj(v) minus {u, v}.
+// Supernodes: consecutive columns k, k+1 are merged when v_{k+1} is a neighbour of v_k at its elimination
+// and the structure grows by at most MD_RELAX blocks (fundamental supernodes: 0), at most MD_MAXW
+// columns per node.
+static const int MD_RELAX = 2, MD_MAXW = 96;
+void lsfm_md_order(int m, const int *ptr, const int *adj, std::vector<int> &perm,
+                   std::vector<int> &nodes)
+{
+    typedef unsigned long long W;
+    const int nw = (m + 63) / 64;
+    std::vector<W> bits((size_t)m * nw, 0);
+    std::vector<int> deg(m);
+    for (int v = 0; v < m; v++) {
+        W *r = &bits[(size_t)v * nw];
+        for (int p = ptr[v]; p < ptr[v + 1]; p++) r[adj[p] >> 6] |= 1ull << (adj[p] & 63);
+        deg[v] = ptr[v + 1] - ptr[v];
+    }
+    std::vector<char> gone(m, 0);
+    std::vector<int> colcnt(m), nb;
+    std::vector<char> nextIsNb(m, 0);
+    perm.clear(); nodes.clear();
+    perm.reserve(m);
+    for (int k = 0; k < m; k++) {
+        int v = -1, bd = 1 << 30;
+        for (int i = 0; i < m; i++)
+            if (!gone[i] && deg[i] < bd) { bd = deg[i]; v = i; }
+        gone[v] = 1;
+        perm.push_back(v);
+        colcnt[k] = bd;
+        const W *rv = &bits[(size_t)v * nw];
+        nb.clear();
+        for (int w = 0; w < nw; w++) {
+            W x = rv[w];
+            while (x) { int b = __builtin_ctzll(x); nb.push_back(w * 64 + b); x &= x - 1; }
+        }
+        for (int u : nb) {
+            W *ru = &bits[(size_t)u * nw];
+            int d = 0;
+            for (int w = 0; w < nw; w++) { ru[w] |= rv[w]; }
+            ru[u >> 6] &= ~(1ull << (u & 63));
+            ru[v >> 6] &= ~(1ull << (v & 63));
+            for (int w = 0; w < nw; w++) d += __builtin_popcountll(ru[w]);
+            deg[u] = d;
+        }
+    }
+    // was the vertex emitted at k+1 a neighbour of the one emitted at k (at ITS elimination)?  Row v keeps
+    // its neighbourhood at elimination time (nothing touches a row once its vertex is gone).
+    for (int k = 0; k + 1 < m; k++) {
+        const W *rv = &bits[(size_t)perm[k] * nw];
+        const int u = perm[k + 1];
+        nextIsNb[k] = (rv[u >> 6] >> (u & 63)) & 1ull;
+    }
+    nodes.push_back(0);
+    int width = 0;
+    for (int k = 0; k < m; k++) {
+        width++;
+        bool merge = k + 1 < m && nextIsNb[k] && width < MD_MAXW &&
+                     colcnt[k + 1] + 1 - colcnt[k] >= 0 && colcnt[k + 1] + 1 - colcnt[k] <= MD_RELAX;
+        if (!merge) { nodes.push_back(k + 1); width = 0; }
+    }
+}
+
+// The ordering rule of the library: LSFM-ND, unless one of its separators has more than
+// ND_MAX_SEPARATOR poses -- then LSFM-MD.
+static const int ND_MAX_SEPARATOR = 64;
+void lsfm_order(int m, const int *ptr, const int *adj, std::vector<int> &perm, std::vector<int> &nodes)
+{
+    lsfm_nd_order(m, ptr, adj, perm, nodes);
+    int big = 0;
+    for (size_t s = 0; s + 1 < nodes.size(); s++) big = std::max(big, nodes[s + 1] - nodes[s]);
+    if (m > 32 && big > ND_MAX_SEPARATOR) lsfm_md_order(m, ptr, adj, perm, nodes);
+}
+
 namespace {
 
 struct JoinSym {
@@ -138,7 +216,7 @@ void analyse_join(int m, const u64 *keys, int nk, JoinSym &J)
     // the keys are sorted by (row, col) with row <= col: vertex v first receives its smaller
     // neighbours (rows a < v, in ascending a), then the larger ones (row v, ascending col) -- every
     // adjacency list is already ascending, no sort needed
-    lsfm_nd_order(m, ptr.data(), adj.data(), J.perm, J.nodes);
+    lsfm_order(m, ptr.data(), adj.data(), J.perm, J.nodes);
     if ((int)J.perm.size() != m) throw std::runtime_error("ordering lost vertices");
     J.iperm.assign(m, 0);
     for (int k = 0; k < m; k++) J.iperm[J.perm[k]] = k;

@@ -11,6 +11,12 @@
 // becomes one (relaxed) supernode.
 void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm,
                    std::vector<int> &nodes);
+// LSFM-MD (exact minimum degree, tie: smallest index; relaxed supernodes) and the library's rule:
+// LSFM-ND unless one of its separators exceeds 64 poses (loop closures, dense overlap), then LSFM-MD.
+// The oracle's twins: oracle/cholmod_shim.c:lsfm_md_order / lsfm_shim_order.
+void lsfm_md_order(int m, const int *ptr, const int *adj, std::vector<int> &perm,
+                   std::vector<int> &nodes);
+void lsfm_order(int m, const int *ptr, const int *adj, std::vector<int> &perm, std::vector<int> &nodes);
 
 struct SnodeDesc {
     int join;            // which join (map) of the batch

@@ -124,6 +124,7 @@ static graph_t build_graph_upper(int n, const int *Ap, const int *Ai)
 
 static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
 
+static int g_nd_max_sep;   /* largest separator of the current dissection */
 /* where[v] : 0 outside the current list, 1 = A, 2 = B, 3 = separator; restored to 0 on return */
 static void nd_dissect(const graph_t *g, const int *L, int len, char *where, int *out, int *nout)
 {
@@ -148,6 +149,7 @@ static void nd_dissect(const graph_t *g, const int *L, int len, char *where, int
         sep[ns++] = best;
     }
     qsort(sep, ns, sizeof(int), cmp_int);
+    if (ns > g_nd_max_sep) g_nd_max_sep = ns;
     int *A = (int *)malloc(len * sizeof(int)), *B = (int *)malloc(len * sizeof(int)), na = 0, nb = 0;
     for (int i = 0; i < len; i++) {
         if (where[L[i]] == 1) A[na++] = L[i];
@@ -160,6 +162,42 @@ static void nd_dissect(const graph_t *g, const int *L, int len, char *where, int
     free(A); free(B); free(sep);
 }
 
+/* LSFM-MD (spec in DESIGN.md): exact minimum degree on the block graph, naive set implementation.  */
+/*   repeat n times: v = remaining vertex with the fewest remaining neighbours (tie: smallest index); */
+/*   emit v; the neighbours of v become pairwise adjacent; v leaves the graph                         */
+static void lsfm_md_order(const graph_t *g, int *perm)
+{
+    int n = g->n;
+    unsigned char *a = (unsigned char *)calloc((size_t)n * n, 1);   /* dense adjacency: an oracle may */
+    char *gone = (char *)calloc(n, 1);
+    int *nb = (int *)malloc(n * sizeof(int));
+    for (int v = 0; v < n; v++)
+        for (int p = g->ptr[v]; p < g->ptr[v + 1]; p++) a[(size_t)v * n + g->adj[p]] = 1;
+    int *deg = (int *)calloc(n, sizeof(int));
+    for (int v = 0; v < n; v++) deg[v] = g->ptr[v + 1] - g->ptr[v];
+    for (int k = 0; k < n; k++) {
+        int v = -1;
+        for (int i = 0; i < n; i++)
+            if (!gone[i] && (v < 0 || deg[i] < deg[v])) v = i;
+        perm[k] = v;
+        gone[v] = 1;
+        int c = 0;
+        for (int u = 0; u < n; u++)
+            if (a[(size_t)v * n + u] && !gone[u]) nb[c++] = u;
+        for (int x = 0; x < c; x++) {
+            unsigned char *ru = a + (size_t)nb[x] * n;
+            for (int y = 0; y < c; y++)
+                if (y != x) ru[nb[y]] = 1;
+            ru[v] = 0;
+            int d = 0;
+            for (int u = 0; u < n; u++) d += (ru[u] && !gone[u]);
+            deg[nb[x]] = d;
+        }
+    }
+    free(a); free(gone); free(nb); free(deg);
+}
+
+/* the ordering rule: LSFM-ND unless one of its separators has more than 64 vertices, then LSFM-MD */
 static void lsfm_nd_order(int n, const int *Ap, const int *Ai, int *perm)
 {
     if (n <= 32) { for (int i = 0; i < n; i++) perm[i] = i; return; }
@@ -168,7 +206,9 @@ static void lsfm_nd_order(int n, const int *Ap, const int *Ai, int *perm)
     for (int i = 0; i < n; i++) L[i] = i;
     char *where = (char *)calloc(n, 1);
     int nout = 0;
+    g_nd_max_sep = 0;
     nd_dissect(&g, L, n, where, perm, &nout);
+    if (g_nd_max_sep > 64) lsfm_md_order(&g, perm);
     free(where); free(L); free(g.ptr); free(g.adj);
 }
 

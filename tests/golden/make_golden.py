@@ -87,3 +87,26 @@ def main_root_pattern():
 
 if __name__ == "__main__" and "--root-pattern" in __import__("sys").argv:
     main_root_pattern()
+
+
+def main_root_pattern_closed():
+    """Block pattern of the reduced camera system of the ROOT join of the 3499-map scene with loop
+    closures (synth revisit=0.1, lap=500, max_depth=15, gate): pose pairs that share a feature of the
+    reference's root joint map + its U pattern (the reference's smask rule, LinearSFMImp.cpp:2156-2173),
+    upper CSC.  The reference's tree is run level by level up to the root (several minutes of CPU)."""
+    import scipy.sparse as sp
+    ro.build()
+    maps = synth.make_stereo_scene(3499, feats_per_frame=128, revisit=0.1, lap=500, max_depth=15.0, gate=True)
+    j = None
+    for rec in ro.run_levels_stereo(maps):
+        if rec["level"] != "final":
+            j = rec["J"][0]
+    m = j.m
+    A = sp.csr_matrix((np.ones(len(j.feature)), (j.photo, j.feature)), shape=(m, j.n))
+    Pm = (A @ A.T).tocoo()
+    rows = np.concatenate([Pm.row, j.Ui, j.Uj]); cols = np.concatenate([Pm.col, j.Uj, j.Ui])
+    G = sp.csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(m, m))
+    U = sp.triu(G).tocsc(); U.sort_indices()
+    np.savez_compressed(os.path.join(HERE, "root_pattern_closed_3499.npz"), Ap=U.indptr.astype(np.int32),
+                        Ai=U.indices.astype(np.int32))
+    print("wrote root_pattern_closed_3499.npz", m, U.nnz)

@@ -60,3 +60,42 @@ def test_ordering_on_the_headline_root_pattern(oracle):
     p_got = api.block_ordering(Ap, Ai)
     assert sorted(p_got.tolist()) == list(range(3499))
     assert np.array_equal(p_got, p_ref)
+
+
+def _fill(m, Ap, Ai, perm):
+    """nnz(L) in blocks of the Cholesky factor of the pattern under `perm` (plain symbolic elimination)."""
+    inv = np.empty(m, np.int64)
+    inv[perm] = np.arange(m)
+    cols = [set() for _ in range(m)]
+    for j in range(m):
+        for i in Ai[Ap[j]:Ap[j + 1]]:
+            a, b = sorted((int(inv[i]), int(inv[j])))
+            if a != b:
+                cols[a].add(b)
+    children = [[] for _ in range(m)]
+    nnz = 0
+    for j in range(m):
+        s = cols[j]
+        for ch in children[j]:
+            s |= cols[ch]
+            cols[ch] = None
+        s.discard(j)
+        nnz += len(s) + 1
+        if s:
+            children[min(s)].append(j)
+    return nnz
+
+
+def test_ordering_on_the_loop_closure_root_pattern(oracle):
+    """Root join of the 3499-map scene WITH loop closures (7 laps, tests/golden/root_pattern_closed_3499.npz,
+    captured from the reference: m = 3499, 203,400 blocks).  Index bisection has no small separator here
+    (LSFM-ND alone: 2.35 M factor blocks, a 1635-pose front); the library's rule switches to LSFM-MD: same
+    permutation as the oracle's twin, and a factor below 0.5 M blocks."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "root_pattern_closed_3499.npz"))
+    Ap, Ai = g["Ap"], g["Ai"]
+    assert Ap.shape[0] == 3500 and int(Ap[-1]) == 203400
+    p_got = api.block_ordering(Ap, Ai)
+    assert sorted(p_got.tolist()) == list(range(3499))
+    assert np.array_equal(p_got, oracle.shim_order(Ap, Ai))
+    assert _fill(3499, Ap, Ai, p_got) < 500_000
