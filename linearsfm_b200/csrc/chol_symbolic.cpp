@@ -24,8 +24,16 @@
 // The map-joining index order is [End poses, Cur poses] recursively, so index bisection follows the
 // merge tree; the vertex cover puts the few "hub" poses (former frame origins, adjacent to a whole
 // sub-map) into the separators instead of their many neighbours.
+// `sepLimit` > 0: give up (return false, outputs unspecified) as soon as a separator exceeds it
+static bool nd_order_impl(int m, const int *ptr, const int *adj, std::vector<int> &perm,
+                          std::vector<int> &nodes, int sepLimit);
 void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm,
                    std::vector<int> &nodes)
+{
+    nd_order_impl(m, ptr, adj, perm, nodes, 0);
+}
+static bool nd_order_impl(int m, const int *ptr, const int *adj, std::vector<int> &perm,
+                          std::vector<int> &nodes, int sepLimit)
 {
     perm.clear(); nodes.clear();
     perm.reserve(m);
@@ -33,7 +41,7 @@ void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm
     if (m <= 32) {
         for (int i = 0; i < m; i++) perm.push_back(i);
         if (m > 0) nodes.push_back(m);
-        return;
+        return true;
     }
     struct Item { std::vector<int> L; bool emit; };
     std::vector<Item> stack;
@@ -81,6 +89,7 @@ void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm
             side[best] = 3;
             sep.push_back(best);
         }
+        if (sepLimit > 0 && (int)sep.size() > sepLimit) return false;
         std::sort(sep.begin(), sep.end());
         std::vector<int> A, B;
         for (size_t i = 0; i < L.size(); i++) {
@@ -93,6 +102,7 @@ void lsfm_nd_order(int m, const int *ptr, const int *adj, std::vector<int> &perm
         stack.push_back({std::move(B), false});
         stack.push_back({std::move(A), false});
     }
+    return true;
 }
 
 // LSFM-MD: exact minimum degree on the block graph, the fallback for patterns on which the index
@@ -111,38 +121,72 @@ void lsfm_md_order(int m, const int *ptr, const int *adj, std::vector<int> &perm
     typedef unsigned long long W;
     const int nw = (m + 63) / 64;
     std::vector<W> bits((size_t)m * nw, 0);
-    std::vector<int> deg(m);
+    const int INF = 1 << 30;
+    std::vector<int> deg(m);              // degree of the remaining vertices, INF once eliminated
     for (int v = 0; v < m; v++) {
         W *r = &bits[(size_t)v * nw];
         for (int p = ptr[v]; p < ptr[v + 1]; p++) r[adj[p] >> 6] |= 1ull << (adj[p] & 63);
         deg[v] = ptr[v + 1] - ptr[v];
     }
-    std::vector<char> gone(m, 0);
-    std::vector<int> colcnt(m), nb;
+    std::vector<int> colcnt(m), nb, nzw;
     std::vector<char> nextIsNb(m, 0);
     perm.clear(); nodes.clear();
     perm.reserve(m);
+    // degree buckets as bit rows over the vertices (smallest index of a bucket = first set bit); rows are
+    // created on first use: the degrees that occur are far fewer than m
+    std::vector<std::vector<W>> bucket(m + 1);
+    std::vector<int> bcount(m + 1, 0);
+    auto bucket_set = [&](int d, int v) {
+        if (bucket[d].empty()) bucket[d].assign(nw, 0);
+        bucket[d][v >> 6] |= 1ull << (v & 63);
+        bcount[d]++;
+    };
+    auto bucket_clear = [&](int d, int v) { bucket[d][v >> 6] &= ~(1ull << (v & 63)); bcount[d]--; };
+    for (int v = 0; v < m; v++) bucket_set(deg[v], v);
+    int mind = 0;
     for (int k = 0; k < m; k++) {
-        int v = -1, bd = 1 << 30;
-        for (int i = 0; i < m; i++)
-            if (!gone[i] && deg[i] < bd) { bd = deg[i]; v = i; }
-        gone[v] = 1;
+        // minimum degree, smallest index among the ties
+        while (bcount[mind] == 0) mind++;
+        const int bd = mind;
+        int v = 0;
+        {
+            const W *b = bucket[bd].data();
+            int w = 0;
+            while (b[w] == 0) w++;
+            v = w * 64 + __builtin_ctzll(b[w]);
+        }
+        bucket_clear(bd, v);
+        deg[v] = INF;
         perm.push_back(v);
         colcnt[k] = bd;
         const W *rv = &bits[(size_t)v * nw];
-        nb.clear();
+        nb.clear(); nzw.clear();
         for (int w = 0; w < nw; w++) {
             W x = rv[w];
+            if (x) nzw.push_back(w);
             while (x) { int b = __builtin_ctzll(x); nb.push_back(w * 64 + b); x &= x - 1; }
         }
+        // adj(u) |= adj(v) \ {u, v}: only the words adj(v) occupies change; the degree follows the new bits
+        const W vbit = 1ull << (v & 63);
+        const int vw = v >> 6;
         for (int u : nb) {
             W *ru = &bits[(size_t)u * nw];
-            int d = 0;
-            for (int w = 0; w < nw; w++) { ru[w] |= rv[w]; }
-            ru[u >> 6] &= ~(1ull << (u & 63));
-            ru[v >> 6] &= ~(1ull << (v & 63));
-            for (int w = 0; w < nw; w++) d += __builtin_popcountll(ru[w]);
-            deg[u] = d;
+            int d = deg[u] - 1;                            // v leaves
+            ru[vw] &= ~vbit;
+            const W ubit = 1ull << (u & 63);
+            const int uw = u >> 6;
+            for (int w : nzw) {
+                W add = rv[w] & ~ru[w];
+                if (w == uw) add &= ~ubit;
+                d += __builtin_popcountll(add);
+                ru[w] |= add;
+            }
+            if (d != deg[u]) {
+                bucket_clear(deg[u], u);
+                bucket_set(d, u);
+                deg[u] = d;
+                if (d < mind) mind = d;
+            }
         }
     }
     // was the vertex emitted at k+1 a neighbour of the one emitted at k (at ITS elimination)?  Row v keeps
@@ -167,10 +211,7 @@ void lsfm_md_order(int m, const int *ptr, const int *adj, std::vector<int> &perm
 static const int ND_MAX_SEPARATOR = 64;
 void lsfm_order(int m, const int *ptr, const int *adj, std::vector<int> &perm, std::vector<int> &nodes)
 {
-    lsfm_nd_order(m, ptr, adj, perm, nodes);
-    int big = 0;
-    for (size_t s = 0; s + 1 < nodes.size(); s++) big = std::max(big, nodes[s + 1] - nodes[s]);
-    if (m > 32 && big > ND_MAX_SEPARATOR) lsfm_md_order(m, ptr, adj, perm, nodes);
+    if (!nd_order_impl(m, ptr, adj, perm, nodes, ND_MAX_SEPARATOR)) lsfm_md_order(m, ptr, adj, perm, nodes);
 }
 
 namespace {

@@ -552,6 +552,95 @@ __global__ void k_front_rhs(const int *__restrict__ poseSn, const int *__restric
     fronts[d.frontOff + (size_t)(6 * poseLcol[p] + q) * ld + fs] = E[6 * (size_t)p + q];
 }
 
+// Factor a panel held in (shared or global) memory: P is [pc][ldp] column-major, rows 0..pc-1 hold the
+// diagonal block (lower triangle), rows pc..rows-1 everything below it.  6x6 diagonal blocks by one
+// thread in registers (factor + its inverse), row solves and the in-panel updates by the whole CTA.
+__device__ __forceinline__ void factor_panel(double *P, const int ldp, const int rows, const int pc, double *Li,
+                                             int *errflag, const int tid, const int nt)
+{
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int b0 = 0; b0 < pc; b0 += 6) {
+        if (tid == 0) {
+            // 6x6 Cholesky of the diagonal block and the inverse of its factor, in registers
+            double a[6][6], li[6][6];
+#pragma unroll
+            for (int j = 0; j < 6; j++)
+#pragma unroll
+                for (int i = j; i < 6; i++) a[i][j] = P[(b0 + j) * ldp + b0 + i];
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                double sdiag = a[j][j];
+#pragma unroll
+                for (int q = 0; q < j; q++) sdiag = fma(-a[j][q], a[j][q], sdiag);
+                if (!(sdiag > 0.0)) { bad = true; sdiag = 1.0; }
+                double djj = sqrt(sdiag);
+                double inv = 1.0 / djj;
+                a[j][j] = djj;
+                li[j][j] = inv;
+#pragma unroll
+                for (int i = j + 1; i < 6; i++) {
+                    double v = a[i][j];
+#pragma unroll
+                    for (int q = 0; q < j; q++) v = fma(-a[i][q], a[j][q], v);
+                    a[i][j] = v * inv;
+                }
+            }
+            // li = L^-1 (lower): li[i][j] = -li[i][i] * sum_{q=j}^{i-1} L[i][q] li[q][j]
+#pragma unroll
+            for (int j = 0; j < 6; j++)
+#pragma unroll
+                for (int i = j + 1; i < 6; i++) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int q = j; q < i; q++) v = fma(a[i][q], li[q][j], v);
+                    li[i][j] = -li[i][i] * v;
+                }
+            if (bad) atomicOr(errflag, 1);
+#pragma unroll
+            for (int j = 0; j < 6; j++)
+#pragma unroll
+                for (int i = j; i < 6; i++) {
+                    P[(b0 + j) * ldp + b0 + i] = a[i][j];
+                    Li[6 * i + j] = li[i][j];
+                }
+        }
+        __syncthreads();
+        // rows below the diagonal block: X = A L^-T, no dependent chain per row
+        for (int rr = b0 + 6 + tid; rr < rows; rr += nt) {
+            double av[6], x[6];
+#pragma unroll
+            for (int q = 0; q < 6; q++) av[q] = P[(b0 + q) * ldp + rr];
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                double v = 0.0;
+#pragma unroll
+                for (int p = 0; p <= q; p++) v = fma(av[p], Li[6 * q + p], v);
+                x[q] = v;
+            }
+#pragma unroll
+            for (int q = 0; q < 6; q++) P[(b0 + q) * ldp + rr] = x[q];
+        }
+        __syncthreads();
+        // remaining panel columns
+        const int rem = pc - b0 - 6;
+        if (rem > 0) {
+            for (int c = b0 + 6 + warp; c < pc; c += nw) {
+                double lc[6];
+#pragma unroll
+                for (int q = 0; q < 6; q++) lc[q] = P[(b0 + q) * ldp + c];
+                for (int rr = c + lane; rr < rows; rr += 32) {
+                    double v = P[c * ldp + rr];
+#pragma unroll
+                    for (int q = 0; q < 6; q++) v -= P[(b0 + q) * ldp + rr] * lc[q];
+                    P[c * ldp + rr] = v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // one CTA per front of the level: extend-add the children, factor the leading ncols block columns,
 // leave the Schur complement (+ updated rhs row) in place for the parent.
 // The factorisation is blocked: a panel of up to `pcMax` columns (all rows below, rhs row included)
@@ -628,86 +717,7 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
             P[q * ldp + rr] = (rr >= q) ? F[(size_t)(p0 + q) * ld + p0 + rr] : 0.0;
         }
         __syncthreads();
-        for (int b0 = 0; b0 < pc; b0 += 6) {
-            if (tid == 0) {
-                // 6x6 Cholesky of the diagonal block and the inverse of its factor, in registers
-                double a[6][6], li[6][6];
-#pragma unroll
-                for (int j = 0; j < 6; j++)
-#pragma unroll
-                    for (int i = j; i < 6; i++) a[i][j] = P[(b0 + j) * ldp + b0 + i];
-                bool bad = false;
-#pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    double sdiag = a[j][j];
-#pragma unroll
-                    for (int q = 0; q < j; q++) sdiag = fma(-a[j][q], a[j][q], sdiag);
-                    if (!(sdiag > 0.0)) { bad = true; sdiag = 1.0; }
-                    double djj = sqrt(sdiag);
-                    double inv = 1.0 / djj;
-                    a[j][j] = djj;
-                    li[j][j] = inv;
-#pragma unroll
-                    for (int i = j + 1; i < 6; i++) {
-                        double v = a[i][j];
-#pragma unroll
-                        for (int q = 0; q < j; q++) v = fma(-a[i][q], a[j][q], v);
-                        a[i][j] = v * inv;
-                    }
-                }
-                // li = L^-1 (lower): li[i][j] = -li[i][i] * sum_{q=j}^{i-1} L[i][q] li[q][j]
-#pragma unroll
-                for (int j = 0; j < 6; j++)
-#pragma unroll
-                    for (int i = j + 1; i < 6; i++) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int q = j; q < i; q++) v = fma(a[i][q], li[q][j], v);
-                        li[i][j] = -li[i][i] * v;
-                    }
-                if (bad) atomicOr(errflag, 1);
-#pragma unroll
-                for (int j = 0; j < 6; j++)
-#pragma unroll
-                    for (int i = j; i < 6; i++) {
-                        P[(b0 + j) * ldp + b0 + i] = a[i][j];
-                        Li[6 * i + j] = li[i][j];
-                    }
-            }
-            __syncthreads();
-            // rows below the diagonal block: X = A L^-T, no dependent chain per row
-            for (int rr = b0 + 6 + tid; rr < rows; rr += nt) {
-                double av[6], x[6];
-#pragma unroll
-                for (int q = 0; q < 6; q++) av[q] = P[(b0 + q) * ldp + rr];
-#pragma unroll
-                for (int q = 0; q < 6; q++) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int p = 0; p <= q; p++) v = fma(av[p], Li[6 * q + p], v);
-                    x[q] = v;
-                }
-#pragma unroll
-                for (int q = 0; q < 6; q++) P[(b0 + q) * ldp + rr] = x[q];
-            }
-            __syncthreads();
-            // remaining panel columns
-            const int rem = pc - b0 - 6;
-            if (rem > 0) {
-                for (int c = b0 + 6 + warp; c < pc; c += nw) {
-                    double lc[6];
-#pragma unroll
-                    for (int q = 0; q < 6; q++) lc[q] = P[(b0 + q) * ldp + c];
-                    for (int rr = c + lane; rr < rows; rr += 32) {
-                        double v = P[c * ldp + rr];
-#pragma unroll
-                        for (int q = 0; q < 6; q++) v -= P[(b0 + q) * ldp + rr] * lc[q];
-                        P[c * ldp + rr] = v;
-                    }
-                }
-                __syncthreads();
-            }
-        }
+        factor_panel(P, ldp, rows, pc, Li, errflag, tid, nt);
         // write the factored panel back
         for (int t = tid; t < pc * rows; t += nt) {
             int q = t / rows, rr = t - q * rows;
@@ -758,6 +768,9 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
 // triangular solve is latency-bound: shared memory instead of L2 for every step).
 constexpr int BS_PC = 48;
 constexpr int BS_TS = BS_PC + 1;      // padded stride: a lane walks a ROW of the column-major triangle
+// PRE = true (big fronts): y_J - L21^T x_struct was formed by k_bf_back_gemv (many CTAs) and waits in
+// the node's own slice of xperm; only the triangular solve with L11 is left for this CTA.
+template <bool PRE>
 __global__ void __launch_bounds__(512)
 k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
                   const int *__restrict__ structIdx, const double *__restrict__ fronts,
@@ -765,7 +778,7 @@ k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__
 {
     const SnodeDesc d = sn[levelSn[blockIdx.x]];
     const double *F = fronts + d.frontOff;
-    const int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1, nc = 6 * d.ncols, us = 6 * d.nstruct;
+    const int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1, nc = 6 * d.ncols, us = PRE ? 0 : 6 * d.nstruct;
     extern __shared__ double sh[];
     double *xs = sh;            // us entries: solution at the struct rows
     double *t = sh + us;        // nc entries
@@ -773,9 +786,11 @@ k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     double *xj = xperm + 6 * (size_t)d.poseOff;
     for (int i = tid; i < us; i += nt) xs[i] = xj[6 * structIdx[d.structOff + i / 6] + (i % 6)];
+    if (PRE)
+        for (int c = tid; c < nc; c += nt) t[c] = xj[6 * (size_t)d.first + c];
     __syncthreads();
     // four columns per warp and pass: their loads are independent, the L2 latency is paid once
-    for (int cb = 4 * warp; cb < nc; cb += 4 * nw) {
+    for (int cb = 4 * warp; cb < nc && !PRE; cb += 4 * nw) {
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         for (int r = lane; r < us; r += 32) {
             const double x = xs[r];
@@ -844,6 +859,9 @@ k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__
     for (int c = tid; c < nc; c += nt) xj[6 * (size_t)d.first + c] = t[c];
 }
 
+} // namespace
+#include "chol_big.cuh"
+namespace {
 __global__ void k_unpermute(DMap *__restrict__ J, const int *__restrict__ posePre, int K, int totP,
                             const int *__restrict__ perm, const double *__restrict__ xperm)
 {
@@ -1113,7 +1131,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     DevBuf<int> dStruct(sym.structIdx.size(), s); dStruct.upload(sym.structIdx);
     DevBuf<int> dRel(sym.relIdx.size(), s); dRel.upload(sym.relIdx);
     DevBuf<int> dChild(sym.childIdx.size(), s); dChild.upload(sym.childIdx);
-    DevBuf<int> dLevelSn(sym.levelSn.size(), s); dLevelSn.upload(sym.levelSn);
+    DevBuf<int> dLevelSn(sym.levelSn.size(), s);        // filled below (small fronts first, then the big ones)
     DevBuf<SlotMap> dSlot(sym.slot.size(), s); dSlot.upload(sym.slot);
     DevBuf<int> dPoseSn(J.totPose, s); dPoseSn.upload(sym.poseSn);
     DevBuf<int> dPoseLcol(J.totPose, s); dPoseLcol.upload(sym.poseLcol);
@@ -1125,9 +1143,33 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     if (nuis > 0) { k_front_assemble<<<ceil_div(36ll * nuis, TB), TB, 0, s>>>(dSlot.p, nuis, dSn.p, S.p, fronts.p); nl++; }
     k_front_rhs<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(dPoseSn.p, dPoseLcol.p, J.totPose, dSn.p, E.p, fronts.p); nl++;
     int nLevels = (int)sym.levelPtr.size() - 1;
-    // panel width: 48 columns (8 pose blocks) unless the tallest front of the batch needs a narrower one;
-    // fronts whose panel would be narrower than two pose blocks keep it in global memory instead
-    const size_t frows = 6 * (size_t)sym.maxFdim + 2;
+    // Fronts of bigfront::BF_MIN_FS or more scalar rows (loop closures, dense overlap) are factored by the
+    // whole GPU (chol_big.cuh: multi-CTA panels + DMMA trailing updates); the others one CTA per front.
+    // Per level: the small fronts first in the level's list, then the big ones.
+    static const bool no_big = getenv("LSFM_NO_BIGFRONT") != nullptr;      // test hook: one CTA per front always
+    // (test hook: LSFM_BIGFRONT_MIN_FS lowers the size from which a front takes the multi-CTA path)
+    static const int big_min_fs = getenv("LSFM_BIGFRONT_MIN_FS") ? std::max(48, atoi(getenv("LSFM_BIGFRONT_MIN_FS")))
+                                                                 : bigfront::BF_MIN_FS;
+    std::vector<int> lvlList(sym.levelSn.size()), nSmall(nLevels, 0);
+    int maxSmallFdim = 1;
+    for (int l = 0; l < nLevels; l++) {
+        int a = sym.levelPtr[l], b = sym.levelPtr[l + 1], w = a;
+        auto is_big = [&](int sid) {
+            const SnodeDesc &d = sym.sn[sid];
+            return !no_big && 6 * (d.ncols + d.nstruct) >= big_min_fs;
+        };
+        for (int i = a; i < b; i++) if (!is_big(sym.levelSn[i])) lvlList[w++] = sym.levelSn[i];
+        nSmall[l] = w - a;
+        for (int i = a; i < a + nSmall[l]; i++) {
+            const SnodeDesc &d = sym.sn[lvlList[i]];
+            maxSmallFdim = std::max(maxSmallFdim, d.ncols + d.nstruct);
+        }
+        for (int i = a; i < b; i++) if (is_big(sym.levelSn[i])) lvlList[w++] = sym.levelSn[i];
+    }
+    dLevelSn.upload(lvlList);
+    // panel width: 48 columns (8 pose blocks) unless the tallest small front of the batch needs a narrower
+    // one; fronts whose panel would be narrower than two pose blocks keep it in global memory instead
+    const size_t frows = 6 * (size_t)maxSmallFdim + 2;
     int pcMax = (int)std::min<size_t>(48, ((size_t)200 * 1024 / (8 * frows)) / 6 * 6);
     static const bool force_gp = getenv("LSFM_FORCE_GLOBAL_PANEL") != nullptr;      // test hook
     const bool globalPanel = pcMax < 12 || force_gp;
@@ -1135,35 +1177,81 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     const size_t panelStride = (size_t)pcMax * frows;
     const size_t shf = globalPanel ? 0 : sizeof(double) * panelStride;
     int maxCnt = 1;
-    for (int l = 0; l < nLevels; l++) maxCnt = std::max(maxCnt, sym.levelPtr[l + 1] - sym.levelPtr[l]);
+    for (int l = 0; l < nLevels; l++) maxCnt = std::max(maxCnt, nSmall[l]);
     DevBuf<double> panelG(globalPanel ? panelStride * (size_t)maxCnt : 1, s);
     if (shf > 48 * 1024)
         CUDA_CHECK(cudaFuncSetAttribute(k_front_factor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shf));
+    const size_t shSyrk = sizeof(double) * 2 * bigfront::BF_PC * bigfront::BF_LDS;
+    const size_t shPanel = sizeof(double) * bigfront::BF_PC * (bigfront::BF_PC + bigfront::BF_RS + 1);
+    bool syrkAttr = false;
     for (int l = 0; l < nLevels; l++) {
-        int cnt = sym.levelPtr[l + 1] - sym.levelPtr[l];
-        if (cnt == 0) continue;
-        // few fronts on the level (the top of the assembly tree): twice the threads per front --
-        // the SMs are idle anyway and the extend-add / trailing update scale with the warps
-        const int thr = (cnt <= ctx.num_sms) ? 512 : 256;
-        if (globalPanel)
-            k_front_factor<true><<<cnt, thr, 0, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p,
-                                                    pcMax, panelG.p, panelStride);
-        else
-            k_front_factor<false><<<cnt, thr, shf, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p,
-                                                       err.p, pcMax, nullptr, 0);
-        nl++;
+        const int cnt = nSmall[l];
+        const int nBig = sym.levelPtr[l + 1] - sym.levelPtr[l] - cnt;
+        if (cnt > 0) {
+            // few fronts on the level (the top of the assembly tree): twice the threads per front --
+            // the SMs are idle anyway and the extend-add / trailing update scale with the warps
+            const int thr = (cnt <= ctx.num_sms) ? 512 : 256;
+            if (globalPanel)
+                k_front_factor<true><<<cnt, thr, 0, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p,
+                                                        pcMax, panelG.p, panelStride);
+            else
+                k_front_factor<false><<<cnt, thr, shf, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p,
+                                                           err.p, pcMax, nullptr, 0);
+            nl++;
+        }
+        if (nBig > 0) {
+            const int *bigSn = dLevelSn.p + sym.levelPtr[l] + cnt;
+            int maxFd = 0, maxNc = 0, maxFs = 0;
+            bool anyChild = false;
+            for (int i = 0; i < nBig; i++) {
+                const SnodeDesc &d = sym.sn[lvlList[sym.levelPtr[l] + cnt + i]];
+                maxFd = std::max(maxFd, d.ncols + d.nstruct);
+                maxNc = std::max(maxNc, 6 * d.ncols);
+                maxFs = std::max(maxFs, 6 * (d.ncols + d.nstruct));
+                anyChild = anyChild || d.nchild > 0;
+            }
+            if (!syrkAttr) {
+                CUDA_CHECK(cudaFuncSetAttribute(bigfront::k_bf_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shSyrk));
+                CUDA_CHECK(cudaFuncSetAttribute(bigfront::k_bf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shPanel));
+                syrkAttr = true;
+            }
+            if (anyChild) {
+                bigfront::k_bf_extend<<<dim3(maxFd, nBig), 256, 0, s>>>(bigSn, dSn.p, dChild.p, dRel.p, fronts.p);
+                nl++;
+            }
+            for (int p0 = 0; p0 < maxNc; p0 += bigfront::BF_PC) {
+                const int below = maxFs + 1 - p0;          // upper bound of the rows below any front's panel
+                bigfront::k_bf_panel<<<dim3(std::max(1, ceil_div(below, bigfront::BF_RS)), nBig), bigfront::BF_PT, shPanel, s>>>(
+                    bigSn, dSn.p, fronts.p, err.p, p0);
+                const int nT = ceil_div(below, bigfront::BF_T);
+                bigfront::k_bf_syrk<<<dim3(nT * (nT + 1) / 2, nBig), 128, shSyrk, s>>>(bigSn, dSn.p, fronts.p, p0);
+                nl += 2;
+            }
+        }
     }
-    size_t shb = sizeof(double) * (6 * (size_t)(sym.maxFdim + 1) + BS_PC * BS_TS);
+    size_t shb = sizeof(double) * (6 * (size_t)(maxSmallFdim + 1) + BS_PC * BS_TS);
     if (shb > 220 * 1024)
-        throw LsfmError(LSFM_ERR_ARG, "a Cholesky front of " + std::to_string(sym.maxFdim) +
+        throw LsfmError(LSFM_ERR_ARG, "a Cholesky front of " + std::to_string(maxSmallFdim) +
                                           " pose blocks exceeds the back-solve's shared-memory capacity (~4400 blocks)");
     if (shb > 48 * 1024)
-        CUDA_CHECK(cudaFuncSetAttribute(k_front_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
+        CUDA_CHECK(cudaFuncSetAttribute(k_front_backsolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
     for (int l = nLevels - 1; l >= 0; l--) {
-        int cnt = sym.levelPtr[l + 1] - sym.levelPtr[l];
-        if (cnt == 0) continue;
-        const int thr = (cnt <= ctx.num_sms) ? 512 : 256;
-        k_front_backsolve<<<cnt, thr, shb, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dStruct.p, fronts.p, xperm.p); nl++;
+        const int cnt = nSmall[l];
+        const int nBig = sym.levelPtr[l + 1] - sym.levelPtr[l] - cnt;
+        if (cnt > 0) {
+            const int thr = (cnt <= ctx.num_sms) ? 512 : 256;
+            k_front_backsolve<false><<<cnt, thr, shb, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dStruct.p, fronts.p, xperm.p);
+            nl++;
+        }
+        if (nBig > 0) {
+            const int *bigSn = dLevelSn.p + sym.levelPtr[l] + cnt;
+            int maxNc = 0;
+            for (int i = 0; i < nBig; i++) maxNc = std::max(maxNc, 6 * sym.sn[lvlList[sym.levelPtr[l] + cnt + i]].ncols);
+            bigfront::k_bf_back_gemv<<<dim3(ceil_div(maxNc, 8), nBig), 256, 0, s>>>(bigSn, dSn.p, dStruct.p, fronts.p, xperm.p);
+            const size_t shbig = sizeof(double) * ((size_t)maxNc + BS_PC * BS_TS);
+            k_front_backsolve<true><<<nBig, 512, shbig, s>>>(bigSn, dSn.p, dStruct.p, fronts.p, xperm.p);
+            nl += 2;
+        }
     }
     k_unpermute<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(J.d.p, J.dPosePre.p, K, J.totPose, dPerm.p, xperm.p); nl++;
     // the not-SPD flag is sticky in the context and checked once per API call (no sync here)

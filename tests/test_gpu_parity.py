@@ -78,13 +78,20 @@ def test_tree_88(gpu, oracle):
                                       ({"LSFM_SCHUR_DENSE": "1"}, ("37", "30")),
                                       ({"LSFM_SCHUR_DENSE": "1"}, ("300", "128")),
                                       ({"LSFM_SCHUR_V1": "1"}, ("37", "30")),
-                                      ({"LSFM_FORCE_GLOBAL_PANEL": "1"}, ("88", "64"))])
+                                      ({"LSFM_FORCE_GLOBAL_PANEL": "1"}, ("88", "64")),
+                                      ({"LSFM_BIGFRONT_MIN_FS": "96"}, ("300", "64")),
+                                      ({"LSFM_BIGFRONT_MIN_FS": "96"}, ("480", "48", "closed80")),
+                                      ({"LSFM_NO_BIGFRONT": "1"}, ("480", "48", "closed80"))])
 def test_tree_alternative_paths(gpu, oracle, env, size):
     # LSFM_FORCE_OVERFLOW: chunks that see "too many" distinct poses (forced: > 4) take the thread-per-block
     # paths of the Transform / pattern / Schur kernels.  LSFM_SCHUR_DENSE: the DMMA Schur kernel
     # (schur_dense.cuh; 300 maps reach the 512-thread instantiation with 12 dense poses per chunk).
     # LSFM_SCHUR_V1: the first, atomics-only Schur kernel.  LSFM_FORCE_GLOBAL_PANEL: the Cholesky fronts'
-    # global-memory panel (the path fronts taller than ~2100 rows take).  Read once per process.
+    # global-memory panel (the path fronts taller than ~2100 rows take).  LSFM_BIGFRONT_MIN_FS=96: fronts of
+    # 16 pose blocks or more take the multi-CTA path (chol_big.cuh: extend-add, panels, DMMA trailing update,
+    # split back-solve) -- on the open chain (LSFM-ND fronts, one panel) and on a scene with loop closures
+    # every 80 frames (LSFM-MD supernodes of several panels); LSFM_NO_BIGFRONT: the same scene with one CTA
+    # per front.  Read once per process.
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     e = dict(os.environ); e.update(env)

@@ -8,7 +8,11 @@ import ref_oracle as ro  # noqa: E402
 from util import assert_maps_match, state_rel_err  # noqa: E402
 
 n, fpf = int(sys.argv[1]), int(sys.argv[2])
-maps = synth.make_stereo_scene(n, feats_per_frame=fpf, seed=100 + n)
+if len(sys.argv) > 3 and sys.argv[3].startswith("closed"):      # loop closures every <k> frames: closed<k>
+    maps = synth.make_stereo_scene(n, feats_per_frame=fpf, seed=100 + n, revisit=0.1, lap=int(sys.argv[3][6:]),
+                                   max_depth=15.0, gate=True)
+else:
+    maps = synth.make_stereo_scene(n, feats_per_frame=fpf, seed=100 + n)
 ref, _, _ = ro.run_tree_stereo(maps)
 api.init(0)
 got = api.CLinearSFMImp().lmj_PF3D_Divide_ConquerStereo(maps)
