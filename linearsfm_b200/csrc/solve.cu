@@ -552,6 +552,24 @@ __global__ void k_front_rhs(const int *__restrict__ poseSn, const int *__restric
     fronts[d.frontOff + (size_t)(6 * poseLcol[p] + q) * ld + fs] = E[6 * (size_t)p + q];
 }
 
+// Dependency flags of the single-launch ("persistent") factor / back-solve kernels: one CTA per front,
+// fronts in assembly-tree level order, so every front a CTA waits for belongs to a CTA with a SMALLER block
+// index -- already finished or resident (the hardware hands out blocks in index order): no deadlock.  The
+// spin is bounded anyway (~2 s): on a timeout the error flag is raised instead of hanging the device.
+__device__ __forceinline__ void front_wait(const int *flag, int *errflag)
+{
+    const long long t0 = clock64();
+    while (*(volatile const int *)flag == 0) {
+        __nanosleep(100);
+        if (clock64() - t0 > (1ll << 32)) { atomicOr(errflag, 4); break; }
+    }
+}
+__device__ __forceinline__ void front_signal(int *flag)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicExch(flag, 1); }
+}
+
 // Factor a panel held in (shared or global) memory: P is [pc][ldp] column-major, rows 0..pc-1 hold the
 // diagonal block (lower triangle), rows pc..rows-1 everything below it.  6x6 diagonal blocks by one
 // thread in registers (factor + its inverse), row solves and the in-panel updates by the whole CTA.
@@ -654,12 +672,20 @@ __global__ void __launch_bounds__(512)
 k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
                const int *__restrict__ childIdx, const int *__restrict__ relIdx,
                double *__restrict__ fronts, int *__restrict__ errflag, int pcMax,
-               double *__restrict__ panelG, size_t panelStride)
+               double *__restrict__ panelG, size_t panelStride, int *__restrict__ done)
 {
     extern __shared__ double Psh[];               // [pc][ldp] column-major panel
     double *P = GP ? panelG + (size_t)blockIdx.x * panelStride : Psh;
     __shared__ double Li[36];                     // inverse of the current diagonal block's factor
-    const SnodeDesc d = sn[levelSn[blockIdx.x]];
+    const int sid = levelSn[blockIdx.x];
+    const SnodeDesc d = sn[sid];
+    if (done) {                                   // single-launch mode: wait for the children's fronts
+        if (threadIdx.x == 0) {
+            for (int ci = 0; ci < d.nchild; ci++) front_wait(done + childIdx[d.childOff + ci], errflag);
+            __threadfence();
+        }
+        __syncthreads();
+    }
     double *F = fronts + d.frontOff;
     const int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1, nc = 6 * d.ncols;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -692,9 +718,9 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
                     pr[j] = -1;
                     if (r < rows) {
                         pr[j] = (r == us) ? fs : 6 * rel[r / 6] + (r % 6);
-                        cv0[j] = src0[r];
+                        cv0[j] = __ldcg(src0 + r);
                         pv0[j] = dst0[pr[j]];
-                        if (has2 && r > cc) { cv1[j] = src1[r]; pv1[j] = dst1[pr[j]]; }
+                        if (has2 && r > cc) { cv1[j] = __ldcg(src1 + r); pv1[j] = dst1[pr[j]]; }
                     }
                 }
 #pragma unroll
@@ -761,6 +787,7 @@ k_front_factor(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn
         }
         __syncthreads();
     }
+    if (done) front_signal(done + sid);
 }
 
 // top-down: x_J = L11^-T (y_J - L21^T x_struct); xperm holds the solution in elimination order.
@@ -774,9 +801,15 @@ template <bool PRE>
 __global__ void __launch_bounds__(512)
 k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__ sn,
                   const int *__restrict__ structIdx, const double *__restrict__ fronts,
-                  double *__restrict__ xperm)
+                  double *__restrict__ xperm, int *__restrict__ done, int *__restrict__ errflag)
 {
-    const SnodeDesc d = sn[levelSn[blockIdx.x]];
+    // single-launch mode (done != nullptr): the list is walked from its END (parents first)
+    const int sid = done ? levelSn[gridDim.x - 1 - blockIdx.x] : levelSn[blockIdx.x];
+    const SnodeDesc d = sn[sid];
+    if (done) {
+        if (threadIdx.x == 0 && d.parent >= 0) { front_wait(done + d.parent, errflag); __threadfence(); }
+        __syncthreads();
+    }
     const double *F = fronts + d.frontOff;
     const int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1, nc = 6 * d.ncols, us = PRE ? 0 : 6 * d.nstruct;
     extern __shared__ double sh[];
@@ -785,7 +818,7 @@ k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__
     double *T = t + nc;         // [BS_PC][BS_PC] triangle of the current column block (column-major)
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     double *xj = xperm + 6 * (size_t)d.poseOff;
-    for (int i = tid; i < us; i += nt) xs[i] = xj[6 * structIdx[d.structOff + i / 6] + (i % 6)];
+    for (int i = tid; i < us; i += nt) xs[i] = __ldcg(xj + 6 * structIdx[d.structOff + i / 6] + (i % 6));
     if (PRE)
         for (int c = tid; c < nc; c += nt) t[c] = xj[6 * (size_t)d.first + c];
     __syncthreads();
@@ -857,6 +890,7 @@ k_front_backsolve(const int *__restrict__ levelSn, const SnodeDesc *__restrict__
         __syncthreads();
     }
     for (int c = tid; c < nc; c += nt) xj[6 * (size_t)d.first + c] = t[c];
+    if (done) front_signal(done + sid);
 }
 
 } // namespace
@@ -1184,7 +1218,22 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     const size_t shSyrk = sizeof(double) * 2 * bigfront::BF_PC * bigfront::BF_LDS;
     const size_t shPanel = sizeof(double) * bigfront::BF_PC * (bigfront::BF_PC + bigfront::BF_RS + 1);
     bool syrkAttr = false;
-    for (int l = 0; l < nLevels; l++) {
+    // No big front anywhere (sequential scenes: fronts <= ~200 rows): ONE launch for the whole assembly tree of
+    // every join of the batch instead of one per tree level -- a CTA per front in level order, children /
+    // parents awaited through flags (front_wait / front_signal).  LSFM_CHOL_LEVELS=1: per-level launches.
+    static const bool per_level = getenv("LSFM_CHOL_LEVELS") != nullptr;
+    int totSmall = 0;
+    for (int l = 0; l < nLevels; l++) totSmall += nSmall[l];
+    const bool oneLaunch = !per_level && !globalPanel && totSmall == ns && ns > 0;
+    DevBuf<int> doneF(oneLaunch ? 2 * (size_t)ns : 1, s);
+    if (oneLaunch) {
+        CUDA_CHECK(cudaMemsetAsync(doneF.p, 0, sizeof(int) * 2 * (size_t)ns, s));
+        const int thr = (ns <= 8 * ctx.num_sms) ? 512 : 256;
+        k_front_factor<false><<<ns, thr, shf, s>>>(dLevelSn.p, dSn.p, dChild.p, dRel.p, fronts.p, err.p, pcMax, nullptr, 0,
+                                                   doneF.p);
+        nl++;
+    }
+    for (int l = 0; l < nLevels && !oneLaunch; l++) {
         const int cnt = nSmall[l];
         const int nBig = sym.levelPtr[l + 1] - sym.levelPtr[l] - cnt;
         if (cnt > 0) {
@@ -1193,10 +1242,10 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             const int thr = (cnt <= ctx.num_sms) ? 512 : 256;
             if (globalPanel)
                 k_front_factor<true><<<cnt, thr, 0, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p, err.p,
-                                                        pcMax, panelG.p, panelStride);
+                                                        pcMax, panelG.p, panelStride, nullptr);
             else
                 k_front_factor<false><<<cnt, thr, shf, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dChild.p, dRel.p, fronts.p,
-                                                           err.p, pcMax, nullptr, 0);
+                                                           err.p, pcMax, nullptr, 0, nullptr);
             nl++;
         }
         if (nBig > 0) {
@@ -1235,12 +1284,18 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
                                           " pose blocks exceeds the back-solve's shared-memory capacity (~4400 blocks)");
     if (shb > 48 * 1024)
         CUDA_CHECK(cudaFuncSetAttribute(k_front_backsolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
-    for (int l = nLevels - 1; l >= 0; l--) {
+    if (oneLaunch) {
+        const int thr = (ns <= 8 * ctx.num_sms) ? 512 : 256;
+        k_front_backsolve<false><<<ns, thr, shb, s>>>(dLevelSn.p, dSn.p, dStruct.p, fronts.p, xperm.p, doneF.p + ns, err.p);
+        nl++;
+    }
+    for (int l = nLevels - 1; l >= 0 && !oneLaunch; l--) {
         const int cnt = nSmall[l];
         const int nBig = sym.levelPtr[l + 1] - sym.levelPtr[l] - cnt;
         if (cnt > 0) {
             const int thr = (cnt <= ctx.num_sms) ? 512 : 256;
-            k_front_backsolve<false><<<cnt, thr, shb, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dStruct.p, fronts.p, xperm.p);
+            k_front_backsolve<false><<<cnt, thr, shb, s>>>(dLevelSn.p + sym.levelPtr[l], dSn.p, dStruct.p, fronts.p, xperm.p,
+                                                           nullptr, err.p);
             nl++;
         }
         if (nBig > 0) {
@@ -1249,7 +1304,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             for (int i = 0; i < nBig; i++) maxNc = std::max(maxNc, 6 * sym.sn[lvlList[sym.levelPtr[l] + cnt + i]].ncols);
             bigfront::k_bf_back_gemv<<<dim3(ceil_div(maxNc, 8), nBig), 256, 0, s>>>(bigSn, dSn.p, dStruct.p, fronts.p, xperm.p);
             const size_t shbig = sizeof(double) * ((size_t)maxNc + BS_PC * BS_TS);
-            k_front_backsolve<true><<<nBig, 512, shbig, s>>>(bigSn, dSn.p, dStruct.p, fronts.p, xperm.p);
+            k_front_backsolve<true><<<nBig, 512, shbig, s>>>(bigSn, dSn.p, dStruct.p, fronts.p, xperm.p, nullptr, err.p);
             nl += 2;
         }
     }

@@ -1,8 +1,9 @@
 """Stress run: synthetic NC3500-shape scene scaled up (BASELINE.json configs[4]: 50k local maps).
 The reference cannot run this size (int overflow / O(m^2) mask, LinearSFMImp.cpp:2131).  The scene is the
-well-conditioned variant (loop closures every 500 frames, outlier-gated landmarks): a 50k-frame OPEN chain
-is numerically hopeless for any FP64 solver.  Two solves: results must be bit-identical.
-Usage: python tools/stress.py N landmarks_per_frame"""
+well-conditioned variant (the trajectory closes on itself: four laps by default, outlier-gated landmarks):
+a 50k-frame OPEN chain is numerically hopeless for any FP64 solver.  Two solves: results must be
+bit-identical.
+Usage: python tools/stress.py N landmarks_per_frame [lap_frames]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,7 +11,8 @@ import numpy as np
 from linearsfm_b200 import api, synth
 N = int(sys.argv[1]); fpf = int(sys.argv[2])
 t = time.time()
-maps, truth = synth.make_stereo_scene(N, feats_per_frame=fpf, return_truth=True, revisit=0.1, lap=500, max_depth=15.0, gate=True)
+lap = int(sys.argv[3]) if len(sys.argv) > 3 else max(500, N // 4)
+maps, truth = synth.make_stereo_scene(N, feats_per_frame=fpf, return_truth=True, revisit=0.1, lap=lap, max_depth=15.0, gate=True)
 print("gen %.1fs, %d landmarks rows" % (time.time() - t, sum(m.n for m in maps)), flush=True)
 api.init(0)
 t = time.time(); tree = api.Tree(maps); print("upload %.2fs" % (time.time() - t), flush=True)
