@@ -325,6 +325,7 @@ def main():
     # ---- N > 1: the sharded result against a single-GPU solve of the same leaves (rank 0, untimed) ----
     verify = None
     if world > 1:
+        be.tree.reset()
         root = lsd.run_sharded(be, nmaps, rank, world, dev)
         barrier()
         if rank == 0:

@@ -225,6 +225,9 @@ struct Context {
         CUDA_CHECK(cudaStreamSynchronize(stream));
         if (h) {
             CUDA_CHECK(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
+            if (h & 4)
+                throw LsfmError(LSFM_ERR_CUDA, "Cholesky: a front waited for more than 2 s for its children (single-launch "
+                                               "factorisation); rerun with LSFM_CHOL_LEVELS=1");
             throw LsfmError(LSFM_ERR_NOT_SPD, "reduced camera system is not positive definite");
         }
     }
