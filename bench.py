@@ -339,7 +339,11 @@ def main():
             scale = float(np.max(np.abs(st_1)))
             diff = float(np.max(np.abs(st_s - st_1)) / scale) if ints_equal else None
             verify = {"against": "single-GPU solve of the same leaves on rank 0 (untimed)", "ints_equal": ints_equal,
-                      "state_max_rel_diff": diff, "bit_identical": bool(ints_equal and np.array_equal(st_s, st_1))}
+                      "state_max_rel_diff": diff, "bit_identical": bool(ints_equal and np.array_equal(st_s, st_1)),
+                      "note": "sharding changes which joins share a launch, hence the order of some fixed-order sums; "
+                              "on the default open 3499-frame chain last-bit differences are amplified to ~1e-3 "
+                              "(the reference's own result moves by 1.6e-3 under 1e-15 input noise there, "
+                              "DESIGN.md section 3); --scene closed is the well-conditioned scene"}
         barrier()
 
     cpu = None
