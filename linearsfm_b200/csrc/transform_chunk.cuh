@@ -283,9 +283,8 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     // ---------------- batches: one thread per W block ----------------
     // phase A for one block; FAST: chunk-local pose slots (lists, Jacobians from shared memory, W
     // through the warp's private part of the Wr tile), else global Jacobians / atomics
-    auto phase_a = [&](auto fast_tag, const int j, int *lc, const unsigned act) {
+    auto phase_a = [&](auto fast_tag, const int j, const int p, int *lc, const unsigned act) {
         constexpr bool FAST = decltype(fast_tag)::value;
-        const int p = M.photo[j];
         int fb;
         {
             int lo = 0, hi = nfeat;             // feature fb with wptr[fb] <= j < wptr[fb+1]
@@ -370,8 +369,11 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     };
 
     int bt = 0;
+    int pNext = (w0 + tid < w1) ? M.photo[w0 + tid] : 0;            // the block's pose, one batch ahead
     for (int jb = w0; jb < w1; jb += TC_BATCH, bt++) {
         const int j = jb + tid;
+        const int pCur = pNext;
+        if (j + TC_BATCH < w1) pNext = M.photo[j + TC_BATCH];
         int *lc = lcnt + (bt & 1) * 128;
         if (fast) {
             // the warp's 32 blocks = one contiguous 4.6 KB span: coalesced 16-byte async copies into
@@ -388,17 +390,38 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
                 const char *nx = reinterpret_cast<const char *>(Wg + 18 * (size_t)(j + TC_BATCH));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128));
-                if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(M.photo + j + TC_BATCH));
             }
             cp_async_wait_all();
             __syncwarp();
             const unsigned act = __ballot_sync(0xffffffffu, j < w1);
-            if (j < w1) phase_a(std::true_type(), j, lc, act);
+            if (j < w1) phase_a(std::true_type(), j, pCur, lc, act);
         } else if (j < w1) {
-            phase_a(std::false_type(), j, lc, 0u);
+            phase_a(std::false_type(), j, pCur, lc, 0u);
         }
         __syncthreads();
         lcnt[((bt & 1) ^ 1) * 128 + tid] = 0;                       // the next batch's counters
+        // W'(pos,f) of the batch's features is a read-modify-write of global memory (the rows were
+        // initialised by the prologue / earlier batches of THIS CTA): issue this thread's first two loads
+        // now, the pose sums below hide their latency
+        const int jl = min(jb + TC_BATCH, w1) - 1;
+        int fLo, nfb;
+        {
+            int lo = 0, hi = nfeat;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= jb) lo = mid; else hi = mid; }
+            fLo = lo;
+            hi = nfeat;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= jl) lo = mid; else hi = mid; }
+            nfb = lo - fLo + 1;
+        }
+        double oldw[2] = {0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int e = tid + u * TC_THREADS;
+            if (e < nfb * 18) {
+                const int fl = e / 18, el = e - 18 * fl;
+                oldw[u] = O.W[18 * (size_t)optr[fLo + fl] + el];
+            }
+        }
         // pose sums (thread owns (local pose, element) pairs for the whole chunk)
 #pragma unroll
         for (int u = 0; u < TC_ACC; u++) {
@@ -423,20 +446,15 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
         }
         // W'(pos,f) += the feature's wadd rows of this batch
         {
-            const int jl = min(jb + TC_BATCH, w1) - 1;
-            int lo = 0, hi = nfeat;
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= jb) lo = mid; else hi = mid; }
-            const int fLo = lo;
-            lo = fLo; hi = nfeat;
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= jl) lo = mid; else hi = mid; }
-            const int nfb = lo - fLo + 1;
-            for (int e = tid; e < nfb * 18; e += TC_THREADS) {
+            int u = 0;
+            for (int e = tid; e < nfb * 18; e += TC_THREADS, u++) {
                 const int fl = e / 18, el = e - 18 * fl;
                 const int fx = fLo + fl;
                 const int j0 = max(wptr[fx], jb) - jb, j1 = min(wptr[fx + 1], jl + 1) - jb;
                 double s = 0.0;
                 for (int b = j0; b < j1; b++) s += WAt[b * TC_LD + el];
-                O.W[18 * (size_t)optr[fx] + el] += s;
+                double *dst = O.W + 18 * (size_t)optr[fx] + el;
+                *dst = (u == 0 ? oldw[0] : u == 1 ? oldw[1] : *dst) + s;
             }
         }
         __syncthreads();
