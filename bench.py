@@ -346,6 +346,22 @@ def main():
                               "DESIGN.md section 3); --scene closed is the well-conditioned scene"}
         barrier()
 
+    # ---- the monocular configs of BASELINE.json (RS90_C / RS468_C shapes), host buffers in and out ----
+    mono = None
+    if world == 1 and args.scene == "default":
+        mono = {}
+        for tag, n in (("rs90_shape_88_maps", 88), ("rs468_shape_466_maps", 466)):
+            mm = synth.make_mono_scene(n, feats_per_frame=40, style="aerial", seed=n + 2)   # seeds 90 / 468 as in tests/test_gpu_mono.py
+            api.run_mono(mm)                                   # warm-up
+            ts = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0m = time.perf_counter()
+                api.run_mono(mm)
+                ts.append(time.perf_counter() - t0m)
+            mono[tag] = {"value": min(ts), "unit": "s",
+                         "note": "lsfm_run_mono through host buffers (H2D + merge tree + D2H), best of 3"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -378,6 +394,8 @@ def main():
             line["stages"] = stages
         if cpu:
             line["cpu_baseline"] = cpu
+        if mono:
+            line["mono_configs"] = mono
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if dist is not None:
         dist.barrier()
