@@ -91,7 +91,7 @@ k_bf_extend(const int *__restrict__ bigSn, const SnodeDesc *__restrict__ sn,
 constexpr int BF_PT = 256;
 __global__ void __launch_bounds__(BF_PT)
 k_bf_panel(const int *__restrict__ bigSn, const SnodeDesc *__restrict__ sn, double *__restrict__ fronts,
-           int *__restrict__ errflag, int p0)
+           int *__restrict__ errflag, int p0, double *__restrict__ diagOut)
 {
     const SnodeDesc d = sn[bigSn[blockIdx.y]];
     const int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1, nc = 6 * d.ncols;
@@ -114,22 +114,38 @@ k_bf_panel(const int *__restrict__ bigSn, const SnodeDesc *__restrict__ sn, doub
     }
     __syncthreads();
     factor_panel(P, ldp, rows, pc, Li, errflag, tid, BF_PT);
+    // The factored diagonal block must NOT go back into the front here: CTAs of this launch that start later
+    // still have to read the unfactored block.  CTA 0 parks it in diagOut[front]; k_bf_syrk (next launch)
+    // copies it into place.
+    double *dg = diagOut + (size_t)blockIdx.y * (BF_PC * BF_PC);
     for (int t = tid; t < pc * rows; t += BF_PT) {
         const int q = t / rows, rr = t - q * rows;
-        if (rr < q || (rr < pc && blockIdx.x > 0)) continue;
-        const int gr = rr < pc ? p0 + rr : below0 + slab0 + (rr - pc);
-        F[(size_t)(p0 + q) * ld + gr] = P[q * ldp + rr];
+        if (rr < q) continue;
+        if (rr < pc) {
+            if (blockIdx.x == 0) dg[q * BF_PC + rr] = P[q * ldp + rr];
+            continue;
+        }
+        F[(size_t)(p0 + q) * ld + below0 + slab0 + (rr - pc)] = P[q * ldp + rr];
     }
 }
 
 // ---- trailing update on the FP64 tensor cores; grid (lower-triangle tile, front), 128 threads ----
 __global__ void __launch_bounds__(128)
-k_bf_syrk(const int *__restrict__ bigSn, const SnodeDesc *__restrict__ sn, double *__restrict__ fronts, int p0)
+k_bf_syrk(const int *__restrict__ bigSn, const SnodeDesc *__restrict__ sn, double *__restrict__ fronts, int p0,
+          const double *__restrict__ diagIn)
 {
     const SnodeDesc d = sn[bigSn[blockIdx.y]];
     const int fs = 6 * (d.ncols + d.nstruct), ld = fs + 1, nc = 6 * d.ncols;
     if (p0 >= nc) return;
     const int pc = min(BF_PC, nc - p0);
+    if (blockIdx.x == 0) {                        // the panel's factored diagonal block, parked by k_bf_panel
+        const double *dg = diagIn + (size_t)blockIdx.y * (BF_PC * BF_PC);
+        double *Fd = fronts + d.frontOff;
+        for (int t = threadIdx.x; t < pc * pc; t += 128) {
+            const int q = t / pc, rr = t - q * pc;
+            if (rr >= q) Fd[(size_t)(p0 + q) * ld + p0 + rr] = dg[q * BF_PC + rr];
+        }
+    }
     const int t0 = p0 + pc;                       // first trailing row / column
     const int nrows = fs + 1 - t0;                // trailing rows incl. the right-hand-side row
     const int nT = (nrows + BF_T - 1) / BF_T;

@@ -153,6 +153,10 @@ template <class T> struct DevBuf {
 struct MapHandle {
     DMap d;
     std::shared_ptr<Arena> arena;
+    // Feature chunks of the chunk kernels (pattern / Schur / Transform W-V pass): ascending start indices
+    // ending with n.  nullptr = 128 consecutive features per chunk.  Set by the join whose pattern stage had
+    // to split chunks that saw more than 30 distinct poses (loop closures, dense overlap); Transforms keep it.
+    std::shared_ptr<const std::vector<int>> chunkStarts;
 };
 
 // Per-stage accounting (kernel launches, device time, algorithmic bytes / flops).

@@ -544,7 +544,23 @@ std::vector<MapHandle> join_stereo_batch(Context &ctx, const std::vector<MapHand
         KERNEL_CHECK();
         ctx.end(valueBytes, 0.0, 2);
     };
+    // feature chunks: End's features keep their indices in the joint map (Cur's new ones follow), so End's
+    // chunk boundaries -- narrowed where chunks saw too many poses -- seed the joint map's
+    std::vector<std::shared_ptr<const std::vector<int>>> seed(K), chunksOut;
+    for (int k = 0; k < K; k++) {
+        if (!End[k].chunkStarts) continue;
+        const std::vector<int> &es = *End[k].chunkStarts;
+        const int nE = E.h[k].n, nJ = J.h[k].n;
+        if (es.empty() || es.front() != 0 || es.back() != nE) continue;
+        std::vector<int> st(es.begin(), es.end() - 1);
+        for (int f0 = nE; f0 < nJ; f0 += 128) st.push_back(f0);
+        st.push_back(nJ);
+        seed[k] = std::make_shared<const std::vector<int>>(std::move(st));
+    }
+    ex.chunkSeed = &seed;
+    ex.chunksOut = &chunksOut;
     solve_stereo_batch(ctx, J, eP.p, eF.p, nullptr, nullptr, &ex);
+    for (int k = 0; k < K && k < (int)chunksOut.size(); k++) out[k].chunkStarts = chunksOut[k];
 
     if (ctx.want_objective) {
         ctx.begin("objective");

@@ -1,6 +1,7 @@
 // Host-side interfaces of the batched ("segmented") device operators of the hot path.
 // Each operator processes EVERY map / join of one merge-tree level in a handful of launches.
 #pragma once
+#include <memory>
 #include "device.h"
 #include <vector>
 #include <functional>
@@ -66,6 +67,10 @@ struct SolveExtra {
     std::function<void()> after_pattern;
     const double *xhat = nullptr;
     const int *split = nullptr;
+    // feature chunks: optional per-join seed (start indices ending with n, nullptr entries = default) and the
+    // lists the pattern stage ended up with (one per join; nullptr when every chunk is the default width)
+    const std::vector<std::shared_ptr<const std::vector<int>>> *chunkSeed = nullptr;
+    std::vector<std::shared_ptr<const std::vector<int>>> *chunksOut = nullptr;
 };
 void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const double *eF,
                         SolveDebug *dbg, const MonoGauge *gauge = nullptr, const SolveExtra *ex = nullptr);

@@ -954,25 +954,45 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     // feature chunks shared by the pattern and the Schur kernels
     std::vector<FeatChunk> chunks;
     int maxWords = 1;
+    for (int k = 0; k < K; k++) maxWords = std::max(maxWords, (J.h[k].m + 31) / 32);
+    // chunk boundaries per join: start indices ending with n (seeded by the caller or SCH_FCHUNK wide)
+    std::vector<std::vector<int>> starts(K);
+    bool customChunks = false;
     for (int k = 0; k < K; k++) {
-        maxWords = std::max(maxWords, (J.h[k].m + 31) / 32);
-        for (int f0 = 0; f0 < J.h[k].n; f0 += SCH_FCHUNK)
-            chunks.push_back({k, f0, std::min(J.h[k].n, f0 + SCH_FCHUNK)});
+        const int n = J.h[k].n;
+        const std::vector<int> *seed = (ex && ex->chunkSeed && (*ex->chunkSeed)[k]) ? (*ex->chunkSeed)[k].get() : nullptr;
+        if (seed && !seed->empty() && seed->front() == 0 && seed->back() == n) { starts[k] = *seed; customChunks = true; }
+        else {
+            for (int f0 = 0; f0 < n; f0 += SCH_FCHUNK) starts[k].push_back(f0);
+            starts[k].push_back(n);
+        }
     }
-    const int nChunks = (int)chunks.size();
-    DevBuf<FeatChunk> dChunks(nChunks, s);
-    dChunks.upload(chunks);
+    int nChunks = 0;
+    DevBuf<FeatChunk> dChunks;
     int maxNposes = 1 << 30;             // max distinct poses of any chunk (measured by k_pat_chunk)
     DevBuf<int> dMaxNp(4, s);            // [0] max #poses per chunk, [2..3] pair-feature count (stage timing only)
-    DevBuf<int> chunkInfo((size_t)CHUNK_INFO_INTS * std::max(nChunks, 1), s), blkInfo((size_t)std::max(J.totW, 1), s);
+    DevBuf<int> chunkInfo, blkInfo((size_t)std::max(J.totW, 1), s);
     // per chunk: pose bitmap + popcount prefix (the E gather's index) and the chunks of every join
     const int bitsStride = maxWords;
-    DevBuf<unsigned> patBits(2 * (size_t)bitsStride * std::max(nChunks, 1), s);
-    std::vector<int> chunkPre(K + 1, 0);
-    for (const FeatChunk &c : chunks) chunkPre[c.k + 1]++;
-    for (int k = 0; k < K; k++) chunkPre[k + 1] += chunkPre[k];
+    DevBuf<unsigned> patBits;
+    std::vector<int> chunkPre;
     DevBuf<int> dChunkPre(K + 1, s);
-    dChunkPre.upload(chunkPre);
+    auto build_chunks = [&]() {
+        chunks.clear();
+        chunkPre.assign(K + 1, 0);
+        for (int k = 0; k < K; k++) {
+            for (size_t i = 0; i + 1 < starts[k].size(); i++)
+                if (starts[k][i + 1] > starts[k][i]) chunks.push_back({k, starts[k][i], starts[k][i + 1]});
+            chunkPre[k + 1] = (int)chunks.size();
+        }
+        nChunks = (int)chunks.size();
+        dChunks.alloc(nChunks, s);
+        dChunks.upload(chunks);
+        chunkInfo.alloc((size_t)CHUNK_INFO_INTS * std::max(nChunks, 1), s);
+        patBits.alloc(2 * (size_t)bitsStride * std::max(nChunks, 1), s);
+        dChunkPre.upload(chunkPre);
+    };
+    build_chunks();
     // test hook: LSFM_FORCE_OVERFLOW=1 sends every chunk with > 4 poses down the overflow paths
     static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
     const int pat_cmax_used = force_ovf ? 4 : PAT_CMAX;
@@ -993,7 +1013,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     dBmOff.upload(bmOff);
     DevBuf<unsigned> bm((size_t)std::max(bmOff[K], 1), s);
     bm.zero();
-    if (nChunks > 0) {
+    auto pattern_chunk_pass = [&]() {
+        if (nChunks == 0) return;
         size_t shb = sizeof(int) * (2 * (size_t)maxWords + 16 + PAT_CMAX + 1 + 4 + 32);
         if (shb > 48 * 1024)
             CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
@@ -1001,7 +1022,8 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
         k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, bm.p, dBmOff.p, dMaxNp.p, pat_cmax_used,
                                                       chunkInfo.p, blkInfo.p, J.dWPre.p, patBits.p, bitsStride,
                                                       ctx.timing ? (unsigned long long *)(dMaxNp.p + 2) : nullptr); nl++;
-    }
+    };
+    pattern_chunk_pass();
     if (gauge) {   // mono: the zero pose has no block at all after the join; keep every diagonal
         k_pat_diag<<<ceil_div(J.totPose, TB), TB, 0, s>>>(J.d.p, J.dPosePre.p, K, J.totPose, bm.p, dBmOff.p); nl++;
     }
@@ -1029,6 +1051,57 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     ctx.idle_begin();
     nuis = hRowPtr[J.totPose];
     if (nChunks > 0) maxNposes = *hMaxNp;
+    // Chunks that see more than PAT_CMAX distinct poses take the slow thread-per-block paths (with FP64
+    // atomics) in the pattern, Schur and Transform kernels.  Split THOSE chunks in four (by features, down to 8
+    // features) and repeat the chunk pass -- the pose-pair bitmap only gains bits it already has, chunkInfo /
+    // blkInfo / patBits are rewritten.  The limit is one below the kernels' capacity: the Transform of the
+    // joined map adds one pose (the new origin) to every feature.  What still overflows at 8 features (a
+    // landmark seen by more than 30 poses) stays on the slow path.
+    static const bool no_split = getenv("LSFM_NO_CHUNK_SPLIT") != nullptr;
+    constexpr int SPLIT_LIMIT = PAT_CMAX - 1;
+    for (int round = 0; round < 3 && nChunks > 0 && maxNposes > SPLIT_LIMIT && !force_ovf && !no_split; round++) {
+        std::vector<int> np((size_t)nChunks);
+        CUDA_CHECK(cudaMemcpy2DAsync(np.data(), sizeof(int), chunkInfo.p + 31, sizeof(int) * CHUNK_INFO_INTS, sizeof(int),
+                                     (size_t)nChunks, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        bool any = false;
+        std::vector<std::vector<int>> ns(K);
+        for (int c = 0; c < nChunks; c++) {
+            const FeatChunk &ch = chunks[c];
+            const int w = ch.f1 - ch.f0;
+            if (np[c] > SPLIT_LIMIT && w > 8) {
+                const int part = std::max(8, (w + 3) / 4);
+                for (int f = ch.f0; f < ch.f1; f += part) ns[ch.k].push_back(f);
+                any = true;
+            } else ns[ch.k].push_back(ch.f0);
+        }
+        if (!any) break;
+        for (int k = 0; k < K; k++) { ns[k].push_back(J.h[k].n); starts[k].swap(ns[k]); }
+        customChunks = true;
+        build_chunks();
+        pattern_chunk_pass();
+        CUDA_CHECK(cudaMemcpyAsync(hMaxNp, dMaxNp.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        maxNposes = *hMaxNp;
+    }
+    if (getenv("LSFM_DEBUG") && nChunks > 0 && maxNposes > PAT_CMAX) {
+        std::vector<int> np((size_t)nChunks);
+        CUDA_CHECK(cudaMemcpy2DAsync(np.data(), sizeof(int), chunkInfo.p + 31, sizeof(int) * CHUNK_INFO_INTS, sizeof(int),
+                                     (size_t)nChunks, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        int nov = 0, f8 = 0;
+        for (int c = 0; c < nChunks; c++)
+            if (np[c] > PAT_CMAX) { nov++; f8 += (chunks[c].f1 - chunks[c].f0 <= 8); }
+        fprintf(stderr, "    [chunks] K=%d nChunks=%d maxNposes=%d: %d chunks stay on the slow path (%d of them <= 8 features)\n",
+                K, nChunks, maxNposes, nov, f8);
+    }
+    if (ex && ex->chunksOut) {
+        ex->chunksOut->assign(K, nullptr);
+        if (customChunks)
+            for (int k = 0; k < K; k++)
+                if ((int)starts[k].size() != (J.h[k].n + SCH_FCHUNK - 1) / SCH_FCHUNK + 1)
+                    (*ex->chunksOut)[k] = std::make_shared<const std::vector<int>>(starts[k]);
+    }
     // FP64 work of the Schur stage: 216 flop per (pose pair, feature) product, 108 per block for W V^-1,
     // 36 per block for the reduced right-hand side
     const double schurFlops = 216.0 * (double)(((unsigned long long)(unsigned)hMaxNp[3] << 32) | (unsigned)hMaxNp[2]) +
@@ -1218,6 +1291,9 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     const size_t shSyrk = sizeof(double) * 2 * bigfront::BF_PC * bigfront::BF_LDS;
     const size_t shPanel = sizeof(double) * bigfront::BF_PC * (bigfront::BF_PC + bigfront::BF_RS + 1);
     bool syrkAttr = false;
+    int maxBig = 0;
+    for (int l = 0; l < nLevels; l++) maxBig = std::max(maxBig, sym.levelPtr[l + 1] - sym.levelPtr[l] - nSmall[l]);
+    DevBuf<double> diagScratch((size_t)std::max(maxBig, 1) * bigfront::BF_PC * bigfront::BF_PC, s);
     // No big front anywhere (sequential scenes: fronts <= ~200 rows): ONE launch for the whole assembly tree of
     // every join of the batch instead of one per tree level -- a CTA per front in level order, children /
     // parents awaited through flags (front_wait / front_signal).  LSFM_CHOL_LEVELS=1: per-level launches.
@@ -1271,9 +1347,9 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             for (int p0 = 0; p0 < maxNc; p0 += bigfront::BF_PC) {
                 const int below = maxFs + 1 - p0;          // upper bound of the rows below any front's panel
                 bigfront::k_bf_panel<<<dim3(std::max(1, ceil_div(below, bigfront::BF_RS)), nBig), bigfront::BF_PT, shPanel, s>>>(
-                    bigSn, dSn.p, fronts.p, err.p, p0);
+                    bigSn, dSn.p, fronts.p, err.p, p0, diagScratch.p);
                 const int nT = ceil_div(below, bigfront::BF_T);
-                bigfront::k_bf_syrk<<<dim3(nT * (nT + 1) / 2, nBig), 128, shSyrk, s>>>(bigSn, dSn.p, fronts.p, p0);
+                bigfront::k_bf_syrk<<<dim3(nT * (nT + 1) / 2, nBig), 128, shSyrk, s>>>(bigSn, dSn.p, fronts.p, p0, diagScratch.p);
                 nl += 2;
             }
         }

@@ -636,8 +636,16 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
     int maxWords = 1;
     for (int k = 0; k < K; k++) {
         maxWords = std::max(maxWords, (A.h[k].m + 31) / 32);
-        for (int f0 = 0; f0 < A.h[k].n; f0 += tfc::TC_FCH)
-            chunks.push_back({k, f0, std::min(A.h[k].n, f0 + tfc::TC_FCH)});
+        // the join that produced the map may have narrowed some chunks (> 30 poses); the features are the same
+        const std::vector<int> *cs = in[k].chunkStarts.get();
+        if (cs && !cs->empty() && cs->front() == 0 && cs->back() == A.h[k].n) {
+            for (size_t i = 0; i + 1 < cs->size(); i++)
+                if ((*cs)[i + 1] > (*cs)[i]) chunks.push_back({k, (*cs)[i], (*cs)[i + 1]});
+            out[k].chunkStarts = in[k].chunkStarts;
+        } else {
+            for (int f0 = 0; f0 < A.h[k].n; f0 += tfc::TC_FCH)
+                chunks.push_back({k, f0, std::min(A.h[k].n, f0 + tfc::TC_FCH)});
+        }
         chunkPre[k + 1] = (int)chunks.size();
     }
     const int nChunks = (int)chunks.size();
