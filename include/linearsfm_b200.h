@@ -168,6 +168,14 @@ int lsfm_load_localmap_mono(const char *path, lsfm_map *out);
 int lsfm_save_localmap(const lsfm_map *m, const char *path, int mono);
 int lsfm_save_outputs(const lsfm_map *m, const char *state_path, const char *pose_path,
                       const char *feature_path);
+/* Binary cache of parsed input maps: the reference re-parses every localmap_<i>.txt with one
+ * fscanf per number on each run (LinearSFMImp.cpp:3062-3128, 6678-6750); lsfm_save_cache writes `num` maps as raw
+ * arrays into ONE file, lsfm_load_cache reads them back bit for bit (*maps_out: calloc'd array of `*num_out`
+ * maps whose arrays are malloc'd; release with lsfm_free_cache).  No reference interface is replaced.
+ * CLI: -cache <file> (used when present and matching -num / -type, otherwise written after the text parse). */
+int lsfm_save_cache(const char *file, const lsfm_map *maps, int num, int mono);
+int lsfm_load_cache(const char *file, lsfm_map **maps_out, int *num_out, int *mono_out);
+void lsfm_free_cache(lsfm_map *maps, int num);
 /* CLinearSFMImp::run(argc, argv) (LinearSFMImp.cpp:7972-8106): same flags
  *   -path <dir> -num <N> -type {Monocular|Stereo} [-p <pose>] [-f <feature>] [-st <state>] [-help] */
 int lsfm_cli_main(int argc, char **argv);

@@ -41,7 +41,7 @@ EXPORTS = [
     "lsfm_tree_free", "lsfm_tree_last_solve_ms", "lsfm_tree_adopt_result", "lsfm_tree_append_maps",
     "lsfm_tree_reset", "lsfm_map_device_bytes", "lsfm_tree_export_device", "lsfm_tree_append_device",
     "lsfm_load_localmap_stereo", "lsfm_save_outputs", "lsfm_cli_main", "lsfm_build_localmaps_stereo", "lsfm_save_localmap",
-    "lsfm_pcg_block", "lsfm_solve_mono",
+    "lsfm_pcg_block", "lsfm_solve_mono", "lsfm_save_cache", "lsfm_load_cache", "lsfm_free_cache",
 ]
 
 _lib = None
@@ -62,6 +62,10 @@ def lib():
         L.lsfm_stats_reset.restype = None
         L.lsfm_tree_free.restype = None
         L.lsfm_tree_free.argtypes = [C.c_void_p]
+        L.lsfm_free_cache.restype = None
+        L.lsfm_free_cache.argtypes = [C.POINTER(LsfmMap), C.c_int]
+        L.lsfm_load_cache.argtypes = [C.c_char_p, C.POINTER(C.POINTER(LsfmMap)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.lsfm_save_cache.argtypes = [C.c_char_p, C.POINTER(LsfmMap), C.c_int, C.c_int]
         L.lsfm_tree_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.lsfm_tree_result_count.argtypes = [C.c_void_p]
         L.lsfm_tree_result_shape.argtypes = [C.c_void_p, C.c_int, C.POINTER(LsfmMap)]

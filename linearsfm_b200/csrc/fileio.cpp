@@ -251,9 +251,102 @@ int lsfm_save_outputs(const lsfm_map *M, const char *st, const char *pose, const
     return LSFM_OK;
 }
 
+// ---- binary input cache ------------------------------------------------------
+// The reference parses 3499 text files with one fscanf per number on every run (LinearSFMImp.cpp:3062-3128).
+// The cache is the same maps as raw arrays in ONE file: header {magic, version, num, mono}, then per map the
+// 12 header ints and the ten arrays of struct lsfm_map in declaration order.  Native endianness and sizes.
+static const char CACHE_MAGIC[8] = {'L', 'S', 'F', 'M', 'B', 'C', '0', '1'};
+
+int lsfm_save_cache(const char *file, const lsfm_map *maps, int num, int mono)
+{
+    FILE *f = fopen(file, "wb");
+    if (!f) { lsfm_set_error(std::string("cannot write ") + file); return LSFM_ERR_IO; }
+    bool ok = fwrite(CACHE_MAGIC, 1, 8, f) == 8;
+    int hdr[2] = {num, mono ? 1 : 0};
+    ok = ok && fwrite(hdr, sizeof(int), 2, f) == 2;
+    auto put = [&](const void *p, size_t bytes) { if (ok && bytes) ok = fwrite(p, 1, bytes, f) == bytes; };
+    for (int i = 0; i < num && ok; i++) {
+        const lsfm_map &M = maps[i];
+        int h[12] = {M.Ref, M.FRef, M.m, M.n, M.nU, M.nW, M.r, M.ScaP, M.Fix, M.Sign, M.FScaP, M.FFix};
+        put(h, sizeof(h));
+        put(M.stno, sizeof(int) * (size_t)M.r);
+        put(M.stVal, sizeof(double) * (size_t)M.r);
+        put(M.U, sizeof(double) * 36 * (size_t)M.nU);
+        put(M.Ui, sizeof(int) * (size_t)M.nU);
+        put(M.Uj, sizeof(int) * (size_t)M.nU);
+        put(M.W, sizeof(double) * 18 * (size_t)M.nW);
+        put(M.photo, sizeof(int) * (size_t)M.nW);
+        put(M.feature, sizeof(int) * (size_t)M.nW);
+        put(M.V, sizeof(double) * 9 * (size_t)M.n);
+        put(M.FBlock, sizeof(int) * (size_t)M.n);
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { lsfm_set_error(std::string("write error on ") + file); return LSFM_ERR_IO; }
+    return LSFM_OK;
+}
+
+int lsfm_load_cache(const char *file, lsfm_map **maps_out, int *num_out, int *mono_out)
+{
+    if (!maps_out || !num_out) { lsfm_set_error("load_cache: null output"); return LSFM_ERR_ARG; }
+    *maps_out = nullptr; *num_out = 0;
+    FILE *f = fopen(file, "rb");
+    if (!f) { lsfm_set_error(std::string("cannot open ") + file); return LSFM_ERR_IO; }
+    char magic[8];
+    int hdr[2] = {0, 0};
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, CACHE_MAGIC, 8) != 0 || fread(hdr, sizeof(int), 2, f) != 2 ||
+        hdr[0] < 0) {
+        fclose(f);
+        lsfm_set_error(std::string(file) + ": not a LinearSFM map cache");
+        return LSFM_ERR_FORMAT;
+    }
+    const int num = hdr[0];
+    lsfm_map *maps = (lsfm_map *)calloc((size_t)std::max(num, 1), sizeof(lsfm_map));
+    bool ok = maps != nullptr;
+    auto get = [&](void **dst, size_t bytes) {
+        if (!ok) return;
+        *dst = malloc(bytes ? bytes : 1);
+        if (!*dst) { ok = false; return; }
+        if (bytes && fread(*dst, 1, bytes, f) != bytes) ok = false;
+    };
+    for (int i = 0; i < num && ok; i++) {
+        lsfm_map &M = maps[i];
+        int h[12];
+        if (fread(h, sizeof(int), 12, f) != 12) { ok = false; break; }
+        M.Ref = h[0]; M.FRef = h[1]; M.m = h[2]; M.n = h[3]; M.nU = h[4]; M.nW = h[5]; M.r = h[6];
+        M.ScaP = h[7]; M.Fix = h[8]; M.Sign = h[9]; M.FScaP = h[10]; M.FFix = h[11];
+        if (M.m < 0 || M.n < 0 || M.nU < 0 || M.nW < 0 || M.r != 6 * M.m + 3 * M.n) { ok = false; break; }
+        get((void **)&M.stno, sizeof(int) * (size_t)M.r);
+        get((void **)&M.stVal, sizeof(double) * (size_t)M.r);
+        get((void **)&M.U, sizeof(double) * 36 * (size_t)M.nU);
+        get((void **)&M.Ui, sizeof(int) * (size_t)M.nU);
+        get((void **)&M.Uj, sizeof(int) * (size_t)M.nU);
+        get((void **)&M.W, sizeof(double) * 18 * (size_t)M.nW);
+        get((void **)&M.photo, sizeof(int) * (size_t)M.nW);
+        get((void **)&M.feature, sizeof(int) * (size_t)M.nW);
+        get((void **)&M.V, sizeof(double) * 9 * (size_t)M.n);
+        get((void **)&M.FBlock, sizeof(int) * (size_t)M.n);
+    }
+    fclose(f);
+    if (!ok) {
+        if (maps) { for (int i = 0; i < num; i++) lsfm_free_map(&maps[i]); free(maps); }
+        lsfm_set_error(std::string(file) + ": truncated or corrupt map cache");
+        return LSFM_ERR_FORMAT;
+    }
+    *maps_out = maps; *num_out = num;
+    if (mono_out) *mono_out = hdr[1];
+    return LSFM_OK;
+}
+
+void lsfm_free_cache(lsfm_map *maps, int num)
+{
+    if (!maps) return;
+    for (int i = 0; i < num; i++) lsfm_free_map(&maps[i]);
+    free(maps);
+}
+
 int lsfm_cli_main(int argc, char **argv)
 {
-    std::string path, st, pose, feat, type, mapout;
+    std::string path, st, pose, feat, type, mapout, cache;
     int num = 0;
     bool hasPath = false, hasNum = false, hasType = false;
     for (int i = 1; i < argc; i++) {
@@ -268,6 +361,7 @@ int lsfm_cli_main(int argc, char **argv)
         else if (name == "p") arg(pose);
         else if (name == "f") arg(feat);
         else if (name == "map") arg(mapout);          // extension: the joined map (state + information) in localmap format
+        else if (name == "cache") arg(cache);         // extension: binary cache of the parsed input maps
         else if (name == "num") { std::string v; arg(v); num = atoi(v.c_str()); hasNum = true; }
         else if (name == "type") {
             std::string v; arg(v);
@@ -282,21 +376,39 @@ int lsfm_cli_main(int argc, char **argv)
     if (lsfm_init(0) != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1; }
 
     std::vector<lsfm_map> maps(num);
-    std::vector<int> rc(num, LSFM_OK);
-    std::vector<std::string> errs(num);
-    int nth = std::min<int>(std::max(1u, std::thread::hardware_concurrency()), 32);
-    nth = std::min(nth, num);
-    auto work = [&](int tid) {
-        for (int i = tid; i < num; i += nth) {
-            std::string p = path + "/localmap_" + std::to_string(i + 1) + ".txt";
-            rc[i] = load_map_impl(p.c_str(), &maps[i], errs[i], mono);
+    // -cache <file>: an existing cache with the same map count and type replaces the text parse; otherwise
+    // the text files are parsed and the cache is (re)written
+    bool fromCache = false;
+    if (!cache.empty()) {
+        lsfm_map *cm = nullptr;
+        int cn = 0, cmono = 0;
+        if (lsfm_load_cache(cache.c_str(), &cm, &cn, &cmono) == LSFM_OK) {
+            if (cn == num && (cmono != 0) == mono) {
+                for (int i = 0; i < num; i++) maps[i] = cm[i];      // the arrays move into `maps`
+                free(cm);
+                fromCache = true;
+            } else lsfm_free_cache(cm, cn);
         }
-    };
-    std::vector<std::thread> th;
-    for (int t = 0; t < nth; t++) th.emplace_back(work, t);
-    for (auto &t : th) t.join();
-    for (int i = 0; i < num; i++)
-        if (rc[i] != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", errs[i].c_str()); return 1; }
+    }
+    if (!fromCache) {
+        std::vector<int> rc(num, LSFM_OK);
+        std::vector<std::string> errs(num);
+        int nth = std::min<int>(std::max(1u, std::thread::hardware_concurrency()), 32);
+        nth = std::min(nth, num);
+        auto work = [&](int tid) {
+            for (int i = tid; i < num; i += nth) {
+                std::string p = path + "/localmap_" + std::to_string(i + 1) + ".txt";
+                rc[i] = load_map_impl(p.c_str(), &maps[i], errs[i], mono);
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 0; t < nth; t++) th.emplace_back(work, t);
+        for (auto &t : th) t.join();
+        for (int i = 0; i < num; i++)
+            if (rc[i] != LSFM_OK) { fprintf(stderr, "LinearSFM (B200): %s\n", errs[i].c_str()); return 1; }
+        if (!cache.empty() && lsfm_save_cache(cache.c_str(), maps.data(), num, mono ? 1 : 0) != LSFM_OK)
+            fprintf(stderr, "LinearSFM (B200): %s (continuing without the cache)\n", lsfm_last_error());
+    }
 
     if (mono) {
         // CLinearSFMImp::runMono (LinearSFMImp.cpp:3136-3152)

@@ -100,3 +100,29 @@ def test_parallel_writers_byte_identical_on_a_large_map(oracle, tmp_path):
     oracle.save_outputs(lm, st=ref["st"], pose=ref["p"], feat=ref["f"])
     for k in got:
         assert filecmp.cmp(got[k], ref[k], shallow=False), k
+
+
+def test_binary_cache_round_trip(tmp_path):
+    """lsfm_save_cache / lsfm_load_cache: the maps come back bit for bit; a truncated file and a
+    file of another kind are refused."""
+    from linearsfm_b200.localmap import maps_equal_int
+    maps = synth.make_stereo_scene(5, feats_per_frame=12, seed=11)
+    arr, _keep = api.to_c_array(maps)
+    f = str(tmp_path / "maps.lsfmcache")
+    _lib.check(_lib.lib().lsfm_save_cache(f.encode(), arr, C.c_int(len(maps)), C.c_int(0)))
+    out = C.POINTER(_lib.LsfmMap)()
+    num, mono = C.c_int(0), C.c_int(-1)
+    _lib.check(_lib.lib().lsfm_load_cache(f.encode(), C.byref(out), C.byref(num), C.byref(mono)))
+    assert num.value == len(maps) and mono.value == 0
+    for i, lm in enumerate(maps):
+        got = api.from_c(out[i], free=False)
+        assert not maps_equal_int(got, lm)
+        for name in ("stVal", "U", "W", "V"):
+            assert np.array_equal(getattr(got, name), getattr(lm, name)), name
+    _lib.lib().lsfm_free_cache(out, num)
+    raw = open(f, "rb").read()
+    open(f, "wb").write(raw[: len(raw) // 2])
+    assert _lib.lib().lsfm_load_cache(f.encode(), C.byref(out), C.byref(num), C.byref(mono)) == 6
+    open(f, "wb").write(b"not a cache at all")
+    assert _lib.lib().lsfm_load_cache(f.encode(), C.byref(out), C.byref(num), C.byref(mono)) == 6
+    assert _lib.lib().lsfm_load_cache(str(tmp_path / "missing").encode(), C.byref(out), C.byref(num), C.byref(mono)) == 5

@@ -73,3 +73,29 @@ def test_cli_map_output_can_be_joined_again(gpu, oracle, tmp_path):
     got = oracle.load_localmap_stereo(mp)                       # read by the REFERENCE's parser
     ref, _, _ = oracle.run_tree_stereo(maps)
     assert_maps_match(got, ref, tol_state=1e-8, tol_info=1e-8, what="-map output vs reference tree")
+
+
+@pytest.mark.parametrize("typ,n", [("Stereo", 6), ("Monocular", 5)])
+def test_cli_binary_cache(gpu, tmp_path, typ, n):
+    # -cache <file> (extension): first run parses the text files and writes the cache, the second
+    # run reads ONLY the cache (the text files are gone by then) and writes byte-identical outputs
+    import tempfile
+    mono = typ == "Monocular"
+    maps = synth.make_mono_scene(n, 16, seed=31) if mono else synth.make_stereo_scene(n, 12, seed=32)
+    d = tempfile.mkdtemp(prefix="lsfm", dir="/tmp")
+    for i, lm in enumerate(maps):
+        write_localmap(os.path.join(d, f"localmap_{i + 1}.txt"), lm, mono=mono)
+    cache = os.path.join(d, "maps.lsfmcache")
+    outs = []
+    for run in range(2):
+        o = {k: os.path.join(d, f"run{run}_{k}.txt") for k in ("p", "f", "st")}
+        r = subprocess.run([_lib.CLI_PATH, "-path", d, "-num", str(n), "-type", typ, "-cache", cache,
+                            "-p", o["p"], "-f", o["f"], "-st", o["st"]], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and os.path.exists(cache), r.stderr
+        outs.append(o)
+        for i in range(n):                                   # the second run must not need the text files
+            p = os.path.join(d, f"localmap_{i + 1}.txt")
+            if os.path.exists(p):
+                os.remove(p)
+    for k in ("p", "f", "st"):
+        assert open(outs[0][k], "rb").read() == open(outs[1][k], "rb").read(), k

@@ -13,4 +13,4 @@ for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 12):
 arr, keep = api.to_c_array(maps)
 for it in range(4):
     t = time.perf_counter(); tree.set_maps_c(arr, len(maps)); t1 = time.perf_counter(); tree.solve(); t2 = time.perf_counter(); tree.download_state(0); t3 = time.perf_counter()
-    print("e2e %d upload %.4f solve %.4f download %.4f" % (it, t1 - t, t2 - t1, t3 - t2), flush=True)
+    print("e2e %d upload %.4f solve %.4f (device %.2f ms) download %.4f" % (it, t1 - t, t2 - t1, tree.last_solve_ms(), t3 - t2), flush=True)
