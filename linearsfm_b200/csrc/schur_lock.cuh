@@ -17,11 +17,11 @@
 //   * pairs are laid out diagonal first, then row-major (i, j>i): the lanes of a warp read the SAME
 //     W V^-1 block (broadcast) and CONSECUTIVE W blocks of the feature, ~3 shared-memory wavefronts per
 //     pair of 16-byte operand loads instead of 8;
-//   * when the chunk has P pairs and P + nposes <= THREADS the features of a batch are dealt to
-//     NS = (THREADS - nposes) / P feature slices (thread = (slice, pair)); the slices' partial blocks
-//     are summed in slice order through shared memory (fixed order: same bits every run);
-//   * the pose's share of E is carried by nposes extra "E lanes" (18 FMAs per feature instead of 108)
+//   * the pose's share of E is carried by nposes extra "E items" (18 FMAs per feature instead of 108)
 //     so that the pair lanes run one branch-free body;
+//   * when the chunk's P pairs fit THREADS several times, the features of a batch are dealt to NS feature
+//     slices of the pairs and ceil(NS / 3) slices of the E items (thread = (slice, item)); the slices'
+//     partial sums are added in slice order through shared memory (fixed order: same bits every run);
 //   * chunks with more items than threads (> 21 poses: ~1 % of the root level) take several passes
 //     over their features, one item window per pass;
 //   * top levels: 256 threads, 128 registers, ~108 KB of shared memory: TWO CTAs per SM, so one chunk's
@@ -102,9 +102,16 @@ k_schur_lock(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         return;
     }
     const int P = nposes * (nposes + 1) / 2;
-    int NS = 1, npass = 1;
-    if (P + nposes <= THREADS) NS = min((THREADS - nposes) / P, NBMAX);
-    else npass = (P + nposes + THREADS - 1) / THREADS;
+    // Items: NS feature slices of the P pairs, then NSE feature slices of the nposes E items.  An E item costs
+    // about a third of a pair item per feature (lookup + 18 FMAs against 108), so NSE = ceil(NS / 3) keeps the
+    // E lanes from becoming the stragglers of a batch without spending pair lanes on them.
+    int NS = 1, NSE = 1, npass = 1;
+    if (P + nposes <= THREADS) {
+        NS = min((THREADS - nposes) / P, NBMAX);
+        while (NS > 1 && NS * P + ((NS + 2) / 3) * nposes > THREADS) NS--;
+        NSE = (NS + 2) / 3;
+    } else npass = (P + nposes + THREADS - 1) / THREADS;
+    const int nPairItems = NS * P;
 
     const double *Wg = M.W;
     const int *Pg = blkInfo + wPre[k];
@@ -137,24 +144,23 @@ k_schur_lock(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     for (int pass = 0; pass < npass; pass++) {
         // this thread's item: a pose pair (kind 1; diagonal pairs first, then (i, j>i) row by row), a
         // pose's share of E (kind 2), or nothing
-        int kind = 0, pi = 0, pj = 0, slice = 0;
-        {
-            int t = tid + pass * THREADS;
-            if (t < NS * P) {
-                kind = 1;
-                slice = t / P;
-                t -= slice * P;
-                if (t < nposes) { pi = t; pj = t; }
-                else {
-                    t -= nposes;
-                    int i = 0;
-                    while (t >= nposes - 1 - i) { t -= nposes - 1 - i; i++; }
-                    pi = i; pj = i + 1 + t;
-                }
-            } else if (t - NS * P < nposes) {
-                kind = 2;
-                pi = pj = t - NS * P;
+        int kind = 0, pi = 0, pj = 0, slice = 0, nsl = 1;   // nsl: slices of this item's kind
+        const int item = tid + pass * THREADS;        // [0, NS P): slice-major pairs; then slice-major E items
+        if (item < nPairItems) {
+            kind = 1; nsl = NS;
+            slice = item / P;
+            int t = item - slice * P;
+            if (t < nposes) { pi = t; pj = t; }
+            else {
+                t -= nposes;
+                int i = 0;
+                while (t >= nposes - 1 - i) { t -= nposes - 1 - i; i++; }
+                pi = i; pj = i + 1 + t;
             }
+        } else if (item - nPairItems < NSE * nposes) {
+            kind = 2; nsl = NSE;
+            slice = (item - nPairItems) / nposes;
+            pi = pj = (item - nPairItems) - slice * nposes;
         }
         double acc[36];
 #pragma unroll
@@ -220,7 +226,7 @@ k_schur_lock(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
                 }
             } else if (kind == 2) {
                 const double *rE = rawEf + buf * (NBMAX * 6) + sideOff;
-                for (int fb = 0; fb < nbf; fb++) {
+                for (int fb = slice; fb < nbf; fb += NSE) {
                     const int bb = bo[fb * 32 + pi];
                     if (bb == RB) continue;
                     const double2 *w2 = reinterpret_cast<const double2 *>(rW + bb * 18);
@@ -237,23 +243,27 @@ k_schur_lock(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         }
         // partial blocks of slices 1.. go through shared memory ([entry][thread]: conflict-free) and are
         // added by the slice-0 thread of the pair in slice order
-        if (NS > 1) {
+        if (NS > 1) {                                      // (NSE > 1 implies NS > 1)
             __syncthreads();                               // every operand buffer is free now
             double *red = (double *)smraw;
-            const int nred = (NS - 1) * P;
-            if (kind == 1 && slice > 0) {
+            // scratch rows: the pair items of slices 1.., then the E items of slices 1..
+            const int nredP = (NS - 1) * P, nred = nredP + (NSE - 1) * nposes;
+            const int width = kind == 1 ? P : nposes;                     // items per slice of this kind
+            const int base = kind == 1 ? item - P : nredP + (item - nPairItems) - nposes;   // row of a slice > 0 item
+            if (kind != 0 && slice > 0) {
 #pragma unroll
-                for (int q = 0; q < 36; q++) red[q * nred + (tid - P)] = acc[q];
+                for (int q = 0; q < 36; q++) red[q * nred + base] = acc[q];
             }
             __syncthreads();
-            if (kind == 1 && slice == 0) {
-                for (int sl = 1; sl < NS; sl++) {
+            if (kind != 0 && slice == 0) {
+                const int first = kind == 1 ? item : nredP + (item - nPairItems);   // this item's row in slice 1
+                for (int sl = 1; sl < nsl; sl++) {
 #pragma unroll
-                    for (int q = 0; q < 36; q++) acc[q] += red[q * nred + (sl - 1) * P + tid];
+                    for (int q = 0; q < 36; q++) acc[q] += red[q * nred + first + (sl - 1) * width];
                 }
             }
         }
-        if (kind == 2) {
+        if (kind == 2 && slice == 0) {
             // the pose's share of E from this chunk: a record, gathered per pose by k_e_gather
             double *e = Erec + 6 * (32 * (size_t)blockIdx.x + pi);
 #pragma unroll
