@@ -1172,15 +1172,17 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             static const bool use_dense = getenv("LSFM_SCHUR_DENSE") != nullptr;
             static const bool use_pipe = getenv("LSFM_SCHUR_PIPE") != nullptr;    // previous per-lane-list kernel
             static const int lock_t = getenv("LSFM_SCHUR_LOCK_T") ? atoi(getenv("LSFM_SCHUR_LOCK_T")) : 0;
+            // smallest per-level maximum of poses per chunk from which the lock-step kernel is used
+            static const int lock_min = getenv("LSFM_SCHUR_LOCK_MIN") ? std::max(2, atoi(getenv("LSFM_SCHUR_LOCK_MIN"))) : 3;   // measured: level 2 0.35 -> 0.29 ms, level 1 0.26 -> 0.25, level 0 (two poses) stays with k_schur_pipe
             if (use_dense) {
                 if (maxNposes <= 16 || force_ovf2)
                     launch(schur_dense::k_schur_dense<16, 160, 256, 2, 8>, schur_dense::Layout<16, 160, 256>::bytes(), 256);
                 else
                     launch(schur_dense::k_schur_dense<31, 248, 512, 4, 16>, schur_dense::Layout<31, 248, 512>::bytes(), 512);
-            } else if (maxNposes <= 8 || force_ovf2)
+            } else if (maxNposes <= lock_min - 1 || force_ovf2)
                 launch(schur_pipe::k_schur_pipe<8, 64, 32, 128, 1>, schur_pipe::Layout<8, 64, 32>::bytes(), 128);
             else if (!use_pipe)
-                // upper levels (9-31 poses per chunk): lock-step kernel, two 256-thread CTAs per SM
+                // 3-31 poses per chunk: lock-step kernel (128 threads x 4 CTAs/SM up to 17 poses, 256 x 2 above)
                 // (LSFM_SCHUR_LOCK_T: 0 = pick by the level's maximum, 128 / 256 = force one instantiation)
                 if (lock_t == 128 || (lock_t == 0 && maxNposes <= 17))
                     launch(schur_lock::k_schur_lock<96, 32, 128, 4>, schur_lock::Layout<96, 32>::bytes(), 128);
