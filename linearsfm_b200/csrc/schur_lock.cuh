@@ -63,7 +63,8 @@ k_schur_lock(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
              const double *__restrict__ Vinv, const double *__restrict__ dvec, const int *__restrict__ split,
              const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
              double *__restrict__ S, double *__restrict__ E,
-             const int *__restrict__ sexp, long long *__restrict__ Sfx, double *__restrict__ Erec)
+             const int *__restrict__ sexp, long long *__restrict__ Sfx, double *__restrict__ Erec,
+             const SlowFx slow)
 {
     static_assert(RB >= 62 && RB <= 254, "block budget (a feature has <= 31 blocks; indices are bytes)");
     static_assert(Layout<RB, NBMAX>::scratch >= (THREADS - 3) * 36 * 8, "slice reduction scratch");
@@ -98,7 +99,7 @@ k_schur_lock(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     if (nposes == 0) return;
     if (nposes > 31 || nposes > pat_cmax) {       // the pattern kernel's overflow chunks
         for (int a = w0 + tid; a < w1; a += THREADS)
-            schur_block_slow(M, k, a, featPre, posePre, Vinv, dvec, split, keys, rowPtr, S, E);
+            schur_block_slow(M, k, a, featPre, posePre, Vinv, dvec, split, keys, rowPtr, slow);
         return;
     }
     const int P = nposes * (nposes + 1) / 2;

@@ -74,7 +74,8 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
              const double *__restrict__ Vinv, const double *__restrict__ dvec, const int *__restrict__ split,
              const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
              double *__restrict__ S, double *__restrict__ E,
-             const int *__restrict__ sexp, long long *__restrict__ Sfx, double *__restrict__ Erec)
+             const int *__restrict__ sexp, long long *__restrict__ Sfx, double *__restrict__ Erec,
+             const SlowFx slow)
 {
     static_assert(MAXBLK >= 2 * CMAX && MAXBLK <= 255, "block budget");
     static_assert(SLOTS == 1, "one pair slot per thread");
@@ -105,7 +106,7 @@ k_schur_pipe(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
     if (nposes == 0) return;
     if (nposes > CMAX || nposes > pat_cmax) {   // not expected: the host picks CMAX from the measured maximum
         for (int a = w0 + tid; a < w1; a += THREADS)
-            schur_block_slow(M, k, a, featPre, posePre, Vinv, dvec, split, keys, rowPtr, S, E);
+            schur_block_slow(M, k, a, featPre, posePre, Vinv, dvec, split, keys, rowPtr, slow);
         return;
     }
     const int npairs = nposes * (nposes + 1) / 2;

@@ -353,36 +353,6 @@ k_schur(const DMap *__restrict__ J, const int *__restrict__ wPre, const int *__r
     }
 }
 
-// Slow path for one W block (global atomics), used when a chunk sees too many distinct poses.
-__device__ __noinline__ void schur_block_slow(const DMap &M, int k, int a, const int *__restrict__ featPre,
-                                 const int *__restrict__ posePre, const double *__restrict__ Vinv,
-                                 const double *__restrict__ dvec, const int *__restrict__ split,
-                                 const u64 *__restrict__ keys,
-                                 const int *__restrict__ rowPtr, double *__restrict__ S,
-                                 double *__restrict__ E)
-{
-    int f = M.feature[a], pa = M.photo[a];
-    double W[18], Vi[9], WV[18], d[3], y[6];
-    sm::load<18>(M.W + 18 * (size_t)a, W);
-    sm::load<9>(Vinv + 9 * (size_t)(featPre[k] + f), Vi);
-    sm::mmt<6, 3, 3>(W, Vi, WV);
-    sm::load<3>(dvec + 6 * (size_t)(featPre[k] + f) + ((split && pa >= split[k]) ? 3 : 0), d);
-    sm::mm<6, 3, 1>(W, d, y);
-    for (int q = 0; q < 6; q++) atomicAdd(E + 6 * (size_t)(posePre[k] + pa) + q, -y[q]);
-    for (int b = M.wPtr[f]; b < M.wPtr[f + 1]; b++) {
-        int pb = M.photo[b];
-        if (pb < pa) continue;
-        double Wb[18], P[36];
-        sm::load<18>(M.W + 18 * (size_t)b, Wb);
-        sm::mmt<6, 3, 6>(WV, Wb, P);
-        int slot = find_slot(keys, rowPtr, posePre[k] + pa, pair_key(k, pa, pb));
-        double *s = S + 36 * (size_t)slot;
-        for (int q = 0; q < 36; q++) atomicAdd(s + q, -P[q]);
-    }
-}
-
-constexpr int SCH_FCHUNK = 128;        // features per chunk (pattern + Schur kernels)
-
 // ---- order-independent accumulation of S ------------------------------------------------------
 // The chunks' contributions to one S block arrive in an order the hardware chooses.  FP64 atomics would
 // make the last bits of S differ from run to run; instead every contribution is converted to 64-bit
@@ -395,6 +365,99 @@ constexpr int SCH_FCHUNK = 128;        // features per chunk (pattern + Schur ke
 __device__ __forceinline__ int row_exp_of(double u) { return (u > 0.0 && u < 1e300) ? ilogb(u) + 1 : 0; }
 __device__ __forceinline__ int fx_shift(int ea, int eb_) { return 60 - ((ea + eb_ + 1) >> 1); }
 __device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
+
+// Fixed-point accumulation of E for the slow path below: the contributions y = W_pf d_f have no a-priori
+// bound, so a pre-pass over the overflow chunks (k_schur_slow_pre) records, per (pose, row), the largest
+// exponent of a contribution and, per pose, how many there are; every partial sum then stays below
+// 2^(emax + ceil(log2(count + 1))) and is accumulated as round(y 2^shift) with integer atomics.
+struct SlowFx {
+    const int *sexp;            // [6 totPose] exponents of the diagonal of U (S scale)
+    long long *Sfx;             // [36 nuis]
+    int *eexp;                  // [6 totPose] largest contribution exponent per (pose, row); < -2000: none
+    int *ecnt;                  // [totPose]   contributions per pose
+    long long *Efx;             // [6 totPose]
+};
+__device__ __forceinline__ int e_shift(int emax, int cnt) { return 60 - emax - (32 - __clz(cnt)); }
+
+// Slow path for one W block, used when a chunk sees too many distinct poses: exact integer atomics into the
+// fixed-point accumulators of S and E (order-independent, like the fast path's flush).
+__device__ __noinline__ void schur_block_slow(const DMap &M, int k, int a, const int *__restrict__ featPre,
+                                 const int *__restrict__ posePre, const double *__restrict__ Vinv,
+                                 const double *__restrict__ dvec, const int *__restrict__ split,
+                                 const u64 *__restrict__ keys,
+                                 const int *__restrict__ rowPtr, const SlowFx fx)
+{
+    int f = M.feature[a], pa = M.photo[a];
+    double W[18], Vi[9], WV[18], d[3], y[6];
+    sm::load<18>(M.W + 18 * (size_t)a, W);
+    sm::load<9>(Vinv + 9 * (size_t)(featPre[k] + f), Vi);
+    sm::mmt<6, 3, 3>(W, Vi, WV);
+    sm::load<3>(dvec + 6 * (size_t)(featPre[k] + f) + ((split && pa >= split[k]) ? 3 : 0), d);
+    sm::mm<6, 3, 1>(W, d, y);
+    const size_t gpa = (size_t)(posePre[k] + pa);
+    const int cnt = fx.ecnt[gpa];
+    for (int q = 0; q < 6; q++) {
+        const int em = fx.eexp[6 * gpa + q];
+        if (em < -2000) continue;                                       // every contribution to this row is 0
+        const long long v = __double2ll_rn(-y[q] * pow2(e_shift(em, cnt)));
+        atomicAdd(reinterpret_cast<unsigned long long *>(fx.Efx) + 6 * gpa + q, (unsigned long long)v);
+    }
+    int ea[6];
+    for (int q = 0; q < 6; q++) ea[q] = fx.sexp[6 * gpa + q];
+    for (int b = M.wPtr[f]; b < M.wPtr[f + 1]; b++) {
+        int pb = M.photo[b];
+        if (pb < pa) continue;
+        double Wb[18], P[36];
+        sm::load<18>(M.W + 18 * (size_t)b, Wb);
+        sm::mmt<6, 3, 6>(WV, Wb, P);
+        int slot = find_slot(keys, rowPtr, posePre[k] + pa, pair_key(k, pa, pb));
+        unsigned long long *sp = reinterpret_cast<unsigned long long *>(fx.Sfx) + 36 * (size_t)slot;
+        const size_t gpb = (size_t)(posePre[k] + pb);
+        for (int r = 0; r < 6; r++)
+            for (int c = 0; c < 6; c++) {
+                const long long v = __double2ll_rn(P[6 * r + c] * pow2(fx_shift(ea[r], fx.sexp[6 * gpb + c])));
+                atomicAdd(sp + 6 * r + c, (unsigned long long)v);
+            }
+    }
+}
+
+// pre-pass of the slow path: exponent / count bookkeeping of the E contributions of the overflow chunks
+__global__ void __launch_bounds__(128)
+k_schur_slow_pre(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks, const int *__restrict__ chunkInfo,
+                 int pat_cmax, const int *__restrict__ featPre, const int *__restrict__ posePre,
+                 const double *__restrict__ dvec, const int *__restrict__ split, int *__restrict__ eexp,
+                 int *__restrict__ ecnt)
+{
+    const int np = chunkInfo[CHUNK_INFO_INTS * (size_t)blockIdx.x + 31];
+    if (np <= 31 && np <= pat_cmax) return;
+    const FeatChunk ch = chunks[blockIdx.x];
+    const DMap &M = J[ch.k];
+    const int k = ch.k;
+    for (int a = M.wPtr[ch.f0] + threadIdx.x; a < M.wPtr[ch.f1]; a += blockDim.x) {
+        const int f = M.feature[a], pa = M.photo[a];
+        double W[18], d[3], y[6];
+        sm::load<18>(M.W + 18 * (size_t)a, W);
+        sm::load<3>(dvec + 6 * (size_t)(featPre[k] + f) + ((split && pa >= split[k]) ? 3 : 0), d);
+        sm::mm<6, 3, 1>(W, d, y);
+        const size_t gpa = (size_t)(posePre[k] + pa);
+        atomicAdd(ecnt + gpa, 1);
+        for (int q = 0; q < 6; q++)
+            if (y[q] != 0.0 && fabs(y[q]) < 1e300) atomicMax(eexp + 6 * gpa + q, ilogb(y[q]) + 1);
+    }
+}
+
+// E += the slow path's fixed-point sums (one thread per (pose, row))
+__global__ void k_e_convert(int n6, const int *__restrict__ eexp, const int *__restrict__ ecnt,
+                            const long long *__restrict__ Efx, double *__restrict__ E)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n6) return;
+    const int em = eexp[g];
+    if (em < -2000) return;
+    E[g] += (double)Efx[g] * pow2(-e_shift(em, ecnt[g / 6]));
+}
+
+constexpr int SCH_FCHUNK = 128;        // features per chunk (pattern + Schur kernels)
 
 // one thread per (pose, row): exponent of the diagonal entry U(ir,ir), read from S after k_s_from_u
 __global__ void k_row_exp(const u64 *__restrict__ keys, const int *__restrict__ rowPtr,
@@ -1143,6 +1206,18 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     DevBuf<double> Erec(6 * 32 * (size_t)std::max(nChunks, 1), s);
     CUDA_CHECK(cudaMemsetAsync(Sfx.p, 0, sizeof(long long) * 36 * (size_t)std::max(nuis, 1), s));
     k_row_exp<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(keys.p, rowPtr.p, J.d.p, J.dPosePre.p, K, J.totPose, S.p, sexp.p); nl++;
+    // slow path (chunks with more than PAT_CMAX poses): fixed-point E accumulators + the pre-pass that sizes them
+    const bool anySlow = nChunks > 0 && (maxNposes > PAT_CMAX || maxNposes > pat_cmax_used);
+    DevBuf<int> eexp(anySlow ? 6 * (size_t)J.totPose : 1, s), ecnt(anySlow ? (size_t)J.totPose : 1, s);
+    DevBuf<long long> Efx(anySlow ? 6 * (size_t)J.totPose : 1, s);
+    if (anySlow) {
+        CUDA_CHECK(cudaMemsetAsync(eexp.p, 0x80, sizeof(int) * 6 * (size_t)J.totPose, s));      // 0x80808080 < -2000
+        CUDA_CHECK(cudaMemsetAsync(ecnt.p, 0, sizeof(int) * (size_t)J.totPose, s));
+        CUDA_CHECK(cudaMemsetAsync(Efx.p, 0, sizeof(long long) * 6 * (size_t)J.totPose, s));
+        k_schur_slow_pre<<<nChunks, 128, 0, s>>>(J.d.p, dChunks.p, chunkInfo.p, pat_cmax_used, J.dFeatPre.p, J.dPosePre.p,
+                                                 dvec.p, split, eexp.p, ecnt.p); nl++;
+    }
+    const SlowFx slowFx{sexp.p, Sfx.p, eexp.p, ecnt.p, Efx.p};
     ctx.end(72.0 * J.totFeat * 2 + 576.0 * J.totU, 0.0, nl);
     nl = 0;
     ctx.begin("solve.schur");
@@ -1161,7 +1236,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
                 }
                 kern<<<nChunks, threads, shb, s>>>(J.d.p, dChunks.p, chunkInfo.p, blkInfo.p, pat_cmax_used, J.dWPre.p,
                                                   J.dFeatPre.p, J.dPosePre.p, Vinv.p, dvec.p, split, keys.p, rowPtr.p, S.p, E.p,
-                                                  sexp.p, Sfx.p, Erec.p);
+                                                  sexp.p, Sfx.p, Erec.p, slowFx);
             };
             static const bool force_ovf2 = getenv("LSFM_FORCE_OVERFLOW") != nullptr;
             // LSFM_SCHUR_DENSE=1: the chunk's dense pose pairs as one DMMA contraction (schur_dense.cuh).
@@ -1199,6 +1274,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             ctx.begin("solve.schur_fin");
             // S -= the fixed-point sums; E_p -= the chunks' shares, gathered per pose in a fixed order
             k_s_convert<<<ceil_div(36ll * nuis, TB), TB, 0, s>>>(keys.p, nuis, J.dPosePre.p, sexp.p, Sfx.p, S.p); nl++;
+            if (anySlow) { k_e_convert<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(6 * J.totPose, eexp.p, ecnt.p, Efx.p, E.p); nl++; }
             k_e_gather<<<ceil_div(32ll * J.totPose, 128), 128, 0, s>>>(J.dPosePre.p, K, J.totPose, dChunkPre.p, patBits.p,
                                                                     bitsStride, Erec.p, E.p); nl++;
         }

@@ -677,10 +677,25 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
     DevBuf<double> poseAcc(36 * (size_t)A.totPose, s);      // slow-path (chunk overflow) sums only
     dChunkPre.upload(chunkPre);
     poseAcc.zero();
+    // Chunks with more than TC_CMAX distinct poses can only occur in maps whose join already had to split
+    // chunks (landmarks seen by more than 30 poses stay in overflowing chunks): only then the slow path's
+    // fixed-point bookkeeping is set up (k_tf_slow_pre).
+    static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;   // test hook: slow path
+    bool maySlow = force_ovf;
+    for (int k = 0; k < K; k++) maySlow = maySlow || (bool)in[k].chunkStarts;
+    DevBuf<int> pexp(maySlow ? 36 * (size_t)A.totPose : 1, s), pcnt(maySlow ? (size_t)A.totPose : 1, s);
+    DevBuf<long long> poseFx(maySlow ? 36 * (size_t)A.totPose : 1, s);
     if (nChunks > 0) {
         dChunks.upload(chunks);
-        static const bool force_ovf = getenv("LSFM_FORCE_OVERFLOW") != nullptr;   // test hook: slow path
         const int cmaxUse = force_ovf ? 4 : tfc::TC_CMAX;
+        if (maySlow) {
+            CUDA_CHECK(cudaMemsetAsync(pexp.p, 0x80, sizeof(int) * 36 * (size_t)A.totPose, s));     // < -2000: nothing
+            CUDA_CHECK(cudaMemsetAsync(pcnt.p, 0, sizeof(int) * (size_t)A.totPose, s));
+            CUDA_CHECK(cudaMemsetAsync(poseFx.p, 0, sizeof(long long) * 36 * (size_t)A.totPose, s));
+            const size_t shp = sizeof(unsigned) * (size_t)maxWords;
+            ctx.ensure_smem((const void *)tfc::k_tf_slow_pre, shp);
+            tfc::k_tf_slow_pre<<<nChunks, 128, shp, s>>>(A.d.p, dChunks.p, A.dPosePre.p, tc.p, cmaxUse, pexp.p, pcnt.p); nl++;
+        }
         const size_t shb = tfc::Layout::bytes(maxWords);
         ctx.ensure_smem((const void *)tfc::k_tf_chunk, shb);
         // stage timer of its own: this one kernel carries the W/V bytes of the transform
@@ -690,7 +705,7 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
         nl = 0;
         ctx.begin("transform.wv");
         tfc::k_tf_chunk<<<nChunks, tfc::TC_THREADS, shb, s>>>(A.d.p, B.d.p, dChunks.p, A.dFeatPre.p, A.dPosePre.p,
-                                                            tc.p, pj.p, fScan.p, poseAcc.p, cmaxUse,
+                                                            tc.p, pj.p, fScan.p, pexp.p, pcnt.p, poseFx.p, cmaxUse,
                                                             chunkBits.p, bitsStride, chunkRec.p, ppKey.p + ppC,
                                                             ppVal.p + 36 * ppC);
         {
@@ -701,6 +716,10 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
             ctx.end(wvBytes, 0.0, 1);
         }
         ctx.begin("transform");
+        if (maySlow) {
+            tfc::k_tf_slow_convert<<<ceil_div(36ll * A.totPose, 256), 256, 0, s>>>(36 * A.totPose, pexp.p, pcnt.p, poseFx.p,
+                                                                                 poseAcc.p); nl++;
+        }
     }
     k_tf_posefin<<<ceil_div(32ll * A.totPose, 128), 128, 0, s>>>(A.dPosePre.p, K, A.totPose, tc.p, pj.p, dChunkPre.p,
                                                               chunkBits.p, bitsStride, chunkRec.p, poseAcc.p,

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3)
 k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__restrict__ chunks,
            const int *__restrict__ featPre, const int *__restrict__ posePre,
            const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj, const int *__restrict__ fScan,
-           double *__restrict__ poseAcc, int cmaxUse,
+           const int *__restrict__ pexp, const int *__restrict__ pcnt, long long *__restrict__ poseFx, int cmaxUse,
            unsigned *__restrict__ chunkBits, int bitsStride, double *__restrict__ chunkRec,
            int *__restrict__ ppKey, double *__restrict__ ppVal)
 {
@@ -318,9 +318,19 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
 #pragma unroll
                 for (int i = 0; i < 9; i++) row[i] = make_double2(WT[2 * i], WT[2 * i + 1]);
             } else {
-                double *pa = poseAcc + 36 * (size_t)(posePre[k] + p);
+                // slow path: exact fixed-point integer atomics (scale from k_tf_slow_pre's exponent / count
+                // bookkeeping): order-independent, same bits every run
+                const size_t gp = (size_t)(posePre[k] + p);
+                unsigned long long *pa = reinterpret_cast<unsigned long long *>(poseFx) + 36 * gp;
+                const int bits = 32 - __clz(pcnt[gp]);
 #pragma unroll
-                for (int i = 0; i < 18; i++) { atomicAdd(pa + i, W[i]); atomicAdd(pa + 18 + i, WT[i]); }
+                for (int i = 0; i < 36; i++) {
+                    const int em = pexp[36 * gp + i];
+                    if (em < -2000) continue;
+                    const double v = i < 18 ? W[i] : WT[i - 18];
+                    const int sh = 60 - em - bits;
+                    atomicAdd(pa + i, (unsigned long long)__double2ll_rn(v * __longlong_as_double((long long)(1023 + sh) << 52)));
+                }
             }
         }
         double X[18];
@@ -464,6 +474,69 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
         const int it = tid + u * TC_THREADS;
         if (it < nitems) chunkRec[36 * 32 * (size_t)blockIdx.x + it] = acc[u];   // [chunk][slot][36]
     }
+}
+
+// Pre-pass of the slow path (chunks with more than cmaxUse distinct poses): per (pose, element) the largest
+// exponent of a contribution to SW / SWT and per pose the number of contributions, so that the chunk kernel can
+// accumulate them in fixed point.  Launched only when a map carries split chunks (or the test hook is on).
+__global__ void __launch_bounds__(128)
+k_tf_slow_pre(const DMap *__restrict__ in, const Chunk *__restrict__ chunks, const int *__restrict__ posePre,
+              const TfConst *__restrict__ tc, int cmaxUse, int *__restrict__ pexp, int *__restrict__ pcnt)
+{
+    extern __shared__ unsigned bm[];               // [words] pose bitmap of the chunk
+    __shared__ int cntSh;
+    const Chunk ch = chunks[blockIdx.x];
+    const DMap &M = in[ch.k];
+    const TfConst &c = tc[ch.k];
+    const int k = ch.k, words = (M.m + 31) >> 5, tid = threadIdx.x;
+    const int w0 = M.wPtr[ch.f0], w1 = M.wPtr[ch.f1];
+    for (int i = tid; i < words; i += 128) bm[i] = 0u;
+    if (tid == 0) cntSh = 0;
+    __syncthreads();
+    for (int j = w0 + tid; j < w1; j += 128) { const int p = M.photo[j]; atomicOr(&bm[p >> 5], 1u << (p & 31)); }
+    __syncthreads();
+    int pc = 0;
+    for (int i = tid; i < words; i += 128) pc += __popc(bm[i]);
+    if (pc) atomicAdd(&cntSh, pc);
+    __syncthreads();
+    if (cntSh <= cmaxUse) return;
+    for (int j = w0 + tid; j < w1; j += 128) {
+        const int p = M.photo[j], f = M.feature[j];
+        const double *x = M.featVal + 3 * (size_t)f;
+        const double d0[3] = {x[0] - c.t[0], x[1] - c.t[1], x[2] - c.t[2]};
+        double xn[3];
+        geom::mat3_vec(c.R, d0, xn);
+        const double d[3] = {xn[0] - c.tn[0], xn[1] - c.tn[1], xn[2] - c.tn[2]};
+        double Tf[9], v[3];
+        geom::mat3_vec(c.QA, d, v); Tf[0] = v[0]; Tf[3] = v[1]; Tf[6] = v[2];
+        geom::mat3_vec(c.QB, d, v); Tf[1] = v[0]; Tf[4] = v[1]; Tf[7] = v[2];
+        geom::mat3_vec(c.QG, d, v); Tf[2] = v[0]; Tf[5] = v[1]; Tf[8] = v[2];
+        double W[18], WT[18];
+        sm::load<18>(M.W + 18 * (size_t)j, W);
+        sm::mm<6, 3, 3>(W, Tf, WT);
+        const size_t gp = (size_t)(posePre[k] + p);
+        atomicAdd(pcnt + gp, 1);
+        for (int i = 0; i < 36; i++) {
+            const double val = i < 18 ? W[i] : WT[i - 18];
+            // +1: the chunk kernel forms T_f with fused multiply-adds, its W T_f can exceed this one by an ulp
+            if (val != 0.0 && fabs(val) < 1e300) atomicMax(pexp + 36 * gp + i, ilogb(val) + 2);
+        }
+    }
+}
+
+// poseAcc = the slow path's fixed-point sums (one thread per (pose, element)); zero where nothing was added
+__global__ void k_tf_slow_convert(int n36, const int *__restrict__ pexp, const int *__restrict__ pcnt,
+                                  const long long *__restrict__ poseFx, double *__restrict__ poseAcc)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n36) return;
+    const int em = pexp[g];
+    double v = 0.0;
+    if (em >= -2000) {
+        const int sh = 60 - em - (32 - __clz(pcnt[g / 36]));
+        v = (double)poseFx[g] * __longlong_as_double((long long)(1023 - sh) << 52);
+    }
+    poseAcc[g] = v;
 }
 
 } // namespace tfc
