@@ -208,3 +208,15 @@ def test_two_runs_bit_identical(gpu):
     assert not maps_equal_int(a, b)
     for name in ("stVal", "U", "W", "V"):
         assert np.array_equal(getattr(a, name), getattr(b, name)), f"{name} differs between two runs"
+
+
+def test_two_runs_bit_identical_on_the_slow_paths(gpu):
+    """Chunks that see too many distinct poses (loop closures; forced here for every chunk with more than 4) take
+    the thread-per-block paths of the Schur and Transform kernels: their sums are exact fixed-point integer
+    accumulations (pre-pass for the scales), so two solves still give the same bits.  Fresh process: the
+    switch is read once."""
+    import subprocess, sys
+    e = dict(os.environ); e["LSFM_FORCE_OVERFLOW"] = "1"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dev_determinism.py"), "300", "64", "80"],
+                       env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "bit-identical: True" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
