@@ -88,6 +88,7 @@ static bool nd_order_impl(int m, const int *ptr, const int *adj, std::vector<int
             cnt[best] = 0;
             side[best] = 3;
             sep.push_back(best);
+            if (sepLimit > 0 && (int)sep.size() > sepLimit) return false;     // (the cover loop is O(|S| |L|))
         }
         if (sepLimit > 0 && (int)sep.size() > sepLimit) return false;
         std::sort(sep.begin(), sep.end());
