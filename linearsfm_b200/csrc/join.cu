@@ -262,16 +262,19 @@ k_join_w(const DMap *__restrict__ E, const DMap *__restrict__ C, DMap *__restric
     double W[18];
     double *dst = J[k].W;
     if (uni) {
-        const double *src = S.W + 18 * (size_t)(sb - lane);       // the warp's first block
+        // 16-byte pieces: a block is nine of them (144 bytes, 16-byte aligned in both maps)
+        const double2 *src = reinterpret_cast<const double2 *>(S.W + 18 * (size_t)(sb - lane));   // the warp's first block
+        double2 *dst2 = reinterpret_cast<double2 *>(dst);
         double *tw = tile[warp];
 #pragma unroll
-        for (int it = 0; it < 18; it++) {
+        for (int it = 0; it < 9; it++) {
             int e = it * 32 + lane;
-            int blk = e / 18, el = e - 18 * blk;
-            double v = src[e];
+            int blk = e / 9, el = e - 9 * blk;
+            double2 v = src[e];
             int ob = __shfl_sync(full, o, blk);
-            dst[18 * (size_t)ob + el] = v;
-            tw[blk * 19 + el] = v;
+            dst2[9 * (size_t)ob + el] = v;
+            tw[blk * 19 + 2 * el] = v.x;
+            tw[blk * 19 + 2 * el + 1] = v.y;
         }
         __syncwarp();
 #pragma unroll
