@@ -981,8 +981,13 @@ __global__ void k_backsub(DMap *__restrict__ J, const int *__restrict__ featPre,
     double acc[3] = {0, 0, 0};
     for (int j = M.wPtr[f]; j < M.wPtr[f + 1]; j++) {
         double W[18], xp[6], t[3];
-        sm::load<18>(M.W + 18 * (size_t)j, W);
-        sm::load<6>(M.poseVal + 6 * (size_t)M.photo[j], xp);
+        // 16-byte loads: W blocks (144 bytes) and pose rows (48 bytes) are 16-byte aligned in the arena
+        const double2 *w2 = reinterpret_cast<const double2 *>(M.W + 18 * (size_t)j);
+        const double2 *x2 = reinterpret_cast<const double2 *>(M.poseVal + 6 * (size_t)M.photo[j]);
+#pragma unroll
+        for (int q = 0; q < 9; q++) { const double2 v = w2[q]; W[2 * q] = v.x; W[2 * q + 1] = v.y; }
+#pragma unroll
+        for (int q = 0; q < 3; q++) { const double2 v = x2[q]; xp[2 * q] = v.x; xp[2 * q + 1] = v.y; }
         sm::mtm<3, 6, 1>(W, xp, t);
         acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2];
     }
