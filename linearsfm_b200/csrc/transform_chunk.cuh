@@ -15,9 +15,11 @@
 //     A   nine 16-byte loads of the block (-> shared tile); T_f from d_f; W T_f -> shared tile; X = W Q;
 //         a1 -> its output slot directly (nine 16-byte stores); wadd -> shared tile;
 //         the block joins the batch list of its local pose
-//     B   thread per (local pose, element): SW / SWT partial sums in REGISTERS for the whole chunk
-//         (from the W and W T_f tiles);
-//         thread per (feature, element): the feature's wadd rows of this batch -> W'(pos,f)
+//     B   pose sums SW / SWT on the FP64 tensor cores: [slot x block] indicator (from the batch's slot
+//         bytes) times the [block x 36] W | W T_f tiles, mma.sync m8n8k4 (DMMA); warp w owns element
+//         columns 8w..8w+7 for all 128 blocks, the last four columns are split by block quarter;
+//         accumulators stay in REGISTERS for the whole chunk;
+//         thread per (feature, element pair): the feature's wadd rows of this batch -> W'(pos,f)
 // Two barriers per batch; W is read once from HBM and written once.  At the end the pose sums are
 // written as one record per (chunk, local pose) next to the chunk's pose bitmap; k_tf_posefin gathers
 // them per pose in a fixed order (no FP64 atomics: bit-identical results run to run).
@@ -42,6 +44,11 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 struct Layout {
     static constexpr int WA = 0;                                           // [BATCH][LD] double: wadd rows
@@ -53,7 +60,7 @@ struct Layout {
     static constexpr int wptr = Cst + 36 * 8;                              // [FCH+4] int
     static constexpr int optr = wptr + (TC_FCH + 4) * 4;                   // [FCH+4] int
     static constexpr int pidPos = optr + (TC_FCH + 4) * 4;                 // [FCH] int
-    static constexpr int lcnt = (pidPos + TC_FCH * 4 + 15) / 16 * 16;                       // [2][32][4] unsigned: per local pose, which lanes of each warp hold one of its blocks in the batch
+    static constexpr int lcnt = (pidPos + TC_FCH * 4 + 15) / 16 * 16;                       // [BATCH] bytes: local pose slot of each block of the batch (0xff: no block); 1 KB reserved
     static constexpr int poses = lcnt + 2 * 4 * 32 * 4;                    // [32] int
     static constexpr int misc = poses + 32 * 4;                            // [4] int
     static constexpr int bitmap = misc + 16;                               // [words] unsigned + [words] int
@@ -110,7 +117,7 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     int *wptr = (int *)(smraw + L::wptr);
     int *optr = (int *)(smraw + L::optr);
     int *pidPos = (int *)(smraw + L::pidPos);
-    int *lcnt = (int *)(smraw + L::lcnt);
+    unsigned char *slotB = smraw + L::lcnt;
     int *poses = (int *)(smraw + L::poses);
     int *misc = (int *)(smraw + L::misc);
     unsigned *bitmap = (unsigned *)(smraw + L::bitmap);
@@ -138,7 +145,6 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     }
     for (int i = tid; i < nfeat; i += TC_THREADS) pidPos[i] = 0x7fffffff;
     for (int i = tid; i < words; i += TC_THREADS) bitmap[i] = 0u;
-    for (int i = tid; i < 256; i += TC_THREADS) lcnt[i] = 0;
     if (tid < 9) {
         Cst[tid] = c.Q[tid]; Cst[9 + tid] = c.QA[tid]; Cst[18 + tid] = c.QB[tid]; Cst[27 + tid] = c.QG[tid];
     }
@@ -148,9 +154,8 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
         int p = M.photo[j];
         atomicOr(&bitmap[p >> 5], 1u << (p & 31));
         if (p == pid) {                         // position of the pos block inside its feature
-            int lo = 0, hi = nfeat;
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= j) lo = mid; else hi = mid; }
-            pidPos[lo] = j - wptr[lo];
+            const int fl = M.feature[j] - ch.f0;
+            pidPos[fl] = j - wptr[fl];
         }
     }
     if (tid < nfeat) O.wPtr[ch.f0 + tid] = optr[tid];
@@ -274,23 +279,23 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
         __syncthreads();
     }
 
-    double acc[TC_ACC];
+    // pose-sum accumulators (DMMA C fragments): cm = the warp's own eight element columns, cx = its block
+    // quarter of the last four columns; one pair per tile of eight local poses
+    double cm[4][2], cx[4][2];
 #pragma unroll
-    for (int u = 0; u < TC_ACC; u++) acc[u] = 0.0;
-    const int nitems = fast ? nposes * 36 : 0;
+    for (int u = 0; u < 4; u++) { cm[u][0] = cm[u][1] = cx[u][0] = cx[u][1] = 0.0; }
+    const int nMt = fast ? (nposes + 7) >> 3 : 0;
+    const int fg = lane >> 2, ft = lane & 3;                        // fragment row group / position in the group
+    // B fragment source of this lane: element column 8 warp + fg of the W | W T_f tiles (extra tile: 32 + fg)
+    const double *bMain = ((8 * warp + fg < 18) ? Wrt + (8 * warp + fg) : WTt + (8 * warp + fg - 18)) + TC_LD * 2 * ft;
+    const double *bExtra = WTt + (14 + (fg & 3)) + TC_LD * 2 * ft;
     const double *Wg = M.W;
 
     // ---------------- batches: one thread per W block ----------------
     // phase A for one block; FAST: chunk-local pose slots (lists, Jacobians from shared memory, W
     // through the warp's private part of the Wr tile), else global Jacobians / atomics
-    auto phase_a = [&](auto fast_tag, const int j, const int p, int *lc, const unsigned act) {
+    auto phase_a = [&](auto fast_tag, const int j, const int p, const int fb) {
         constexpr bool FAST = decltype(fast_tag)::value;
-        int fb;
-        {
-            int lo = 0, hi = nfeat;             // feature fb with wptr[fb] <= j < wptr[fb+1]
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= j) lo = mid; else hi = mid; }
-            fb = lo;
-        }
         const bool isPos = (p == pid);
         int slot = 0;
         if (FAST) slot = prefix[p >> 5] + __popc(bitmap[p >> 5] & ((1u << (p & 31)) - 1u));
@@ -364,27 +369,18 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
             row[6] = make_double2(B1[3], B1[4]); row[7] = make_double2(B1[5], B1[6]);
             row[8] = make_double2(B1[7], B1[8]);
         }
-        if (FAST) {
-            // which lanes of this warp hold a block of the same local pose (five ballots, slot < 32);
-            // the lowest of them publishes the mask.  The pose sums below walk the set bits in
-            // ascending order: an order that does not depend on the hardware's scheduling.
-            unsigned peers = act;
-#pragma unroll
-            for (int b = 0; b < 5; b++) {
-                const unsigned v = __ballot_sync(act, (slot >> b) & 1);
-                peers &= ((slot >> b) & 1) ? v : ~v;
-            }
-            if ((peers & ((1u << lane) - 1u)) == 0u) lc[slot * 4 + warp] = (int)peers;
-        }
+        if (FAST) slotB[tid] = (unsigned char)slot;                 // the pose sums select this block by its slot
     };
 
-    int bt = 0;
-    int pNext = (w0 + tid < w1) ? M.photo[w0 + tid] : 0;            // the block's pose, one batch ahead
-    for (int jb = w0; jb < w1; jb += TC_BATCH, bt++) {
+    int pNext = 0, fNext = 0;                                       // the block's pose / feature, one batch ahead
+    if (w0 + tid < w1) { pNext = M.photo[w0 + tid]; fNext = M.feature[w0 + tid]; }
+    for (int jb = w0; jb < w1; jb += TC_BATCH) {
         const int j = jb + tid;
-        const int pCur = pNext;
-        if (j + TC_BATCH < w1) pNext = M.photo[j + TC_BATCH];
-        int *lc = lcnt + (bt & 1) * 128;
+        const int pCur = pNext, fb = fNext - ch.f0;
+        if (j + TC_BATCH < w1) { pNext = M.photo[j + TC_BATCH]; fNext = M.feature[j + TC_BATCH]; }
+        const int jl = min(jb + TC_BATCH, w1) - 1;                  // last block of the batch
+        if (j == jb) misc[1] = fb;                                  // first / last feature of the batch
+        if (j == jl) misc[2] = fb;
         if (fast) {
             // the warp's 32 blocks = one contiguous 4.6 KB span: coalesced 16-byte async copies into
             // the warp's private part of the Wr tile; the next batch is pulled into L2 meanwhile
@@ -403,76 +399,99 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
             }
             cp_async_wait_all();
             __syncwarp();
-            const unsigned act = __ballot_sync(0xffffffffu, j < w1);
-            if (j < w1) phase_a(std::true_type(), j, pCur, lc, act);
+            if (j < w1) phase_a(std::true_type(), j, pCur, fb);
+            else {
+                // no block (last batch): no slot, and zero rows in the W / W T_f tiles (0 x stale bits
+                // must not turn into a NaN in the tensor-core sums)
+                slotB[tid] = 0xffu;
+                double2 *r0 = reinterpret_cast<double2 *>(Wrt + 18 * tid), *r1 = reinterpret_cast<double2 *>(WTt + 18 * tid);
+#pragma unroll
+                for (int i = 0; i < 9; i++) { r0[i] = make_double2(0.0, 0.0); r1[i] = make_double2(0.0, 0.0); }
+            }
         } else if (j < w1) {
-            phase_a(std::false_type(), j, pCur, lc, 0u);
+            phase_a(std::false_type(), j, pCur, fb);
         }
         __syncthreads();
-        lcnt[((bt & 1) ^ 1) * 128 + tid] = 0;                       // the next batch's counters
         // W'(pos,f) of the batch's features is a read-modify-write of global memory (the rows were
         // initialised by the prologue / earlier batches of THIS CTA): issue this thread's first two loads
         // now, the pose sums below hide their latency
-        const int jl = min(jb + TC_BATCH, w1) - 1;
-        int fLo, nfb;
-        {
-            int lo = 0, hi = nfeat;
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= jb) lo = mid; else hi = mid; }
-            fLo = lo;
-            hi = nfeat;
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (wptr[mid] <= jl) lo = mid; else hi = mid; }
-            nfb = lo - fLo + 1;
-        }
-        double oldw[2] = {0.0, 0.0};
+        const int fLo = misc[1], nfb = misc[2] - fLo + 1;
+        // (16-byte pieces: an item is a feature's element pair (2 el, 2 el + 1); rows are 144 bytes, aligned)
+        double2 oldw[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const int e = tid + u * TC_THREADS;
-            if (e < nfb * 18) {
-                const int fl = e / 18, el = e - 18 * fl;
-                oldw[u] = O.W[18 * (size_t)optr[fLo + fl] + el];
+            if (e < nfb * 9) {
+                const int fl = e / 9, el = e - 9 * fl;
+                oldw[u] = reinterpret_cast<const double2 *>(O.W + 18 * (size_t)optr[fLo + fl])[el];
             }
         }
-        // pose sums (thread owns (local pose, element) pairs for the whole chunk)
+        // pose sums: SW | SWT [slot][36] += Ind [slot][block] x (W | W T_f) [block][36] as m8n8k4 DMMAs.  A K step
+        // takes the blocks 8 i + {0,2,4,6} (+1 for the odd step) so that the B loads of a half warp fall into
+        // distinct banks; the summation order is fixed by the code (same bits every run).
+        if (nMt > 0) {
+            const int npair = (jl - jb + 8) >> 3;                   // pairs of K steps that hold a block
+            auto pair_step = [&](const int i, const double *bsrc, double (&c)[4][2], const bool bvalid) {
+                const uint2 sw = *reinterpret_cast<const uint2 *>(slotB + 8 * i);
+                const unsigned w = (ft & 2) ? sw.y : sw.x;
+                const int s0 = (int)((w >> (16 * (ft & 1))) & 0xffu), s1 = (int)((w >> (16 * (ft & 1) + 8)) & 0xffu);
+                const double b0 = bvalid ? bsrc[TC_LD * 8 * i] : 0.0, b1 = bvalid ? bsrc[TC_LD * (8 * i + 1)] : 0.0;
 #pragma unroll
-        for (int u = 0; u < TC_ACC; u++) {
-            const int it = tid + u * TC_THREADS;
-            if (it < nitems) {
-                const int slot = it / 36, el = it - 36 * slot;
-                const double *src = (el < 18) ? (Wrt + el) : (WTt + (el - 18));
-                // one chain per warp of the batch (four independent shared loads in flight), set bits in
-                // ascending order
-                const uint4 m4 = *reinterpret_cast<const uint4 *>(lc + slot * 4);
-                unsigned m0 = m4.x, m1 = m4.y, m2 = m4.z, m3 = m4.w;
-                double s0 = acc[u], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                while (m0 | m1 | m2 | m3) {
-                    if (m0) { s0 += src[TC_LD * (__ffs(m0) - 1)]; m0 &= m0 - 1; }
-                    if (m1) { s1 += src[TC_LD * (32 + __ffs(m1) - 1)]; m1 &= m1 - 1; }
-                    if (m2) { s2 += src[TC_LD * (64 + __ffs(m2) - 1)]; m2 &= m2 - 1; }
-                    if (m3) { s3 += src[TC_LD * (96 + __ffs(m3) - 1)]; m3 &= m3 - 1; }
-                }
-                const double s = (s0 + s1) + (s2 + s3);
-                acc[u] = s;
-            }
+                for (int mt = 0; mt < 4; mt++)
+                    if (mt < nMt) {
+                        dmma(c[mt][0], c[mt][1], (s0 == 8 * mt + fg) ? 1.0 : 0.0, b0);
+                        dmma(c[mt][0], c[mt][1], (s1 == 8 * mt + fg) ? 1.0 : 0.0, b1);
+                    }
+            };
+            for (int i = 0; i < npair; i++) pair_step(i, bMain, cm, true);
+            const int iq1 = min(npair, 4 * warp + 4);
+            for (int i = 4 * warp; i < iq1; i++) pair_step(i, bExtra, cx, fg < 4);
         }
         // W'(pos,f) += the feature's wadd rows of this batch
         {
             int u = 0;
-            for (int e = tid; e < nfb * 18; e += TC_THREADS, u++) {
-                const int fl = e / 18, el = e - 18 * fl;
+            for (int e = tid; e < nfb * 9; e += TC_THREADS, u++) {
+                const int fl = e / 9, el = e - 9 * fl;
                 const int fx = fLo + fl;
                 const int j0 = max(wptr[fx], jb) - jb, j1 = min(wptr[fx + 1], jl + 1) - jb;
-                double s = 0.0;
-                for (int b = j0; b < j1; b++) s += WAt[b * TC_LD + el];
-                double *dst = O.W + 18 * (size_t)optr[fx] + el;
-                *dst = (u == 0 ? oldw[0] : u == 1 ? oldw[1] : *dst) + s;
+                double s0 = 0.0, s1 = 0.0;
+                for (int b = j0; b < j1; b++) {
+                    const double2 v = reinterpret_cast<const double2 *>(WAt + b * TC_LD)[el];
+                    s0 += v.x; s1 += v.y;
+                }
+                double2 *dst = reinterpret_cast<double2 *>(O.W + 18 * (size_t)optr[fx]) + el;
+                const double2 o = (u == 0) ? oldw[0] : (u == 1) ? oldw[1] : *dst;
+                *dst = make_double2(o.x + s0, o.y + s1);
             }
         }
         __syncthreads();
     }
+    if (nMt > 0) {
+        // records [chunk][slot][36]: the warp's own columns straight from the fragments; the last four columns
+        // are the sum of the four warps' block quarters, added in warp order (scratch: the WA tile)
+        double *rec = chunkRec + 36 * 32 * (size_t)blockIdx.x;
+        double *scr = WAt;
 #pragma unroll
-    for (int u = 0; u < TC_ACC; u++) {
-        const int it = tid + u * TC_THREADS;
-        if (it < nitems) chunkRec[36 * 32 * (size_t)blockIdx.x + it] = acc[u];   // [chunk][slot][36]
+        for (int mt = 0; mt < 4; mt++)
+            if (mt < nMt) {
+                const int slot = 8 * mt + fg;
+                if (slot < nposes) {
+                    rec[36 * slot + 8 * warp + 2 * ft] = cm[mt][0];
+                    rec[36 * slot + 8 * warp + 2 * ft + 1] = cm[mt][1];
+                }
+                scr[((warp * 4 + mt) * 32 + lane) * 2] = cx[mt][0];
+                scr[((warp * 4 + mt) * 32 + lane) * 2 + 1] = cx[mt][1];
+            }
+        __syncthreads();
+        for (int it = tid; it < nMt * 64; it += TC_THREADS) {
+            const int mt = it >> 6, r = it & 63, ln = r >> 1, i = r & 1;
+            const int slot = 8 * mt + (ln >> 2), el = 32 + 2 * (ln & 3) + i;
+            if (slot < nposes && el < 36) {
+                double sum = scr[((0 * 4 + mt) * 32 + ln) * 2 + i];
+                for (int w = 1; w < 4; w++) sum += scr[((w * 4 + mt) * 32 + ln) * 2 + i];
+                rec[36 * slot + el] = sum;
+            }
+        }
     }
 }
 
