@@ -15,10 +15,12 @@
 //     A   nine 16-byte loads of the block (-> shared tile); T_f from d_f; W T_f -> shared tile; X = W Q;
 //         a1 -> its output slot directly (nine 16-byte stores); wadd -> shared tile;
 //         the block joins the batch list of its local pose
-//     B   pose sums SW / SWT on the FP64 tensor cores: [slot x block] indicator (from the batch's slot
-//         bytes) times the [block x 36] W | W T_f tiles, mma.sync m8n8k4 (DMMA); warp w owns element
-//         columns 8w..8w+7 for all 128 blocks, the last four columns are split by block quarter;
-//         accumulators stay in REGISTERS for the whole chunk;
+//     A'  pose sums of the WARP's 32 blocks on the FP64 tensor cores: [slot x block] indicator (slots
+//         exchanged by shuffles) times the [block x 36] W | W T_f rows of the warp, mma.sync m8n8k4 (DMMA),
+//         five independent column tiles per tile of eight local poses; the warp's partial sums replace
+//         its (consumed) W / W T_f rows in shared memory
+//     B   thread per (local pose, element): adds the four warps' partial sums, in warp order, to its
+//         accumulator (in REGISTERS for the whole chunk);
 //         thread per (feature, element pair): the feature's wadd rows of this batch -> W'(pos,f)
 // Two barriers per batch; W is read once from HBM and written once.  At the end the pose sums are
 // written as one record per (chunk, local pose) next to the chunk's pose bitmap; k_tf_posefin gathers
@@ -60,7 +62,7 @@ struct Layout {
     static constexpr int wptr = Cst + 36 * 8;                              // [FCH+4] int
     static constexpr int optr = wptr + (TC_FCH + 4) * 4;                   // [FCH+4] int
     static constexpr int pidPos = optr + (TC_FCH + 4) * 4;                 // [FCH] int
-    static constexpr int lcnt = (pidPos + TC_FCH * 4 + 15) / 16 * 16;                       // [BATCH] bytes: local pose slot of each block of the batch (0xff: no block); 1 KB reserved
+    static constexpr int lcnt = (pidPos + TC_FCH * 4 + 15) / 16 * 16;                       // (1 KB, unused)
     static constexpr int poses = lcnt + 2 * 4 * 32 * 4;                    // [32] int
     static constexpr int misc = poses + 32 * 4;                            // [4] int
     static constexpr int bitmap = misc + 16;                               // [words] unsigned + [words] int
@@ -117,7 +119,6 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     int *wptr = (int *)(smraw + L::wptr);
     int *optr = (int *)(smraw + L::optr);
     int *pidPos = (int *)(smraw + L::pidPos);
-    unsigned char *slotB = smraw + L::lcnt;
     int *poses = (int *)(smraw + L::poses);
     int *misc = (int *)(smraw + L::misc);
     unsigned *bitmap = (unsigned *)(smraw + L::bitmap);
@@ -150,12 +151,19 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
     }
     __syncthreads();
     const int w0 = wptr[0], w1 = wptr[nfeat];
-    for (int j = w0 + tid; j < w1; j += TC_THREADS) {
-        int p = M.photo[j];
-        atomicOr(&bitmap[p >> 5], 1u << (p & 31));
-        if (p == pid) {                         // position of the pos block inside its feature
-            const int fl = M.feature[j] - ch.f0;
-            pidPos[fl] = j - wptr[fl];
+    for (int j0 = w0 + tid; j0 < w1; j0 += 4 * TC_THREADS) {       // (four loads in flight per thread)
+        int pp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) pp[u] = (j0 + u * TC_THREADS < w1) ? M.photo[j0 + u * TC_THREADS] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int p = pp[u], j = j0 + u * TC_THREADS;
+            if (p < 0) continue;
+            atomicOr(&bitmap[p >> 5], 1u << (p & 31));
+            if (p == pid) {                     // position of the pos block inside its feature
+                const int fl = M.feature[j] - ch.f0;
+                pidPos[fl] = j - wptr[fl];
+            }
         }
     }
     if (tid < nfeat) O.wPtr[ch.f0 + tid] = optr[tid];
@@ -279,26 +287,23 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
         __syncthreads();
     }
 
-    // pose-sum accumulators (DMMA C fragments): cm = the warp's own eight element columns, cx = its block
-    // quarter of the last four columns; one pair per tile of eight local poses
-    double cm[4][2], cx[4][2];
+    double acc[TC_ACC];                                             // pose sums: thread owns (local pose, element) items
 #pragma unroll
-    for (int u = 0; u < 4; u++) { cm[u][0] = cm[u][1] = cx[u][0] = cx[u][1] = 0.0; }
-    const int nMt = fast ? (nposes + 7) >> 3 : 0;
+    for (int u = 0; u < TC_ACC; u++) acc[u] = 0.0;
+    const int nitems = fast ? nposes * 36 : 0;
+    const int nMt = fast ? (nposes + 7) >> 3 : 0;                   // tiles of eight local poses
     const int fg = lane >> 2, ft = lane & 3;                        // fragment row group / position in the group
-    // B fragment source of this lane: element column 8 warp + fg of the W | W T_f tiles (extra tile: 32 + fg)
-    const double *bMain = ((8 * warp + fg < 18) ? Wrt + (8 * warp + fg) : WTt + (8 * warp + fg - 18)) + TC_LD * 2 * ft;
-    const double *bExtra = WTt + (14 + (fg & 3)) + TC_LD * 2 * ft;
+    // the warp's partial pose sums [slot][36] of a batch live where its W / W T_f rows were: slots 0-15 in the
+    // W rows, 16-31 in the W T_f rows (32 x 18 doubles each)
+    double *stW = Wrt + 18 * 32 * warp, *stT = WTt + 18 * 32 * warp;
     const double *Wg = M.W;
 
     // ---------------- batches: one thread per W block ----------------
     // phase A for one block; FAST: chunk-local pose slots (lists, Jacobians from shared memory, W
     // through the warp's private part of the Wr tile), else global Jacobians / atomics
-    auto phase_a = [&](auto fast_tag, const int j, const int p, const int fb) {
+    auto phase_a = [&](auto fast_tag, const int j, const int p, const int fb, const int slot) {
         constexpr bool FAST = decltype(fast_tag)::value;
         const bool isPos = (p == pid);
-        int slot = 0;
-        if (FAST) slot = prefix[p >> 5] + __popc(bitmap[p >> 5] & ((1u << (p & 31)) - 1u));
         double W[18];
         {
             const double2 *src = FAST ? reinterpret_cast<const double2 *>(Wrt + 18 * tid)
@@ -369,7 +374,6 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
             row[6] = make_double2(B1[3], B1[4]); row[7] = make_double2(B1[5], B1[6]);
             row[8] = make_double2(B1[7], B1[8]);
         }
-        if (FAST) slotB[tid] = (unsigned char)slot;                 // the pose sums select this block by its slot
     };
 
     int pNext = 0, fNext = 0;                                       // the block's pose / feature, one batch ahead
@@ -399,17 +403,64 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
             }
             cp_async_wait_all();
             __syncwarp();
-            if (j < w1) phase_a(std::true_type(), j, pCur, fb);
-            else {
-                // no block (last batch): no slot, and zero rows in the W / W T_f tiles (0 x stale bits
-                // must not turn into a NaN in the tensor-core sums)
-                slotB[tid] = 0xffu;
+            int slot = 0xff;                                        // no block (last batch): no slot
+            if (j < w1) {
+                slot = prefix[pCur >> 5] + __popc(bitmap[pCur >> 5] & ((1u << (pCur & 31)) - 1u));
+                phase_a(std::true_type(), j, pCur, fb, slot);
+            } else {
+                // ... and zero rows in the W / W T_f tiles (0 x stale bits must not turn into a NaN in the
+                // tensor-core sums)
                 double2 *r0 = reinterpret_cast<double2 *>(Wrt + 18 * tid), *r1 = reinterpret_cast<double2 *>(WTt + 18 * tid);
 #pragma unroll
                 for (int i = 0; i < 9; i++) { r0[i] = make_double2(0.0, 0.0); r1[i] = make_double2(0.0, 0.0); }
             }
+            __syncwarp();
+            // pose sums of the warp's blocks: P [slot][36] = Ind [slot][block] x (W | W T_f) [block][36] as m8n8k4
+            // DMMAs.  A K step takes the warp's blocks 8 i + {0,2,4,6} (+1 for the odd step) so that the B loads of a
+            // half warp fall into distinct banks; the summation order is fixed by the code (same bits every run).
+            if (nv > 0) {
+                double c[4][5][2];
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 5; nt++) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+                const int npair = (nv + 7) >> 3;
+                for (int i = 0; i < npair; i++) {
+                    const int s0 = __shfl_sync(0xffffffffu, slot, 8 * i + 2 * ft);
+                    const int s1 = __shfl_sync(0xffffffffu, slot, 8 * i + 2 * ft + 1);
+                    double b0[5], b1[5];
+#pragma unroll
+                    for (int nt = 0; nt < 5; nt++) {
+                        const int el = 8 * nt + fg;
+                        const double *src = (el < 18 ? stW + el : stT + (el - 18)) + TC_LD * (8 * i + 2 * ft);
+                        const bool ok = (nt < 4) || (fg < 4);
+                        b0[nt] = ok ? src[0] : 0.0;
+                        b1[nt] = ok ? src[TC_LD] : 0.0;
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < 4; mt++)
+                        if (mt < nMt) {
+                            const double a0 = __hiloint2double((s0 == 8 * mt + fg) ? 0x3ff00000 : 0, 0);
+                            const double a1 = __hiloint2double((s1 == 8 * mt + fg) ? 0x3ff00000 : 0, 0);
+#pragma unroll
+                            for (int nt = 0; nt < 5; nt++) dmma(c[mt][nt][0], c[mt][nt][1], a0, b0[nt]);
+#pragma unroll
+                            for (int nt = 0; nt < 5; nt++) dmma(c[mt][nt][0], c[mt][nt][1], a1, b1[nt]);
+                        }
+                }
+                __syncwarp();                                       // every lane has read its operands
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+                    if (mt < nMt) {
+                        double *row = ((mt < 2) ? stW : stT) + 36 * (8 * (mt & 1) + fg) + 2 * ft;
+#pragma unroll
+                        for (int nt = 0; nt < 5; nt++)
+                            if (nt < 4 || ft < 2)
+                                *reinterpret_cast<double2 *>(row + 8 * nt) = make_double2(c[mt][nt][0], c[mt][nt][1]);
+                    }
+            }
         } else if (j < w1) {
-            phase_a(std::false_type(), j, pCur, fb);
+            phase_a(std::false_type(), j, pCur, fb, 0);
         }
         __syncthreads();
         // W'(pos,f) of the batch's features is a read-modify-write of global memory (the rows were
@@ -426,26 +477,20 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
                 oldw[u] = reinterpret_cast<const double2 *>(O.W + 18 * (size_t)optr[fLo + fl])[el];
             }
         }
-        // pose sums: SW | SWT [slot][36] += Ind [slot][block] x (W | W T_f) [block][36] as m8n8k4 DMMAs.  A K step
-        // takes the blocks 8 i + {0,2,4,6} (+1 for the odd step) so that the B loads of a half warp fall into
-        // distinct banks; the summation order is fixed by the code (same bits every run).
-        if (nMt > 0) {
-            const int npair = (jl - jb + 8) >> 3;                   // pairs of K steps that hold a block
-            auto pair_step = [&](const int i, const double *bsrc, double (&c)[4][2], const bool bvalid) {
-                const uint2 sw = *reinterpret_cast<const uint2 *>(slotB + 8 * i);
-                const unsigned w = (ft & 2) ? sw.y : sw.x;
-                const int s0 = (int)((w >> (16 * (ft & 1))) & 0xffu), s1 = (int)((w >> (16 * (ft & 1) + 8)) & 0xffu);
-                const double b0 = bvalid ? bsrc[TC_LD * 8 * i] : 0.0, b1 = bvalid ? bsrc[TC_LD * (8 * i + 1)] : 0.0;
+        // pose sums: the warps' partial sums, added in warp order
+        {
+            const int nwa = (jl - jb + 32) >> 5;                    // warps that held a block
 #pragma unroll
-                for (int mt = 0; mt < 4; mt++)
-                    if (mt < nMt) {
-                        dmma(c[mt][0], c[mt][1], (s0 == 8 * mt + fg) ? 1.0 : 0.0, b0);
-                        dmma(c[mt][0], c[mt][1], (s1 == 8 * mt + fg) ? 1.0 : 0.0, b1);
-                    }
-            };
-            for (int i = 0; i < npair; i++) pair_step(i, bMain, cm, true);
-            const int iq1 = min(npair, 4 * warp + 4);
-            for (int i = 4 * warp; i < iq1; i++) pair_step(i, bExtra, cx, fg < 4);
+            for (int u = 0; u < TC_ACC; u++) {
+                const int it = tid + u * TC_THREADS;
+                if (it < nitems) {
+                    const int slot = it / 36, el = it - 36 * slot;
+                    const double *src = ((slot < 16) ? Wrt : WTt) + 36 * (slot & 15) + el;
+                    double sum = acc[u];
+                    for (int w = 0; w < nwa; w++) sum += src[18 * 32 * w];
+                    acc[u] = sum;
+                }
+            }
         }
         // W'(pos,f) += the feature's wadd rows of this batch
         {
@@ -466,32 +511,10 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
         }
         __syncthreads();
     }
-    if (nMt > 0) {
-        // records [chunk][slot][36]: the warp's own columns straight from the fragments; the last four columns
-        // are the sum of the four warps' block quarters, added in warp order (scratch: the WA tile)
-        double *rec = chunkRec + 36 * 32 * (size_t)blockIdx.x;
-        double *scr = WAt;
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++)
-            if (mt < nMt) {
-                const int slot = 8 * mt + fg;
-                if (slot < nposes) {
-                    rec[36 * slot + 8 * warp + 2 * ft] = cm[mt][0];
-                    rec[36 * slot + 8 * warp + 2 * ft + 1] = cm[mt][1];
-                }
-                scr[((warp * 4 + mt) * 32 + lane) * 2] = cx[mt][0];
-                scr[((warp * 4 + mt) * 32 + lane) * 2 + 1] = cx[mt][1];
-            }
-        __syncthreads();
-        for (int it = tid; it < nMt * 64; it += TC_THREADS) {
-            const int mt = it >> 6, r = it & 63, ln = r >> 1, i = r & 1;
-            const int slot = 8 * mt + (ln >> 2), el = 32 + 2 * (ln & 3) + i;
-            if (slot < nposes && el < 36) {
-                double sum = scr[((0 * 4 + mt) * 32 + ln) * 2 + i];
-                for (int w = 1; w < 4; w++) sum += scr[((w * 4 + mt) * 32 + ln) * 2 + i];
-                rec[36 * slot + el] = sum;
-            }
-        }
+    for (int u = 0; u < TC_ACC; u++) {
+        const int it = tid + u * TC_THREADS;
+        if (it < nitems) chunkRec[36 * 32 * (size_t)blockIdx.x + it] = acc[u];   // [chunk][slot][36]
     }
 }
 
