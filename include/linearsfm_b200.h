@@ -144,6 +144,15 @@ int lsfm_tree_result_count(const lsfm_tree *tree);
 int lsfm_tree_result_shape(const lsfm_tree *tree, int idx, lsfm_map *shape_only);
 int lsfm_tree_download(const lsfm_tree *tree, int idx, lsfm_map *out);
 int lsfm_tree_download_state(const lsfm_tree *tree, int idx, int *stno, double *stVal);
+/* Marginal covariances of selected state blocks of a map (the reference frees the final
+ * information matrix unused, LinearSFMImp.cpp:2081-2096).  sel[i] in [0, m) selects pose block i, in
+ * [m, m + n) feature sel[i] - m; cov receives, in the order of sel, the row-major 6x6 (pose) or 3x3
+ * (feature) diagonal block of the inverse of the map's information matrix [[U, W], [W^T, V]]: 36 or 9
+ * doubles per selected block.  Every column is one unit right-hand side through the joint solver (Schur
+ * complement + multifrontal Cholesky + back-substitution), up to 48 columns per segmented batch.
+ * lsfm_tree_marginal_cov works on result `idx` of a solved tree without leaving HBM. */
+int lsfm_marginal_cov_stereo(const lsfm_map *map, int nsel, const int *sel, double *cov);
+int lsfm_tree_marginal_cov(const lsfm_tree *tree, int idx, int nsel, const int *sel, double *cov);
 /* Device-to-device hand-over of a whole map between ranks (multi-GPU tree levels): a map is
  * packed into / unpacked from ONE contiguous device buffer whose layout depends only on its shape
  * (m, n, nU, nW), so the buffer can be moved by NCCL send/recv or a peer copy as raw bytes.       */

@@ -41,7 +41,7 @@ EXPORTS = [
     "lsfm_tree_free", "lsfm_tree_last_solve_ms", "lsfm_tree_adopt_result", "lsfm_tree_append_maps",
     "lsfm_tree_reset", "lsfm_map_device_bytes", "lsfm_tree_export_device", "lsfm_tree_append_device",
     "lsfm_load_localmap_stereo", "lsfm_save_outputs", "lsfm_cli_main", "lsfm_build_localmaps_stereo", "lsfm_save_localmap",
-    "lsfm_pcg_block", "lsfm_solve_mono", "lsfm_save_cache", "lsfm_load_cache", "lsfm_free_cache",
+    "lsfm_pcg_block", "lsfm_marginal_cov_stereo", "lsfm_tree_marginal_cov", "lsfm_solve_mono", "lsfm_save_cache", "lsfm_load_cache", "lsfm_free_cache",
 ]
 
 _lib = None

@@ -161,6 +161,26 @@ def pcg_block(rowptr, colidx, S, E, tol=1e-13, max_iters=None):
     return x, it.value, rr.value
 
 
+def _cov_blocks(m, sel, flat):
+    out, o = [], 0
+    for b in sel:
+        d = 6 if b < m else 3
+        out.append(flat[o:o + d * d].reshape(d, d).copy())
+        o += d * d
+    return out
+
+
+def marginal_cov(lm: LocalMap, sel):
+    """Marginal covariance blocks (6x6 per pose index in [0, m), 3x3 per feature index m + f) of the inverse of the
+    map's information matrix, through the joint solver with unit right-hand sides (lsfm_marginal_cov_stereo)."""
+    sel = _c(sel, np.int32)
+    flat = np.zeros(int(sum(36 if b < lm.m else 9 for b in sel)))
+    c, _keep = to_c(lm)
+    check(lib().lsfm_marginal_cov_stereo(C.byref(c), C.c_int(len(sel)), sel.ctypes.data_as(_pi),
+                                         flat.ctypes.data_as(_pd)))
+    return _cov_blocks(lm.m, sel, flat)
+
+
 class Tree:
     """Leaf maps resident in HBM; `solve()` runs the merge tree on the device."""
 
@@ -229,6 +249,15 @@ class Tree:
         check(lib().lsfm_tree_download_state(self._h, C.c_int(idx), stno.ctypes.data_as(_pi),
                                              stVal.ctypes.data_as(_pd)))
         return stno, stVal
+
+    def marginal_cov(self, sel, idx: int = 0):
+        """Marginal covariance blocks of result `idx` (resident in HBM), see `marginal_cov`."""
+        m = self.result_shape(idx).m
+        sel = _c(sel, np.int32)
+        flat = np.zeros(int(sum(36 if b < m else 9 for b in sel)))
+        check(lib().lsfm_tree_marginal_cov(self._h, C.c_int(idx), C.c_int(len(sel)), sel.ctypes.data_as(_pi),
+                                           flat.ctypes.data_as(_pd)))
+        return _cov_blocks(m, sel, flat)
 
     def close(self):
         if self._h:

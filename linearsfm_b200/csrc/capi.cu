@@ -497,6 +497,106 @@ int lsfm_tree_download(const lsfm_tree *tree, int idx, lsfm_map *out)
     });
 }
 
+// ---------------------------------------------------------------------------------------------
+// Marginal covariances of selected state blocks (the reference frees the final
+// information matrix without using it, LinearSFMImp.cpp:2081-2096).  Sigma = I^-1 of the map's block
+// information matrix I = [[U, W], [W^T, V]]: column c of Sigma is the solution of I x = e_c, so the
+// d (6 or 3) unit right-hand sides of a selected block go through the joint solver of the merge tree
+// (per-feature 3x3 inversion, Schur complement, multifrontal Cholesky, back-substitution) as ONE
+// segmented batch whose K entries share the map's U / W / V arrays and differ in the right-hand
+// side and in the state buffers the solutions are written to.
+// ---------------------------------------------------------------------------------------------
+static __global__ void k_unit_rhs(double *eP, double *eF, const long long *pos, int K)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const long long q = pos[k];                    // >= 0: index into eP, < 0: -(index into eF) - 1
+    if (q >= 0) eP[q] = 1.0; else eF[-q - 1] = 1.0;
+}
+
+static __global__ void k_cov_gather(const double *xP, const double *xF, int m, int n, const int *colBlk,
+                                    const int *colOff, int K, double *out)
+{
+    // column k (unit vector `colOff[k]` of block colBlk[k]) -> the d entries of the block's own rows
+    int k = blockIdx.x, r = threadIdx.x;
+    if (k >= K) return;
+    const int b = colBlk[k];
+    const int d = b < m ? 6 : 3;
+    if (r >= d) return;
+    const double v = b < m ? xP[6 * (size_t)m * k + 6 * (size_t)b + r] : xF[3 * (size_t)n * k + 3 * (size_t)(b - m) + r];
+    out[(size_t)8 * k + r] = v;                    // 8 doubles per column (padded)
+}
+
+static void marginal_cov(Context &ctx, const MapHandle &h, int nsel, const int *sel, double *cov)
+{
+    const DMap &d = h.d;
+    const int m = d.m, n = d.n;
+    if (nsel < 0 || (nsel > 0 && (!sel || !cov))) throw LsfmError(LSFM_ERR_ARG, "marginal_cov: bad arguments");
+    struct Col { int blk, comp; size_t out; };
+    std::vector<Col> cols;
+    size_t off = 0;
+    for (int i = 0; i < nsel; i++) {
+        if (sel[i] < 0 || sel[i] >= m + n) throw LsfmError(LSFM_ERR_ARG, "marginal_cov: block index out of range");
+        const int dd = sel[i] < m ? 6 : 3;
+        for (int c = 0; c < dd; c++) cols.push_back({sel[i], c, off});
+        off += (size_t)dd * dd;
+    }
+    cudaStream_t s = ctx.stream;
+    // columns per batch: bounded by the K state buffers (8 (6 m + 3 n) K bytes) and by K copies of S
+    const size_t perCol = sizeof(double) * (6 * (size_t)m + 3 * (size_t)n) * 2;
+    const int KB = (int)std::max<size_t>(1, std::min<size_t>(48, ((size_t)1 << 30) / std::max<size_t>(perCol, 1)));
+    for (size_t c0 = 0; c0 < cols.size(); c0 += KB) {
+        const int K = (int)std::min<size_t>(KB, cols.size() - c0);
+        DevBuf<double> xP(6 * (size_t)m * K, s), xF(3 * (size_t)std::max(n, 1) * K, s);
+        DevBuf<double> eP(6 * (size_t)m * K, s), eF(3 * (size_t)std::max(n, 1) * K, s);
+        xP.zero(); xF.zero(); eP.zero(); eF.zero();
+        std::vector<DMap> maps(K, d);
+        std::vector<long long> pos(K);
+        std::vector<int> colBlk(K), colOff(K);
+        for (int k = 0; k < K; k++) {
+            const Col &c = cols[c0 + k];
+            maps[k].poseVal = xP.p + 6 * (size_t)m * k;
+            maps[k].featVal = xF.p + 3 * (size_t)n * k;
+            colBlk[k] = c.blk; colOff[k] = c.comp;
+            pos[k] = c.blk < m ? (long long)(6 * (size_t)m * k + 6 * (size_t)c.blk + c.comp)
+                               : -(long long)(3 * (size_t)n * k + 3 * (size_t)(c.blk - m) + c.comp) - 1;
+        }
+        OpMaps J;
+        J.build(maps, s);
+        DevBuf<long long> dPos(K, s);
+        DevBuf<int> dBlk(K, s), dOff(K, s);
+        dPos.upload(pos); dBlk.upload(colBlk); dOff.upload(colOff);
+        k_unit_rhs<<<ceil_div(K, 64), 64, 0, s>>>(eP.p, eF.p, dPos.p, K);
+        solve_stereo_batch(ctx, J, eP.p, eF.p, nullptr);
+        ctx.check_errors();
+        DevBuf<double> outD(8 * (size_t)K, s);
+        k_cov_gather<<<K, 8, 0, s>>>(xP.p, xF.p, m, n, dBlk.p, dOff.p, K, outD.p);
+        std::vector<double> outH = outD.to_host();
+        for (int k = 0; k < K; k++) {
+            const Col &c = cols[c0 + k];
+            const int dd = c.blk < m ? 6 : 3;
+            for (int r = 0; r < dd; r++) cov[c.out + (size_t)r * dd + c.comp] = outH[8 * (size_t)k + r];
+        }
+    }
+}
+
+int lsfm_marginal_cov_stereo(const lsfm_map *map, int nsel, const int *sel, double *cov)
+{
+    return guarded([&] {
+        if (!map) throw LsfmError(LSFM_ERR_ARG, "marginal_cov: null map");
+        std::vector<MapHandle> h = upload_maps(*g_ctx, map, 1, true);
+        marginal_cov(*g_ctx, h[0], nsel, sel, cov);
+    });
+}
+
+int lsfm_tree_marginal_cov(const lsfm_tree *tree, int idx, int nsel, const int *sel, double *cov)
+{
+    return guarded([&] {
+        if (!tree || idx < 0 || idx >= (int)tree->result.size()) throw LsfmError(LSFM_ERR_ARG, "bad result index");
+        marginal_cov(*g_ctx, tree->result[idx], nsel, sel, cov);
+    });
+}
+
 int lsfm_tree_download_state(const lsfm_tree *tree, int idx, int *stno, double *stVal)
 {
     return guarded([&] {

@@ -29,6 +29,7 @@ struct DevicePool {
         if (b < (1u << 26)) return (b + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
         return (b + (1u << 24) - 1) & ~(size_t)((1u << 24) - 1);
     }
+    long long misses = 0;                    // allocations that went to cudaMalloc (LSFM_DEBUG)
     void *alloc(size_t bytes)
     {
         size_t need = round_up(bytes ? bytes : 1);
@@ -44,6 +45,7 @@ struct DevicePool {
         void *p = nullptr;
         static const double limit_gb = getenv("LSFM_POOL_LIMIT_GB") ? atof(getenv("LSFM_POOL_LIMIT_GB")) : 0.0;
         cudaError_t e = cudaErrorMemoryAllocation;
+        misses++;
         if (limit_gb <= 0.0 || (double)(reserved + need) <= limit_gb * 1e9) e = cudaMalloc(&p, need);
         if (e != cudaSuccess) {
             // out of memory: drop the cache and retry once

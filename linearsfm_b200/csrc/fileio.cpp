@@ -346,7 +346,7 @@ void lsfm_free_cache(lsfm_map *maps, int num)
 
 int lsfm_cli_main(int argc, char **argv)
 {
-    std::string path, st, pose, feat, type, mapout, cache;
+    std::string path, st, pose, feat, type, mapout, cache, covout;
     int num = 0;
     bool hasPath = false, hasNum = false, hasType = false;
     for (int i = 1; i < argc; i++) {
@@ -362,6 +362,7 @@ int lsfm_cli_main(int argc, char **argv)
         else if (name == "f") arg(feat);
         else if (name == "map") arg(mapout);          // extension: the joined map (state + information) in localmap format
         else if (name == "cache") arg(cache);         // extension: binary cache of the parsed input maps
+        else if (name == "cov") arg(covout);          // extension: marginal pose covariances of the joined map
         else if (name == "num") { std::string v; arg(v); num = atoi(v.c_str()); hasNum = true; }
         else if (name == "type") {
             std::string v; arg(v);
@@ -455,6 +456,26 @@ int lsfm_cli_main(int argc, char **argv)
         if (lsfm_tree_download_state(tree, 0, out.stno, out.stVal) != LSFM_OK) {
             fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1;
         }
+    }
+    if (!covout.empty()) {
+        // -cov <file> (Stereo): 6x6 marginal covariance of at most 64 poses, evenly spaced, the last pose always
+        // among them; one line per pose: pose id, then the 36 entries row by row
+        const int mP = out.m, stride = std::max(1, (mP + 62) / 63);
+        std::vector<int> sel;
+        for (int p = 0; p < mP; p += stride) sel.push_back(p);
+        if (mP > 0 && sel.back() != mP - 1) sel.push_back(mP - 1);
+        std::vector<double> cv(36 * sel.size());
+        if (lsfm_tree_marginal_cov(tree, 0, (int)sel.size(), sel.data(), cv.data()) != LSFM_OK) {
+            fprintf(stderr, "LinearSFM (B200): %s\n", lsfm_last_error()); return 1;
+        }
+        FILE *fc = fopen(covout.c_str(), "w");
+        if (!fc) { fprintf(stderr, "LinearSFM (B200): cannot write %s\n", covout.c_str()); return 1; }
+        for (size_t i = 0; i < sel.size(); i++) {
+            fprintf(fc, "%d", -out.stno[6 * (size_t)sel[i]]);
+            for (int q = 0; q < 36; q++) fprintf(fc, " %.17g", cv[36 * i + q]);
+            fprintf(fc, "\n");
+        }
+        fclose(fc);
     }
     lsfm_tree_free(tree);
     // usage problems return 0 like the reference (LinearSFM.cpp:17); I/O and solve failures return 1

@@ -108,6 +108,8 @@ std::vector<MapHandle> solve_tree_stereo(Context &ctx, std::vector<MapHandle> le
         fprintf(stderr, "host work between a size read-back and the next launch (GPU idle): transform %.3f ms, join %.3f ms, pattern %.3f ms\n",
                 ctx.idle_ms[0], ctx.idle_ms[1], ctx.idle_ms[2]);
         ctx.idle_ms[0] = ctx.idle_ms[1] = ctx.idle_ms[2] = 0.0;
+        fprintf(stderr, "device pool: %lld cudaMalloc calls so far, %.1f MB reserved\n", DevicePool::get().misses,
+                DevicePool::get().reserved / 1e6);
     }
     return level;
 }

@@ -601,9 +601,12 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
     DevBuf<int> dSizes(2 * (size_t)K, s);
     k_sizes<<<ceil_div(K, TB), TB, 0, s>>>(A.dUPre.p, A.dFeatPre.p, K, uScan.p, fScan.p, dSizes.p, dSizes.p + K); nl++;
     std::vector<int> hPos(K), hSizes(2 * (size_t)K);
+    static const bool dbgT = getenv("LSFM_DEBUG_T") != nullptr;
+    auto tq0 = std::chrono::steady_clock::now();
     dPos.download(hPos.data(), K);
     dSizes.download(hSizes.data(), 2 * (size_t)K);
     CUDA_CHECK(cudaStreamSynchronize(s));
+    auto tq1 = std::chrono::steady_clock::now();
     ctx.idle_begin();
     KERNEL_CHECK();
 
@@ -620,13 +623,21 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
         o.nW = hSizes[K + k];
         bytes += map_bytes(A.h[k]);
     }
+    auto tq2 = std::chrono::steady_clock::now();
     std::vector<MapHandle> out = alloc_maps(ctx, shapes);
+    auto tq3 = std::chrono::steady_clock::now();
     for (int k = 0; k < K; k++) bytes += map_bytes(out[k].d);
     OpMaps B;
     B.build(out, s);
+    auto tq4 = std::chrono::steady_clock::now();
     DevBuf<TfConst> tc(K, s);
     DevBuf<PoseJac> pj(A.totPose, s);
     ctx.idle_end(0);
+    if (dbgT) {
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "[transform K=%d] wait %.0f us | shapes %.0f alloc_maps %.0f build %.0f tc/pj %.0f us\n", K, us(tq0, tq1),
+                us(tq1, tq2), us(tq2, tq3), us(tq3, tq4), us(tq4, std::chrono::steady_clock::now()));
+    }
     k_tf_const<<<ceil_div(K, 64), 64, 0, s>>>(A.d.p, B.d.p, A.dPosePre.p, K, dPos.p, dSizes.p + K, tc.p, pj.p); nl++;
     k_tf_pose<<<ceil_div(A.totPose, 128), 128, 0, s>>>(A.d.p, B.d.p, A.dPosePre.p, K, A.totPose, tc.p, pj.p); nl++;
     k_tf_uinit<<<ceil_div(A.totPose, TB), TB, 0, s>>>(B.d.p, A.dPosePre.p, K, A.totPose, dPos.p); nl++;

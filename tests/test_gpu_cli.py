@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from linearsfm_b200 import _lib, synth
-from linearsfm_b200.localmap import write_localmap
+from linearsfm_b200.localmap import read_localmap, write_localmap
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -99,3 +99,27 @@ def test_cli_binary_cache(gpu, tmp_path, typ, n):
                 os.remove(p)
     for k in ("p", "f", "st"):
         assert open(outs[0][k], "rb").read() == open(outs[1][k], "rb").read(), k
+
+
+def test_cli_pose_covariances(gpu, tmp_path):
+    # -cov <file> (extension): marginal 6x6 covariance of (at most 64 evenly spaced) poses of the
+    # joined map; checked against the dense inverse of the information matrix the same run writes with -map
+    import tempfile
+    n = 6
+    maps = synth.make_stereo_scene(n, 12, seed=41)
+    d = tempfile.mkdtemp(prefix="lsfm", dir="/tmp")
+    for i, lm in enumerate(maps):
+        write_localmap(os.path.join(d, f"localmap_{i + 1}.txt"), lm)
+    cov, mp = os.path.join(d, "cov.txt"), os.path.join(d, "joined.txt")
+    r = subprocess.run([_lib.CLI_PATH, "-path", d, "-num", str(n), "-type", "Stereo", "-cov", cov, "-map", mp],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    joined = read_localmap(mp)
+    Sigma = np.linalg.inv(joined.dense_information())
+    rows = np.loadtxt(cov, ndmin=2)
+    assert rows.shape == (joined.m, 37)
+    ids = list(joined.pose_ids())
+    for row in rows:
+        p = ids.index(int(row[0]))
+        ref = Sigma[6 * p:6 * p + 6, 6 * p:6 * p + 6]
+        assert np.max(np.abs(row[1:].reshape(6, 6) - ref)) <= 1e-6 * np.max(np.abs(ref))
