@@ -8,6 +8,7 @@
 // level are factorised by one segmented launch) instead of the chain a minimum-degree ordering
 // produces on the band+arrow structure of sequential map joining.
 #include "chol_symbolic.h"
+#include <functional>
 #include <algorithm>
 #include <thread>
 #include <stdexcept>
@@ -65,10 +66,20 @@ static bool nd_order_impl(int m, const int *ptr, const int *adj, std::vector<int
         size_t h = L.size() / 2;
         for (size_t i = 0; i < L.size(); i++) side[L[i]] = i < h ? 1 : 2;
         long long uncovered = 0;
-        for (int v : L) {
+        // cross edges: L is ascending, so A lies below mid = L[h] and B at or above it, and the adjacency
+        // lists are ascending -- only the neighbours inside [mid, L.back()] (for a vertex of A) or inside
+        // [L.front(), mid) (for a vertex of B) can be on the other side: two binary searches per vertex
+        // instead of a walk over the whole list (same counts, same ordering; 1.4 -> 0.4 ms at m = 3499)
+        const int lo = L.front(), mid = L[h], hi = L.back();
+        for (size_t i = 0; i < L.size(); i++) {
+            const int v = L[i];
+            const int *b = adj + ptr[v], *e = adj + ptr[v + 1];
             int c = 0;
-            char other = side[v] == 1 ? 2 : 1;
-            for (int p = ptr[v]; p < ptr[v + 1]; p++) c += (side[adj[p]] == other);
+            if (i < h) {
+                for (const int *q = std::lower_bound(b, e, mid); q < e && *q <= hi; ++q) c += (side[*q] == 2);
+            } else {
+                for (const int *q = std::lower_bound(b, e, lo); q < e && *q < mid; ++q) c += (side[*q] == 1);
+            }
             cnt[v] = c;
             uncovered += c;
         }
@@ -79,10 +90,12 @@ static bool nd_order_impl(int m, const int *ptr, const int *adj, std::vector<int
             int best = -1, bc = 0;
             for (int v : cand)
                 if (cnt[v] > bc) { bc = cnt[v]; best = v; }     // ascending scan: ties keep the smallest index
-            char other = side[best] == 1 ? 2 : 1;
-            for (int p = ptr[best]; p < ptr[best + 1]; p++) {
-                int w = adj[p];
-                if (side[w] == other) cnt[w]--;
+            {
+                const bool inA = side[best] == 1;
+                const char other = inA ? 2 : 1;
+                const int *b = adj + ptr[best], *e = adj + ptr[best + 1];
+                for (const int *q = std::lower_bound(b, e, inA ? mid : lo); q < e && (inA ? *q <= hi : *q < mid); ++q)
+                    if (side[*q] == other) cnt[*q]--;
             }
             uncovered -= bc;
             cnt[best] = 0;
@@ -303,6 +316,7 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
                     BatchSymbolic &out, int nthreads)
 {
     std::vector<JoinSym> js(K);
+    const int nthreads0 = std::min(nthreads, 8);
     nthreads = std::max(1, std::min(nthreads, K));
     long long work = (long long)nkeys;
     if (work < 20000) nthreads = 1;
@@ -331,20 +345,47 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
     for (int k = 0; k < K; k++) snBase[k + 1] = snBase[k] + (int)js[k].structs.size();
     int nsTot = snBase[K];
     out.sn.resize(nsTot);
+    // per-join offsets into the flat arrays (struct rows, children, fronts), so that the joins -- and below the
+    // key ranges of the slot map -- can be filled in by several host threads: the symbolic phase of the top tree
+    // levels (K = 1..3 joins of thousands of poses) is longer than the GPU work it overlaps with
+    std::vector<long long> soK(K + 1, 0), coK(K + 1, 0), foK(K + 1, 0);
     int maxLevel = 0;
-    long long structTot = 0, childTot = 0;
-    for (int k = 0; k < K; k++)
-        for (size_t s = 0; s < js[k].structs.size(); s++) {
-            structTot += (long long)js[k].structs[s].size();
-            childTot += (long long)js[k].children[s].size();
-            maxLevel = std::max(maxLevel, js[k].level[s]);
-        }
-    out.structIdx.resize(structTot);
-    out.relIdx.assign(structTot, -1);
-    out.childIdx.resize(childTot);
-    long long so = 0, co = 0, fo = 0;
     for (int k = 0; k < K; k++) {
+        long long so = soK[k], co = coK[k], fo = foK[k];
+        for (size_t s = 0; s < js[k].structs.size(); s++) {
+            so += (long long)js[k].structs[s].size();
+            co += (long long)js[k].children[s].size();
+            maxLevel = std::max(maxLevel, js[k].level[s]);
+            const long long fs = 6 * (long long)((js[k].nodes[s + 1] - js[k].nodes[s]) + (long long)js[k].structs[s].size());
+            fo += (fs + 1) * fs;
+            fo = (fo + 1) & ~1ll;
+        }
+        soK[k + 1] = so; coK[k + 1] = co; foK[k + 1] = fo;
+    }
+    out.structIdx.resize(soK[K]);
+    out.relIdx.assign(soK[K], -1);
+    out.childIdx.resize(coK[K]);
+    const long long fo = foK[K];
+    std::vector<double> flopsK(K, 0.0);
+    std::vector<int> maxFdimK(K, 0);
+    // tasks: run fn(0..n-1) on up to `nthreads` threads (static interleave); exceptions are re-thrown
+    const int poolThreads = std::max(1, nthreads0);
+    auto parallel_for = [&](int n, bool big, const std::function<void(int)> &fn) {
+        const int T = big ? std::min(poolThreads, n) : 1;
+        if (T <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+        std::vector<std::string> er(T);
+        auto w = [&](int tid) {
+            try { for (int i = tid; i < n; i += T) fn(i); } catch (const std::exception &e) { er[tid] = e.what(); }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(w, t);
+        w(0);
+        for (auto &t : th) t.join();
+        for (auto &e : er) if (!e.empty()) throw std::runtime_error(e);
+    };
+    auto fill_join = [&](int k) {
         JoinSym &J = js[k];
+        long long so = soK[k], co = coK[k], fo = foK[k];
         int ns = (int)J.structs.size();
         for (int s = 0; s < ns; s++) {
             SnodeDesc &d = out.sn[snBase[k] + s];
@@ -366,9 +407,9 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
             d.frontOff = fo;
             fo += (fs + 1) * fs;
             fo = (fo + 1) & ~1ll;
-            out.maxFdim = std::max(out.maxFdim, (int)fdim);
+            maxFdimK[k] = std::max(maxFdimK[k], (int)fdim);
             double nc = 6.0 * d.ncols, nr = 6.0 * d.nstruct;
-            for (int q = 0; q < 6 * d.ncols; q++) { double c = (nc - q) + nr; out.flops += c * c; }
+            for (int q = 0; q < 6 * d.ncols; q++) { double c = (nc - q) + nr; flopsK[k] += c * c; }
         }
         // relative indices of every supernode's struct inside its parent's front
         for (int s = 0; s < ns; s++) {
@@ -396,8 +437,20 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
             out.poseLcol[posePre[k] + J.perm[c]] = c - J.nodes[s];
             out.perm[posePre[k] + c] = J.perm[c];
         }
-        // S slot -> front block
-        for (int i = sOff[k]; i < sOff[k + 1]; i++) {
+    };
+    parallel_for(K, work >= 20000, fill_join);
+    for (int k = 0; k < K; k++) { out.maxFdim = std::max(out.maxFdim, maxFdimK[k]); out.flops += flopsK[k]; }
+    // S slot -> front block: pieces of at most SLOT_PIECE keys of one join
+    const int SLOT_PIECE = 8192;
+    struct Piece { int k, i0, i1; };
+    std::vector<Piece> pieces;
+    for (int k = 0; k < K; k++)
+        for (int i = sOff[k]; i < sOff[k + 1]; i += SLOT_PIECE) pieces.push_back({k, i, std::min(sOff[k + 1], i + SLOT_PIECE)});
+    auto fill_slots = [&](int pi) {
+        const Piece &P = pieces[pi];
+        const int k = P.k;
+        const JoinSym &J = js[k];
+        for (int i = P.i0; i < P.i1; i++) {
             int a = (int)((keys[i] >> 22) & M22), b = (int)(keys[i] & M22);
             int pa = J.iperm[a], pb = J.iperm[b];
             int c = std::min(pa, pb), r = std::max(pa, pb);
@@ -419,7 +472,8 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
             // 2474-2481); the front keeps the lower triangle, so take it from the transposed block
             if (a == b) sm.transpose = 1;
         }
-    }
+    };
+    parallel_for((int)pieces.size(), work >= 20000, fill_slots);
     out.frontDoubles = fo;
     // level sets
     out.levelPtr.assign(maxLevel + 2, 0);
