@@ -56,7 +56,8 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
             unsigned *__restrict__ bm, const int *__restrict__ bmOff,
             int *__restrict__ maxNposes, int pat_cmax, int *__restrict__ chunkInfo,
             int *__restrict__ blkInfo, const int *__restrict__ wPre,
-            unsigned *__restrict__ patBits, int bitsStride, unsigned long long *__restrict__ pairFeat)
+            unsigned *__restrict__ patBits, int bitsStride, unsigned long long *__restrict__ pairFeat,
+            const int *__restrict__ posePre, int *__restrict__ poseCR)
 {
     extern __shared__ unsigned smu[];
     const FeatChunk ch = chunks[blockIdx.x];
@@ -140,7 +141,16 @@ k_pat_chunk(const DMap *__restrict__ J, const FeatChunk *__restrict__ chunks,
         for (int i = tid; i < words; i += nt) {
             unsigned b = bitmap[i];
             int r = prefix[i];
-            while (b) { int bit = __ffs(b) - 1; poses[r] = i * 32 + bit; ci[r] = i * 32 + bit; r++; b &= b - 1; }
+            while (b) {
+                int bit = __ffs(b) - 1;
+                poses[r] = i * 32 + bit; ci[r] = i * 32 + bit; r++;
+                // range of chunks that will hold an E record of the pose (running maxima over zeroed memory):
+                // k_e_gather walks only those
+                int *cr = poseCR + 2 * (size_t)(posePre[ch.k] + i * 32 + bit);
+                atomicMax(cr, 0x7fffffff - (int)blockIdx.x);
+                atomicMax(cr + 1, (int)blockIdx.x + 1);
+                b &= b - 1;
+            }
         }
         __syncthreads();
         // the chunk's pair bitmap stays behind for the Schur kernel ([32..47])
@@ -497,7 +507,7 @@ __global__ void k_s_convert(const u64 *__restrict__ keys, int nuis, const int *_
 __global__ void __launch_bounds__(128)
 k_e_gather(const int *__restrict__ posePre, int K, int totP, const int *__restrict__ chunkPre,
            const unsigned *__restrict__ patBits, int bitsStride, const double *__restrict__ Erec,
-           double *__restrict__ E)
+           double *__restrict__ E, const int *__restrict__ poseCR)
 {
     const int lane = threadIdx.x & 31;
     const int gp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -507,7 +517,14 @@ k_e_gather(const int *__restrict__ posePre, int K, int totP, const int *__restri
     const int pw = p >> 5;
     const unsigned pbit = 1u << (p & 31);
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int c = chunkPre[k] + lane; c < chunkPre[k + 1]; c += 32) {
+    // only the chunks between the first and the last one with a record of the pose; the start is rounded down to
+    // a multiple of 32 chunks, so every chunk keeps its lane and the sums their order
+    int cbeg = chunkPre[k], cend = chunkPre[k];
+    {
+        const int vmin = poseCR[2 * (size_t)gp], vmax = poseCR[2 * (size_t)gp + 1];
+        if (vmax > 0) { cbeg += ((0x7fffffff - vmin) - cbeg) & ~31; cend = vmax; }
+    }
+    for (int c = cbeg + lane; c < cend; c += 32) {
         const unsigned *gb = patBits + (size_t)c * 2 * bitsStride;
         const unsigned w = gb[pw];
         if (w & pbit) {
@@ -1081,15 +1098,19 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
     dBmOff.upload(bmOff);
     DevBuf<unsigned> bm((size_t)std::max(bmOff[K], 1), s);
     bm.zero();
+    DevBuf<int> poseCR(2 * (size_t)std::max(J.totPose, 1), s);   // per pose: first / last chunk that records it
+    poseCR.zero();
     auto pattern_chunk_pass = [&]() {
         if (nChunks == 0) return;
         size_t shb = sizeof(int) * (2 * (size_t)maxWords + 16 + PAT_CMAX + 1 + 4 + 32);
         if (shb > 48 * 1024)
             CUDA_CHECK(cudaFuncSetAttribute(k_pat_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb));
         dMaxNp.zero();
+        poseCR.zero();
         k_pat_chunk<<<nChunks, PAT_THREADS, shb, s>>>(J.d.p, dChunks.p, bm.p, dBmOff.p, dMaxNp.p, pat_cmax_used,
                                                       chunkInfo.p, blkInfo.p, J.dWPre.p, patBits.p, bitsStride,
-                                                      ctx.timing ? (unsigned long long *)(dMaxNp.p + 2) : nullptr); nl++;
+                                                      ctx.timing ? (unsigned long long *)(dMaxNp.p + 2) : nullptr,
+                                                      J.dPosePre.p, poseCR.p); nl++;
     };
     pattern_chunk_pass();
     if (gauge) {   // mono: the zero pose has no block at all after the join; keep every diagonal
@@ -1281,7 +1302,7 @@ void solve_stereo_batch(Context &ctx, const OpMaps &J, const double *eP, const d
             k_s_convert<<<ceil_div(36ll * nuis, TB), TB, 0, s>>>(keys.p, nuis, J.dPosePre.p, sexp.p, Sfx.p, S.p); nl++;
             if (anySlow) { k_e_convert<<<ceil_div(6ll * J.totPose, TB), TB, 0, s>>>(6 * J.totPose, eexp.p, ecnt.p, Efx.p, E.p); nl++; }
             k_e_gather<<<ceil_div(32ll * J.totPose, 128), 128, 0, s>>>(J.dPosePre.p, K, J.totPose, dChunkPre.p, patBits.p,
-                                                                    bitsStride, Erec.p, E.p); nl++;
+                                                                    bitsStride, Erec.p, E.p, poseCR.p); nl++;
         }
     }
     KERNEL_CHECK();

@@ -329,7 +329,7 @@ k_tf_posefin(const int *__restrict__ posePre, int K, int totPose,
              const int *__restrict__ chunkPre, const unsigned *__restrict__ chunkBits, int bitsStride,
              const double *__restrict__ chunkRec, const double *__restrict__ poseAccSlow,
              int *__restrict__ rkey, double *__restrict__ rval, int none,
-             int *__restrict__ ppKey, double *__restrict__ ppVal)
+             int *__restrict__ ppKey, double *__restrict__ ppVal, const int *__restrict__ poseCR)
 {
     const int lane = threadIdx.x & 31;
     const int gp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -341,7 +341,14 @@ k_tf_posefin(const int *__restrict__ posePre, int K, int totPose,
     double acc[36];
 #pragma unroll
     for (int q = 0; q < 36; q++) acc[q] = 0.0;
-    for (int c = chunkPre[k] + lane; c < chunkPre[k + 1]; c += 32) {
+    // only the chunks between the first and the last one that recorded the pose (k_tf_chunk's running maxima);
+    // the start is rounded down to a multiple of 32 chunks: every chunk keeps its lane, the sums keep their order
+    int cbeg = chunkPre[k], cend = chunkPre[k];
+    {
+        const int vmin = poseCR[2 * (size_t)gp], vmax = poseCR[2 * (size_t)gp + 1];
+        if (vmax > 0) { cbeg += ((0x7fffffff - vmin) - cbeg) & ~31; cend = vmax; }
+    }
+    for (int c = cbeg + lane; c < cend; c += 32) {
         const unsigned *gb = chunkBits + (size_t)c * 2 * bitsStride;
         const unsigned w = gb[pw];
         if (w & pbit) {
@@ -686,8 +693,10 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
     DevBuf<unsigned> chunkBits(2 * (size_t)bitsStride * std::max(nChunks, 1), s);
     DevBuf<double> chunkRec(36 * 32 * (size_t)std::max(nChunks, 1), s);
     DevBuf<double> poseAcc(36 * (size_t)A.totPose, s);      // slow-path (chunk overflow) sums only
+    DevBuf<int> poseCR(2 * (size_t)std::max(A.totPose, 1), s);   // per pose: first / last chunk with a record of it
     dChunkPre.upload(chunkPre);
     poseAcc.zero();
+    poseCR.zero();
     // Chunks with more than TC_CMAX distinct poses can only occur in maps whose join already had to split
     // chunks (landmarks seen by more than 30 poses stay in overflowing chunks): only then the slow path's
     // fixed-point bookkeeping is set up (k_tf_slow_pre).
@@ -718,7 +727,7 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
         tfc::k_tf_chunk<<<nChunks, tfc::TC_THREADS, shb, s>>>(A.d.p, B.d.p, dChunks.p, A.dFeatPre.p, A.dPosePre.p,
                                                             tc.p, pj.p, fScan.p, pexp.p, pcnt.p, poseFx.p, cmaxUse,
                                                             chunkBits.p, bitsStride, chunkRec.p, ppKey.p + ppC,
-                                                            ppVal.p + 36 * ppC);
+                                                            ppVal.p + 36 * ppC, poseCR.p);
         {
             double wvBytes = 0.0;
             for (int k = 0; k < K; k++)
@@ -735,7 +744,7 @@ std::vector<MapHandle> transform_stereo_batch(Context &ctx, const std::vector<Ma
     k_tf_posefin<<<ceil_div(32ll * A.totPose, 128), 128, 0, s>>>(A.dPosePre.p, K, A.totPose, tc.p, pj.p, dChunkPre.p,
                                                               chunkBits.p, bitsStride, chunkRec.p, poseAcc.p,
                                                               rkey.p + recP, rval.p + 36 * recP, none,
-                                                              ppKey.p + ppP, ppVal.p + 36 * ppP); nl++;
+                                                              ppKey.p + ppP, ppVal.p + 36 * ppP, poseCR.p); nl++;
     {
         det::Sorted srt;
         nl += det::sort_records(ctx, rkey.p, (int)nrec, none, srt);

@@ -106,7 +106,7 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
            const TfConst *__restrict__ tc, const PoseJac *__restrict__ pj, const int *__restrict__ fScan,
            const int *__restrict__ pexp, const int *__restrict__ pcnt, long long *__restrict__ poseFx, int cmaxUse,
            unsigned *__restrict__ chunkBits, int bitsStride, double *__restrict__ chunkRec,
-           int *__restrict__ ppKey, double *__restrict__ ppVal)
+           int *__restrict__ ppKey, double *__restrict__ ppVal, int *__restrict__ poseCR)
 {
     typedef Layout L;
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -199,7 +199,16 @@ k_tf_chunk(const DMap *__restrict__ in, DMap *__restrict__ out, const Chunk *__r
         for (int i = tid; i < words; i += TC_THREADS) {
             unsigned b = bitmap[i];
             int r = prefix[i];
-            while (b) { int bit = __ffs(b) - 1; poses[r++] = i * 32 + bit; b &= b - 1; }
+            while (b) {
+                int bit = __ffs(b) - 1;
+                poses[r++] = i * 32 + bit;
+                // range of chunks that hold a record of the pose (both as running maxima over zeroed memory):
+                // k_tf_posefin walks only those
+                int *cr = poseCR + 2 * (size_t)(posePre[k] + i * 32 + bit);
+                atomicMax(cr, 0x7fffffff - (int)blockIdx.x);
+                atomicMax(cr + 1, (int)blockIdx.x + 1);
+                b &= b - 1;
+            }
         }
     double Q[9];
 #pragma unroll
