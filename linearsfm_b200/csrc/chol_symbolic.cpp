@@ -232,6 +232,12 @@ namespace {
 
 struct JoinSym {
     int m = 0;
+    // m <= 32 (the thousands of joins of the lower tree levels): identity ordering, one dense supernode without
+    // struct rows, children or parent.  Nothing is stored for such a join -- build_symbolic writes its
+    // descriptor, pose entries and slots directly (a tree level of 1,749 two-pose joins took 0.64 ms of
+    // vector allocations, longer than the Schur kernel it is meant to hide behind)
+    bool small = false;
+    int nsn() const { return small ? 1 : (int)structs.size(); }
     std::vector<int> perm, iperm, nodes, snOf;
     std::vector<std::vector<int>> structs, children;
     std::vector<int> parent, level;
@@ -243,19 +249,7 @@ const u64 M22 = (1ull << 22) - 1;
 void analyse_join(int m, const u64 *keys, int nk, JoinSym &J)
 {
     J.m = m;
-    if (m <= 32) {
-        // small joins (the thousands of joins of the lower tree levels): identity ordering, one
-        // dense supernode -- no graph needs to be built
-        J.perm.resize(m); J.iperm.resize(m);
-        for (int i = 0; i < m; i++) { J.perm[i] = i; J.iperm[i] = i; }
-        J.nodes = {0, m};
-        J.snOf.assign(m, 0);
-        J.structs.assign(1, {});
-        J.children.assign(1, {});
-        J.parent.assign(1, -1);
-        J.level.assign(1, 0);
-        return;
-    }
+    if (m <= 32) { J.small = true; return; }
     // symmetric adjacency without self loops
     std::vector<int> ptr(m + 1, 0);
     for (int i = 0; i < nk; i++) {
@@ -318,7 +312,9 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
     std::vector<JoinSym> js(K);
     const int nthreads0 = std::min(nthreads, 8);
     nthreads = std::max(1, std::min(nthreads, K));
-    long long work = (long long)nkeys;
+    // threads pay only for joins that need a graph (m > 32); the rest is a few nanoseconds per key
+    long long work = 0;
+    for (int k = 0; k < K; k++) if (m[k] > 32) work += sOff[k + 1] - sOff[k];
     if (work < 20000) nthreads = 1;
     std::vector<std::string> errs(nthreads);
     auto worker = [&](int tid) {
@@ -342,7 +338,7 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
     out.perm.assign(totPose, 0);
     out.slot.resize(nkeys);
     std::vector<int> snBase(K + 1, 0);
-    for (int k = 0; k < K; k++) snBase[k + 1] = snBase[k] + (int)js[k].structs.size();
+    for (int k = 0; k < K; k++) snBase[k + 1] = snBase[k] + js[k].nsn();
     int nsTot = snBase[K];
     out.sn.resize(nsTot);
     // per-join offsets into the flat arrays (struct rows, children, fronts), so that the joins -- and below the
@@ -352,6 +348,11 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
     int maxLevel = 0;
     for (int k = 0; k < K; k++) {
         long long so = soK[k], co = coK[k], fo = foK[k];
+        if (js[k].small) {
+            const long long fs = 6 * (long long)js[k].m;
+            fo += (fs + 1) * fs;
+            fo = (fo + 1) & ~1ll;
+        }
         for (size_t s = 0; s < js[k].structs.size(); s++) {
             so += (long long)js[k].structs[s].size();
             co += (long long)js[k].children[s].size();
@@ -386,6 +387,29 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
     auto fill_join = [&](int k) {
         JoinSym &J = js[k];
         long long so = soK[k], co = coK[k], fo = foK[k];
+        if (J.small) {
+            SnodeDesc &d = out.sn[snBase[k]];
+            d.join = k;
+            d.first = 0;
+            d.ncols = J.m;
+            d.structOff = (int)so;
+            d.nstruct = 0;
+            d.parent = -1;
+            d.childOff = (int)co;
+            d.nchild = 0;
+            d.poseOff = posePre[k];
+            d.level = 0;
+            d.frontOff = fo;
+            maxFdimK[k] = J.m;
+            const double nc = 6.0 * J.m;
+            for (int q = 0; q < 6 * J.m; q++) { double c = nc - q; flopsK[k] += c * c; }
+            for (int c = 0; c < J.m; c++) {
+                out.poseSn[posePre[k] + c] = snBase[k];
+                out.poseLcol[posePre[k] + c] = c;
+                out.perm[posePre[k] + c] = c;
+            }
+            return;
+        }
         int ns = (int)J.structs.size();
         for (int s = 0; s < ns; s++) {
             SnodeDesc &d = out.sn[snBase[k] + s];
@@ -450,6 +474,18 @@ void build_symbolic(int K, const std::vector<int> &m, const std::vector<int> &po
         const Piece &P = pieces[pi];
         const int k = P.k;
         const JoinSym &J = js[k];
+        if (J.small) {
+            // identity ordering, one front: S(a, b) with a <= b is the front's block (row b, col a), transposed
+            for (int i = P.i0; i < P.i1; i++) {
+                SlotMap &sm = out.slot[i];
+                sm.sn = snBase[k];
+                sm.lcol = (int)((keys[i] >> 22) & M22);
+                sm.lrow = (int)(keys[i] & M22);
+                sm.pad = 0;
+                sm.transpose = 1;
+            }
+            return;
+        }
         for (int i = P.i0; i < P.i1; i++) {
             int a = (int)((keys[i] >> 22) & M22), b = (int)(keys[i] & M22);
             int pa = J.iperm[a], pb = J.iperm[b];
