@@ -18,6 +18,8 @@
 #include <chrono>
 #include <algorithm>
 
+#include "fast_num.h"
+
 void lsfm_set_error(const std::string &msg);          // capi.cu: the string lsfm_last_error() returns
 
 namespace {
@@ -32,10 +34,12 @@ struct IoErr {
 struct Tok {
     char *p, *end;
     bool fail = false;
+    // fastnum::parse_long / parse_double return exactly what strtol / strtod return (fast_num.h), about three
+    // times faster on the 15-17 digit numbers of a localmap file
     long next_int()
     {
         char *q;
-        long v = strtol(p, &q, 10);
+        long v = fastnum::parse_long(p, &q);
         if (q == p) fail = true;
         p = q;
         return v;
@@ -43,7 +47,7 @@ struct Tok {
     double next_dbl()
     {
         char *q;
-        double v = strtod(p, &q);
+        double v = fastnum::parse_double(p, &q);
         if (q == p) fail = true;
         p = q;
         return v;
