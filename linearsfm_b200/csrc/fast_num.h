@@ -13,6 +13,7 @@
 // tests/helpers/fast_num_check.cpp compares both routines with strtod / strtol on random and edge-case inputs.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -99,6 +100,53 @@ static inline double parse_double(const char *p, char **end)
     } else return strtod(p, end);
     *end = const_cast<char *>(s);
     return neg ? -v : v;
+}
+
+// ---- output: the bytes of printf("%lf") = "%.6f" and of "%d" (the reference's writers, LinearSFMImp.cpp:2113,
+// 7946, 7959) ----
+// |v| = m * 2^-s exactly (m < 2^53), so |v| * 10^6 = (m * 10^6) / 2^s is an exact rational with a 73-bit numerator:
+// the shift with round-half-to-even on the exact remainder is what glibc's exact printf produces.  Values of 2^43 and
+// above, infinities and NaNs go to snprintf.  Returns the number of characters written (no terminator).
+static inline int put_uint(char *buf, unsigned long long x)
+{
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + x % 10); x /= 10; } while (x);
+    for (int i = 0; i < n; i++) buf[i] = tmp[n - 1 - i];
+    return n;
+}
+
+static inline int put_int(char *buf, int x)
+{
+    if (x < 0) { buf[0] = '-'; return 1 + put_uint(buf + 1, (unsigned long long)(-(long long)x)); }
+    return put_uint(buf, (unsigned long long)x);
+}
+
+static inline int put_f6(char *buf, size_t cap, double v)
+{
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    const bool neg = (u >> 63) != 0;
+    const int be = (int)((u >> 52) & 0x7ff);
+    uint64_t m = u & ((1ull << 52) - 1);
+    if (be == 0x7ff || be >= 1023 + 43) return snprintf(buf, cap, "%lf", v);       // inf / nan / |v| >= 2^43
+    int s;                                           // |v| = m * 2^-s
+    if (be == 0) s = 1074; else { m |= 1ull << 52; s = 1075 - be; }
+    const unsigned __int128 P = (unsigned __int128)m * 1000000u;                   // < 2^73
+    uint64_t q;
+    if (s >= 100) q = 0;                             // |v| * 10^6 < 2^-27: rounds to zero
+    else {
+        q = (uint64_t)(P >> s);
+        const unsigned __int128 rem = P & ((((unsigned __int128)1) << s) - 1), half = ((unsigned __int128)1) << (s - 1);
+        if (rem > half || (rem == half && (q & 1))) q++;
+    }
+    int n = 0;
+    if (neg) buf[n++] = '-';
+    n += put_uint(buf + n, q / 1000000u);
+    buf[n++] = '.';
+    unsigned f = (unsigned)(q % 1000000u);
+    for (int i = 5; i >= 0; i--) { buf[n + i] = (char)('0' + f % 10); f /= 10; }
+    return n + 6;
 }
 
 } // namespace fastnum

@@ -216,7 +216,12 @@ int lsfm_save_outputs(const lsfm_map *M, const char *st, const char *pose, const
     };
     if (st) {
         int rc = write_rows(st, (size_t)M->r, [&](size_t i, char *buf, size_t cap) {
-            return snprintf(buf, cap, "%d %lf\n", M->stno[i], M->stVal[i]);
+            // "%d %lf\n" (fastnum::put_*: the same bytes as printf, tests/test_fast_num.py)
+            int n = fastnum::put_int(buf, M->stno[i]);
+            buf[n++] = ' ';
+            n += fastnum::put_f6(buf + n, cap - n, M->stVal[i]);
+            buf[n++] = '\n';
+            return n;
         });
         if (rc != LSFM_OK) { printf("Please Input Path to Save Final State Vector!"); return rc; }
     }
@@ -241,14 +246,30 @@ int lsfm_save_outputs(const lsfm_map *M, const char *st, const char *pose, const
     if (pose) {
         int rc = write_rows(pose, poseIdx.size(), [&](size_t k, char *buf, size_t cap) {
             const double *x = M->stVal + poseIdx[k].second;
-            return snprintf(buf, cap, "%d  %lf  %lf  %lf %lf  %lf  %lf\n", poseIdx[k].first, x[0], x[1], x[2], x[3], x[4], x[5]);
+            // "%d  %lf  %lf  %lf %lf  %lf  %lf\n"
+            int n = fastnum::put_int(buf, poseIdx[k].first);
+            for (int q = 0; q < 6; q++) {
+                buf[n++] = ' ';
+                if (q != 3) buf[n++] = ' ';
+                n += fastnum::put_f6(buf + n, cap - n, x[q]);
+            }
+            buf[n++] = '\n';
+            return n;
         });
         if (rc != LSFM_OK) return rc;
     }
     if (feat) {
         int rc = write_rows(feat, featIdx.size(), [&](size_t k, char *buf, size_t cap) {
             const double *x = M->stVal + featIdx[k].second;
-            return snprintf(buf, cap, "%d  %lf  %lf %lf\n", featIdx[k].first, x[0], x[1], x[2]);
+            // "%d  %lf  %lf %lf\n"
+            int n = fastnum::put_int(buf, featIdx[k].first);
+            for (int q = 0; q < 3; q++) {
+                buf[n++] = ' ';
+                if (q != 2) buf[n++] = ' ';
+                n += fastnum::put_f6(buf + n, cap - n, x[q]);
+            }
+            buf[n++] = '\n';
+            return n;
         });
         if (rc != LSFM_OK) return rc;
     }

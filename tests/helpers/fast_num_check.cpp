@@ -1,5 +1,5 @@
-// Fuzz / edge-case check of linearsfm_b200/csrc/fast_num.h against strtod / strtol: the value BITS and the end
-// pointer must be identical for every input.   fast_num_check <seed> <cases>   ->  "mismatches N"
+// Fuzz / edge-case check of linearsfm_b200/csrc/fast_num.h against strtod / strtol (the value BITS and the end
+// pointer must be identical for every input) and of its writers against printf("%lf") / printf("%d") (same bytes).   fast_num_check <seed> <cases>   ->  "mismatches N"
 #include "fast_num.h"
 #include <cstdio>
 #include <cmath>
@@ -86,6 +86,35 @@ int main(int argc, char **argv)
         check(buf);
         snprintf(buf, sizeof buf, "%llue-3", lo);
         check(buf);
+    }
+    // ---- writers: put_f6 / put_int must produce the bytes of printf("%lf") / printf("%d") ----
+    auto chk_f6 = [&](double v) {
+        char a[400], b[400];
+        const int la = snprintf(a, sizeof a, "%lf", v), lb = fastnum::put_f6(b, sizeof b, v);
+        if (la != lb || memcmp(a, b, la)) { if (bad < 20) { b[lb] = 0; printf("MISMATCH %%lf of %.17g: '%s' vs '%s'\n", v, a, b); } bad++; }
+    };
+    const double fedge[] = {0.0, -0.0, 1.0, -1.0, 0.5e-6, 1.5e-6, 2.5e-6, 0.9999995, 0.99999949999999, 1e-7, 4.9e-324, -4.9e-324,
+        2.2e-308, 123456.7890125, 123456.7890135, 8796093022207.999, 8796093022208.0, 8796093022208.5, 1e13, 1e15, 1e22, 1e300,
+        -1e300, INFINITY, -INFINITY, NAN, 0.1, 0.2, 0.3, 999999.9999995, 999999.9999994999, 1e-6, 5e-7, 4.999999999999999e-7,
+        5.000000000000001e-7, -5e-7, -4.9e-7};
+    for (double v : fedge) chk_f6(v);
+    for (long long i = 0; i < cases; i++) {
+        double v;
+        const int k = (int)(rng() % 6);
+        if (k == 0) { uint64_t u = rng(); memcpy(&v, &u, 8); }
+        else if (k == 1) v = ((double)(rng() >> 11) / 9007199254740992.0 * 2 - 1) * pow(10.0, (int)(rng() % 30) - 15);
+        else if (k == 2) v = (double)(long long)(rng() % 4000001 - 2000000) / (double)(1ull << (rng() % 30));      // exact binary fractions: true ties
+        else if (k == 3) v = (double)(long long)(rng() % 2000001 - 1000000) * 1e-6 + ((int)(rng() % 3) - 1) * 5e-7;
+        else if (k == 4) v = ((double)(rng() >> 11) / 9007199254740992.0 * 2 - 1) * 1000.0;
+        else v = ldexp((double)(rng() >> 11), -(int)(rng() % 120));
+        chk_f6(v);
+    }
+    for (long long i = 0; i < cases / 10 + 10; i++) {
+        static const int iedge[10] = {0, 1, -1, 2147483647, -2147483647 - 1, 10, -10, 99, 100, -100};
+        const int x = i < 10 ? iedge[i] : (int)rng();
+        char a[32], b[32];
+        const int la = snprintf(a, 32, "%d", x), lb = fastnum::put_int(b, x);
+        if (la != lb || memcmp(a, b, la)) { if (bad < 20) printf("MISMATCH %%d of %d\n", x); bad++; }
     }
     printf("mismatches %lld\n", bad);
     return bad != 0;
