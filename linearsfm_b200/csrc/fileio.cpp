@@ -155,14 +155,41 @@ int lsfm_save_localmap(const lsfm_map *M, const char *path, int mono)
     setvbuf(fp, buf.data(), _IOFBF, buf.size());
     if (mono) fprintf(fp, "%d %d %d %d\n%d\n", M->Ref, M->ScaP, M->Fix, M->Sign, M->r);
     else fprintf(fp, "%d\n%d\n", M->Ref, M->r);
-    for (int i = 0; i < M->r; i++) fprintf(fp, "%d %.17g\n", M->stno[i], M->stVal[i]);
+    // The joined map of the NC3500-size scene is 112 M doubles of W alone (2.4 GB of text): the elements are
+    // formatted by several host threads, a wave of 4 M elements at a time (same conversions, same bytes as one
+    // fprintf per element), and written in order.
+    auto elems = [&](size_t cnt, const std::function<int(size_t, char *)> &fmt) {
+        const size_t WAVE = (size_t)1 << 22;
+        int nth = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+        if (cnt < 50000) nth = 1;
+        std::vector<std::string> chunks(nth);
+        for (size_t w0 = 0; w0 < cnt; w0 += WAVE) {
+            const size_t w1 = std::min(cnt, w0 + WAVE), per = (w1 - w0 + nth - 1) / nth;
+            auto work = [&](int t) {
+                const size_t a0 = std::min(w1, w0 + per * t), a1 = std::min(w1, a0 + per);
+                std::string &out = chunks[t];
+                out.clear();
+                out.reserve((a1 - a0) * 26);
+                char tmp[64];                      // "%d %.17g\n": at most 11 + 1 + 24 + 1 characters
+                for (size_t i = a0; i < a1; i++) out.append(tmp, (size_t)fmt(i, tmp));
+            };
+            if (nth == 1) work(0);
+            else {
+                std::vector<std::thread> th;
+                for (int t = 0; t < nth; t++) th.emplace_back(work, t);
+                for (auto &t : th) t.join();
+            }
+            for (auto &c : chunks) fwrite(c.data(), 1, c.size(), fp);
+        }
+    };
+    elems((size_t)M->r, [&](size_t i, char *o) { return snprintf(o, 64, "%d %.17g\n", M->stno[i], M->stVal[i]); });
     fprintf(fp, "%d %d\n%d\n", M->m, M->n, M->nU);
-    auto doubles = [&](const double *x, size_t cnt, int per_line) {
-        for (size_t i = 0; i < cnt; i++) fprintf(fp, "%.17g%c", x[i], ((i + 1) % per_line == 0 || i + 1 == cnt) ? '\n' : ' ');
+    auto doubles = [&](const double *x, size_t cnt, size_t per_line) {
+        elems(cnt, [&](size_t i, char *o) { return snprintf(o, 64, "%.17g%c", x[i], ((i + 1) % per_line == 0 || i + 1 == cnt) ? '\n' : ' '); });
         if (cnt == 0) fputc('\n', fp);
     };
     auto ints = [&](const int *x, size_t cnt) {
-        for (size_t i = 0; i < cnt; i++) fprintf(fp, "%d%c", x[i], (i + 1 == cnt) ? '\n' : ' ');
+        elems(cnt, [&](size_t i, char *o) { int n = fastnum::put_int(o, x[i]); o[n++] = (i + 1 == cnt) ? '\n' : ' '; return n; });
         if (cnt == 0) fputc('\n', fp);
     };
     doubles(M->U, 36 * (size_t)M->nU, 6);

@@ -79,6 +79,40 @@ def test_localmap_writer_is_read_back_by_the_reference(oracle, tmp_path):
     assert _lib.lib().lsfm_save_localmap(C.byref(c), str(tmp_path / "no_dir" / "x.txt").encode(), C.c_int(0)) == 5
 
 
+def test_localmap_writer_parallel_path(oracle, tmp_path):
+    # above 50,000 elements per array lsfm_save_localmap formats on several host threads, a wave at a time:
+    # the file is what one fprintf("%.17g") per element would write (Python's "%.17g" is the same conversion),
+    # and the reference's reader gets every number back bit for bit (values across 16 decades, negative zero)
+    from linearsfm_b200.localmap import LocalMap
+    m, n, nW = 40, 6000, 9000
+    rng = np.random.default_rng(3)
+    stno = np.concatenate([np.repeat(-np.arange(2, m + 2), 6), np.repeat(np.arange(n) + 1, 3)]).astype(np.int32)
+    W = rng.normal(size=(nW, 6, 3)) * 10.0 ** rng.integers(-8, 8, (nW, 1, 1))
+    W[5, 0, 0] = -0.0
+    feature = np.sort(rng.integers(0, n, nW)).astype(np.int32)
+    FBlock = np.full(n, -1, np.int32)
+    first = np.flatnonzero(np.r_[True, feature[1:] != feature[:-1]])
+    FBlock[feature[first]] = first
+    lm = LocalMap(Ref=3, stno=stno, stVal=rng.normal(0, 50, 6 * m + 3 * n), m=m, n=n, U=rng.normal(size=(m, 6, 6)),
+                  Ui=np.arange(m), Uj=np.arange(m), W=W, photo=rng.integers(0, m, nW), feature=feature,
+                  V=rng.normal(size=(n, 3, 3)), FBlock=FBlock)
+    p = str(tmp_path / "big.txt")
+    c, keep = api.to_c(lm)
+    _lib.check(_lib.lib().lsfm_save_localmap(C.byref(c), p.encode(), C.c_int(0)))
+    assert_maps_match(oracle.load_localmap_stereo(p), lm, tol_state=0, tol_info=0, what="reference reads the big localmap file")
+
+    def rows(x, per):
+        x = np.asarray(x, np.float64).reshape(-1)
+        return "".join("%.17g%s" % (v, "\n" if (i + 1) % per == 0 or i + 1 == x.size else " ") for i, v in enumerate(x))
+
+    def ints(x):
+        return " ".join(str(int(v)) for v in x) + "\n"
+    want = "%d\n%d\n" % (lm.Ref, lm.r) + "".join("%d %.17g\n" % (a, v) for a, v in zip(lm.stno, lm.stVal))
+    want += "%d %d\n%d\n" % (m, n, m) + rows(lm.U, 6) + ints(lm.Ui) + ints(lm.Uj) + "%d\n" % nW + rows(lm.W, 3)
+    want += ints(lm.photo) + ints(lm.feature) + rows(lm.V, 3) + ints(lm.FBlock)
+    assert open(p).read() == want
+
+
 def test_parallel_writers_byte_identical_on_a_large_map(oracle, tmp_path):
     # the multi-threaded formatting path (>= 20000 rows) against the reference's fprintf loops: same bytes,
     # including a repeated landmark id (the last occurrence wins, std::map semantics of 7907/7925),
